@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- GJK pair-queries/sec on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A "step" is one pass of the batched GJK hot path over one batch of synthetic
+pairs.  Default workload = BASELINE.json configs[1]: 1 M random convex-hull
+pairs, 8-64 vertices, fp64 (per GPU; weak scaling, each rank owns its own
+contiguous slice of pairs, no data-path collective).
+
+Printed JSON line (rank 0):
+  value      whole-job pairs/s with inputs resident in HBM (CUDA events on the
+             launching stream, barrier + synchronize on both sides, max over ranks)
+  e2e        same metric through the host-buffer C-ABI call (ogjk_gjk_host_*):
+             pinned host inputs -> H2D -> kernels -> D2H of distances + gkSimplex
+  roofline   dominant kernel vs the measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline  the reference scalar library (oracle/_ref) or the oracle port on
+             the box's host cores, bounded sample
+`--impl reference` times the reference CPU implementation alone.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from opengjk_b200 import workloads as W  # noqa: E402
+
+L2_BYTES = 126e6
+
+WORKLOADS = {
+    # name: (description, dtype, maker(npairs, seed), default pairs per GPU)
+    "hulls64_f64": ("config2: random convex-hull pairs, 8-64 vertices, fp64", np.float64,
+                    lambda n, seed: W.mixed_hulls(n, 8, 64, seed, np.float64), 1_000_000),
+    "hulls64_f32": ("config2 in fp32: random convex-hull pairs, 8-64 vertices", np.float32,
+                    lambda n, seed: W.mixed_hulls(n, 8, 64, seed, np.float32), 1_000_000),
+    "boxes_f32": ("config3: oriented box-box (8-vertex) pairs, fp32", np.float32,
+                  lambda n, seed: W.boxes(n, True, seed, dtype=np.float32), 8_000_000),
+    "boxes_aligned_f32": ("config3a: axis-aligned unit cubes (tie stress), fp32", np.float32,
+                          lambda n, seed: W.boxes(n, False, seed, dtype=np.float32), 8_000_000),
+    "hulls1k_f32": ("config4a: indexed pairs of 1000-vertex hulls, fp32", np.float32,
+                    lambda n, seed: W.large_hull_pool(n, 32768, 1000, 1000, seed, dtype=np.float32), 200_000),
+    "hulls1k10k_f32": ("config4: indexed pairs of 1k-10k-vertex hulls, fp32", np.float32,
+                       lambda n, seed: W.large_hull_pool(n, 2048, 1000, 10000, seed, dtype=np.float32), 50_000),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_baseline(w, prec, budget_s=12.0):
+    """Reference scalar library (or the oracle port) on all host cores, bounded sample."""
+    from oracle.pyoracle import Oracle, Reference
+    cores = os.cpu_count() or 1
+    n = min(w.npairs, 100_000)
+    if Reference.available(prec):
+        kind, ref = "reference", Reference(prec)
+        prep = Reference.Prepared(ref, w.coords, w.off, w.cnt, w.pa[:n], w.pb[:n])
+        run = lambda: prep.run(cores)
+    else:
+        kind, o = "port", Oracle(prec)
+        run = lambda: o.batch(w.coords, w.off, w.cnt, w.pa[:n], w.pb[:n], nthreads=cores)
+    run()  # warm
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        run()
+        reps += 1
+        if time.perf_counter() - t0 > budget_s or reps >= 200:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": n * reps / dt, "unit": "pairs/s", "cores": cores, "kind": kind,
+            "sample": f"first {n} pairs of the workload x {reps} passes ({dt:.1f} s), OpenMP split over pairs"}
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's own CPU implementation, rank 0 only."""
+    if rank != 0:
+        return
+    desc, dt, maker, default_pairs = WORKLOADS[args.workload]
+    prec = "f64" if dt == np.float64 else "f32"
+    from oracle.pyoracle import Oracle, Reference
+    cores = os.cpu_count() or 1
+    n = min(args.pairs or default_pairs, args.ref_sample)
+    w = maker(n, args.seed)
+    if Reference.available(prec):
+        kind, ref = "reference", Reference(prec)
+        prep = Reference.Prepared(ref, w.coords, w.off, w.cnt, w.pa, w.pb)
+        run = lambda: prep.run(cores)
+    else:
+        kind, o = "port", Oracle(prec)
+        run = lambda: o.batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=cores)
+    for _ in range(args.warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    dt_s = time.perf_counter() - t0
+    v = n * args.steps / dt_s
+    line = {
+        "impl": "reference", "metric": "gjk_pair_queries_per_sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt_s / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": prec, "data": "synthetic",
+        "config": {"workload": desc, "pairs_per_step": n, "note": "CPU reference, bounded sample of the workload"},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind,
+                         "sample": f"{n} pairs per step, all host threads (OpenMP static split over pairs)"},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="hulls64_f64", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (default: the workload's full size)")
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-sample", type=int, default=200_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extra", default="", help="comma list of further workloads reported under other_workloads")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from opengjk_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng = api.Engine(local_rank)
+    hbm_peak, peak_src = peaks()
+
+    def measure(name, pairs, steps, warmup, with_cpu):
+        desc, dt, maker, default_pairs = WORKLOADS[name]
+        prec = "f64" if dt == np.float64 else "f32"
+        n = pairs or default_pairs
+        w = maker(n, args.seed + rank)  # each rank owns its own slice of the job
+        sdt = api.SIMPLEX_F64 if prec == "f64" else api.SIMPLEX_F32
+
+        # ---- pinned host copies (e2e inputs) and device-resident copies (value) ----
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        h_coords, h_off, h_cnt, h_pa, h_pb = pin(w.coords.reshape(-1)), pin(w.off), pin(w.cnt), pin(w.pa), pin(w.pb)
+        h_dist = torch.empty(n, dtype=h_coords.dtype).pin_memory()
+        h_simp = torch.empty(n * sdt.itemsize, dtype=torch.uint8).pin_memory()
+        d_coords, d_off, d_cnt, d_pa, d_pb = (t.to(dev) for t in (h_coords, h_off, h_cnt, h_pa, h_pb))
+        d_dist = torch.empty(n, dtype=h_coords.dtype, device=dev)
+        d_simp = torch.empty(n * sdt.itemsize, dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        in_bytes = sum(t.numel() * t.element_size() for t in (h_coords, h_off, h_cnt, h_pa, h_pb))
+        out_bytes = h_dist.numel() * h_dist.element_size() + h_simp.numel()
+
+        def step():
+            eng.gjk_device(prec, n, d_coords, d_off, d_cnt, d_pa, d_coords, d_off, d_cnt, d_pb, d_simp, d_dist,
+                           api.MODE_AUTO, stream)
+
+        # ---- device-resident timing -------------------------------------------------
+        eng.set_timing(False)
+        for _ in range(warmup):
+            step()
+        barrier()
+        launches0 = eng.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clk:
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            barrier()
+        ms = e0.elapsed_time(e1)
+        launches = eng.launch_count - launches0
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_max = float(t.item())
+        value = n * world * steps / (ms_max * 1e-3)
+
+        # ---- dominant-kernel duration (events around each launch, same stream) ------
+        eng.set_timing(True)
+        per = {"classify": [], "thread": [], "warp": []}
+        for _ in range(max(3, min(steps, 10))):
+            step()
+            torch.cuda.synchronize()
+            lt = eng.last_timing()
+            for k in per:
+                per[k].append(lt[k])
+        eng.set_timing(False)
+        kavg = {k: float(np.mean(v)) for k, v in per.items()}
+        dom = max(("thread", "warp"), key=lambda k: kavg[k])
+        alg_bytes = w.algorithmic_bytes()
+        achieved = alg_bytes / (kavg[dom] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": None, "kernel": f"gjk_{dom}_kernel<{'double' if prec == 'f64' else 'float'}>",
+                    "kernel_ms": kavg[dom], "step_kernels_ms": kavg, "algorithmic_bytes_per_launch": alg_bytes,
+                    "peak_source": peak_src}
+
+        # ---- end to end through the host-buffer C-ABI call --------------------------
+        o = (h_dist.numpy(), h_simp.numpy().view(sdt))
+        hc, ho, hk, ha, hb = (t.numpy() for t in (h_coords, h_off, h_cnt, h_pa, h_pb))
+        e2e_steps = max(2, min(steps, 5))
+        eng.gjk_host(hc, ho, hk, ha, hb, True, o)  # warm (allocates staging)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.gjk_host(hc, ho, hk, ha, hb, True, o)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": n * world * e2e_steps / float(t.item()), "unit": "pairs/s", "h2d_bytes_per_step": in_bytes,
+               "d2h_bytes_per_step": out_bytes, "steps": e2e_steps,
+               "api": f"ogjk_gjk_host_{prec} (pinned host buffers in, distances + gkSimplex out)"}
+
+        # quick self-check on a sample against the oracle (checker only, outside any timed region)
+        res = {"workload": desc, "value": value, "ms_per_step": ms_max / steps, "launches": launches, "roofline": roofline,
+               "e2e": e2e, "clocks": clk.summary(), "prec": prec, "pairs_per_gpu": n,
+               "input_bytes_per_gpu": in_bytes}
+        if with_cpu and rank == 0:
+            res["cpu_baseline"] = cpu_baseline(w, prec)
+            from oracle.pyoracle import Oracle
+            m = min(n, 20000)
+            dref, sref = Oracle(prec).batch(w.coords, w.off, w.cnt, w.pa[:m], w.pb[:m], nthreads=os.cpu_count() or 1)
+            got_d = d_dist[:m].cpu().numpy()
+            res["sample_parity"] = {"pairs": m, "distance_bits_equal": bool(got_d.tobytes() == dref.tobytes()),
+                                    "simplex_bytes_equal": bool(
+                                        d_simp[:m * sdt.itemsize].cpu().numpy().tobytes() == sref.tobytes())}
+        del d_coords, d_simp, d_dist
+        torch.cuda.empty_cache()
+        return res
+
+    main_res = measure(args.workload, args.pairs, args.steps, args.warmup, not args.no_cpu_baseline)
+    others = {}
+    for name in [x for x in args.extra.split(",") if x]:
+        r = measure(name, 0, max(3, args.steps // 2), 3, not args.no_cpu_baseline)
+        others[name] = {k: r[k] for k in ("workload", "value", "ms_per_step", "roofline", "e2e", "prec", "pairs_per_gpu")
+                        if k in r}
+        if "cpu_baseline" in r:
+            others[name]["cpu_baseline"] = r["cpu_baseline"]
+            others[name]["sample_parity"] = r.get("sample_parity")
+
+    if rank == 0:
+        line = {
+            "metric": "gjk_pair_queries_per_sec", "value": main_res["value"], "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": main_res["prec"], "data": "synthetic",
+            "config": {"workload": main_res["workload"], "pairs_per_gpu": main_res["pairs_per_gpu"],
+                       "sharding": "contiguous pair slice per rank, no data-path collective",
+                       "l2": (f"inputs {main_res['input_bytes_per_gpu'] / 1e6:.0f} MB per GPU "
+                              + ("> 126 MB L2 (no flush needed)" if main_res["input_bytes_per_gpu"] > L2_BYTES
+                                 else "< L2: numbers are L2-warm")),
+                       "kernel_mode": "auto (classify + thread-per-pair + warp-per-pair)"},
+            "roofline": main_res["roofline"], "e2e": main_res["e2e"], "gpu_launches": main_res["launches"],
+            "clocks": main_res["clocks"],
+        }
+        if "cpu_baseline" in main_res:
+            line["cpu_baseline"] = main_res["cpu_baseline"]
+            line["sample_parity"] = main_res["sample_parity"]
+        if others:
+            line["other_workloads"] = others
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

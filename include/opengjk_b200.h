@@ -1,0 +1,136 @@
+/*
+ * opengjk_b200.h -- C ABI of the B200-native batch GJK(+EPA) engine.
+ *
+ * Plain C, no CUDA or C++ types in any signature.  This is the drop-in
+ * boundary for the reference's batched collision-query path; each entry point
+ * cites the reference interface it replaces (paths under /root/reference).
+ * Both precisions live in one shared library under _f32 / _f64 suffixes (the
+ * reference selects one at build time with USE_32BITS,
+ * scalar/include/openGJK/openGJK.h:54-60; the reference-named flavour
+ * libraries in include/openGJK/ re-export the unsuffixed names).
+ *
+ * Data model ("polytope pool" + "pair list"):
+ *   coords : xyz-interleaved vertices of all polytopes of a pool, contiguous
+ *            per polytope -- the reference's flattened `coord` blocks
+ *            (gpu/include/openGJK_GPU.h:71-76) laid end to end, exactly what
+ *            its allocate_and_copy_device_arrays builds (gpu/opengjk_gpu.cu:3105-3166)
+ *   off    : first vertex (not byte, not float) of each polytope, int64
+ *   cnt    : vertex count of each polytope (gkPolytope.numpoints)
+ *   idx    : per pair, which polytope of the pool is body 1 / body 2
+ *            (gkCollisionPair, openGJK_GPU.h:89-92); NULL means "pair p uses
+ *            polytope p" (the reference's parallel bd1[]/bd2[] arrays)
+ *
+ * All functions return 0 on success or a negative ogjk_status; the message is
+ * available from ogjk_last_error() (thread local).  There is no CPU fallback:
+ * without a CUDA device every compute entry point fails with OGJK_ERR_CUDA.
+ */
+#ifndef OPENGJK_B200_H_
+#define OPENGJK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define OGJK_API __attribute__((visibility("default")))
+#else
+#define OGJK_API
+#endif
+
+typedef enum ogjk_status_ {
+  OGJK_OK = 0,
+  OGJK_ERR_ARG = -1,   /* bad argument (NULL pointer, negative count, ...) */
+  OGJK_ERR_CUDA = -2,  /* CUDA runtime error or no device */
+  OGJK_ERR_ALLOC = -3  /* host or device allocation failed */
+} ogjk_status;
+
+/* Layout-identical to the reference structs (offsets verified in SURVEY.md 8):
+ * fp32 gkPolytope 32 B, gkSimplex 108 B; fp64 gkPolytope 48 B, gkSimplex 184 B. */
+typedef struct ogjk_polytope_f32_ { int numpoints; float s[3]; int s_idx; float* coord; } ogjk_polytope_f32;
+typedef struct ogjk_polytope_f64_ { int numpoints; double s[3]; int s_idx; double* coord; } ogjk_polytope_f64;
+typedef struct ogjk_simplex_f32_ { int nvrtx; float vrtx[4][3]; int vrtx_idx[4][2]; float witnesses[2][3]; } ogjk_simplex_f32;
+typedef struct ogjk_simplex_f64_ { int nvrtx; double vrtx[4][3]; int vrtx_idx[4][2]; double witnesses[2][3]; } ogjk_simplex_f64;
+typedef struct ogjk_pair_ { int idx1; int idx2; } ogjk_pair; /* gkCollisionPair */
+
+typedef struct ogjk_ctx_ ogjk_ctx; /* one CUDA device + its scratch memory */
+
+/* Kernel selection for ogjk_*_device_*: AUTO bins pairs by vertex count. */
+enum { OGJK_MODE_AUTO = 0, OGJK_MODE_THREAD_PER_PAIR = 1, OGJK_MODE_WARP_PER_PAIR = 2 };
+
+OGJK_API const char* ogjk_last_error(void);
+OGJK_API const char* ogjk_version(void);
+
+/* Context.  `device` is a CUDA ordinal.  Not thread safe per context; distinct
+ * contexts may be used from distinct threads (replaces the reference's use of
+ * the legacy default stream + cudaDeviceSynchronize, gpu/opengjk_gpu.cu:3198-3201). */
+OGJK_API int ogjk_ctx_create(int device, ogjk_ctx** out);
+OGJK_API void ogjk_ctx_destroy(ogjk_ctx* ctx);
+OGJK_API int ogjk_ctx_device(const ogjk_ctx* ctx);
+/* Number of kernels launched by this context so far (bench "gpu_launches"). */
+OGJK_API int64_t ogjk_ctx_launch_count(const ogjk_ctx* ctx);
+/* Per-kernel device timing for the roofline report: when enabled, CUDA events
+ * bracket every launch of the next ogjk_gjk_device_* call on the caller's
+ * stream; ogjk_ctx_last_timing returns {classify, thread-per-pair kernel,
+ * warp-per-pair kernel} milliseconds of the most recent call (0 = not launched). */
+OGJK_API int ogjk_ctx_set_timing(ogjk_ctx* ctx, int enable);
+OGJK_API int ogjk_ctx_last_timing(ogjk_ctx* ctx, float* ms3);
+/* Size (in vertices of body1+body2) from which AUTO uses the warp-cooperative kernel. */
+OGJK_API int ogjk_ctx_set_warp_threshold(ogjk_ctx* ctx, int nverts);
+
+/* ---- device-resident batch (replaces compute_minimum_distance_device and the
+ * indexed kernel launch: gpu/include/openGJK_GPU.h:236-242, gpu/opengjk_gpu.cu:3186-3202,
+ * 3331-3336).  Every pointer is a DEVICE pointer.  `simplices` may be NULL
+ * (distance only).  `stream` is a cudaStream_t passed as void* (NULL = the
+ * legacy default stream).  Asynchronous: returns after enqueueing. */
+OGJK_API int ogjk_gjk_device_f32(ogjk_ctx* ctx, int64_t npairs,
+                                 const float* coords1, const int64_t* off1, const int* cnt1, const int* idx1,
+                                 const float* coords2, const int64_t* off2, const int* cnt2, const int* idx2,
+                                 ogjk_simplex_f32* simplices, float* distances, int mode, void* stream);
+OGJK_API int ogjk_gjk_device_f64(ogjk_ctx* ctx, int64_t npairs,
+                                 const double* coords1, const int64_t* off1, const int* cnt1, const int* idx1,
+                                 const double* coords2, const int64_t* off2, const int* cnt2, const int* idx2,
+                                 ogjk_simplex_f64* simplices, double* distances, int mode, void* stream);
+
+/* ---- host-buffer batch over flat pools (what a zero-copy binding calls; the
+ * e2e number in bench.py goes through this).  All pointers are HOST pointers.
+ * Copies inputs to the device, runs, copies results back, synchronises.
+ * pool2 may alias pool1 (indexed mode: pass the same pointers). */
+OGJK_API int ogjk_gjk_host_f32(ogjk_ctx* ctx, int64_t npairs,
+                               const float* coords1, const int64_t* off1, const int* cnt1, int64_t npoly1, int64_t nverts1, const int* idx1,
+                               const float* coords2, const int64_t* off2, const int* cnt2, int64_t npoly2, int64_t nverts2, const int* idx2,
+                               ogjk_simplex_f32* simplices, float* distances);
+OGJK_API int ogjk_gjk_host_f64(ogjk_ctx* ctx, int64_t npairs,
+                               const double* coords1, const int64_t* off1, const int* cnt1, int64_t npoly1, int64_t nverts1, const int* idx1,
+                               const double* coords2, const int64_t* off2, const int* cnt2, int64_t npoly2, int64_t nverts2, const int* idx2,
+                               ogjk_simplex_f64* simplices, double* distances);
+
+/* ---- reference-shaped high-level API (arrays of gkPolytope structs in host
+ * memory with flattened `coord`), replacing
+ *   compute_minimum_distance          gpu/include/openGJK_GPU.h:153-159, gpu/opengjk_gpu.cu:2977-3005
+ *   compute_minimum_distance_indexed  openGJK_GPU.h:213-220,             opengjk_gpu.cu:3284-3350
+ * n <= 0 returns OGJK_OK without touching anything (reference: silent return, :2984). */
+OGJK_API int ogjk_compute_minimum_distance_f32(ogjk_ctx* ctx, int n, const ogjk_polytope_f32* bd1, const ogjk_polytope_f32* bd2,
+                                               ogjk_simplex_f32* simplices, float* distances);
+OGJK_API int ogjk_compute_minimum_distance_f64(ogjk_ctx* ctx, int n, const ogjk_polytope_f64* bd1, const ogjk_polytope_f64* bd2,
+                                               ogjk_simplex_f64* simplices, double* distances);
+OGJK_API int ogjk_compute_minimum_distance_indexed_f32(ogjk_ctx* ctx, int num_polytopes, int num_pairs, const ogjk_polytope_f32* polytopes,
+                                                       const ogjk_pair* pairs, ogjk_simplex_f32* simplices, float* distances);
+OGJK_API int ogjk_compute_minimum_distance_indexed_f64(ogjk_ctx* ctx, int num_polytopes, int num_pairs, const ogjk_polytope_f64* polytopes,
+                                                       const ogjk_pair* pairs, ogjk_simplex_f64* simplices, double* distances);
+
+/* ---- single query with the scalar library's data layout (coord is an array
+ * of row pointers), replacing compute_minimum_distance(gkPolytope, gkPolytope,
+ * gkSimplex*) -- scalar/include/openGJK/openGJK.h:110, scalar/openGJK.c:941-1046.
+ * Runs as a batch of one on the context's device. */
+OGJK_API int ogjk_single_rows_f32(ogjk_ctx* ctx, int n1, float* const* rows1, int n2, float* const* rows2,
+                                  ogjk_simplex_f32* s, float* distance);
+OGJK_API int ogjk_single_rows_f64(ogjk_ctx* ctx, int n1, double* const* rows1, int n2, double* const* rows2,
+                                  ogjk_simplex_f64* s, double* distance);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENGJK_B200_H_ */

@@ -1,0 +1,77 @@
+"""ctypes binding of the C ABI in include/opengjk_b200.h.
+
+The shared library is built in-tree (opengjk_b200/libopengjk_b200.so) by
+``make -C opengjk_b200/csrc`` / ``__graft_entry__.build()``.  There is no
+fallback of any kind: a missing library or a missing CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libopengjk_b200.so")
+
+_lib = None
+
+
+class OpenGJKError(RuntimeError):
+    pass
+
+
+def simplex_dtype(np_float):
+    """numpy mirror of gkSimplex (scalar/include/openGJK/openGJK.h:84-94)."""
+    return np.dtype([("nvrtx", np.int32), ("vrtx", np_float, (4, 3)), ("vrtx_idx", np.int32, (4, 2)),
+                     ("witnesses", np_float, (2, 3))], align=True)
+
+
+SIMPLEX_F32 = simplex_dtype(np.float32)
+SIMPLEX_F64 = simplex_dtype(np.float64)
+assert SIMPLEX_F32.itemsize == 108 and SIMPLEX_F64.itemsize == 184
+
+# Every symbol include/opengjk_b200.h declares (tests check the .so exports all of them).
+EXPORTS = [
+    "ogjk_last_error", "ogjk_version", "ogjk_ctx_create", "ogjk_ctx_destroy", "ogjk_ctx_device",
+    "ogjk_ctx_launch_count", "ogjk_ctx_set_warp_threshold", "ogjk_ctx_set_timing", "ogjk_ctx_last_timing",
+    "ogjk_gjk_device_f32", "ogjk_gjk_device_f64", "ogjk_gjk_host_f32", "ogjk_gjk_host_f64",
+    "ogjk_compute_minimum_distance_f32", "ogjk_compute_minimum_distance_f64",
+    "ogjk_compute_minimum_distance_indexed_f32", "ogjk_compute_minimum_distance_indexed_f64",
+    "ogjk_single_rows_f32", "ogjk_single_rows_f64",
+]
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OpenGJKError(
+            f"{LIB_PATH} is missing: build it with `make -C opengjk_b200/csrc` "
+            "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.ogjk_last_error.restype = C.c_char_p
+    L.ogjk_version.restype = C.c_char_p
+    L.ogjk_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.ogjk_ctx_destroy.argtypes = [C.c_void_p]
+    L.ogjk_ctx_destroy.restype = None
+    L.ogjk_ctx_device.argtypes = [C.c_void_p]
+    L.ogjk_ctx_launch_count.argtypes = [C.c_void_p]
+    L.ogjk_ctx_launch_count.restype = C.c_int64
+    L.ogjk_ctx_set_warp_threshold.argtypes = [C.c_void_p, C.c_int]
+    L.ogjk_ctx_set_timing.argtypes = [C.c_void_p, C.c_int]
+    L.ogjk_ctx_last_timing.argtypes = [C.c_void_p, C.c_void_p]
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    for sfx in ("f32", "f64"):
+        getattr(L, f"ogjk_gjk_device_{sfx}").argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
+        getattr(L, f"ogjk_gjk_host_{sfx}").argtypes = [vp, i64, vp, vp, vp, i64, i64, vp, vp, vp, vp, i64, i64, vp,
+                                                       vp, vp]
+        getattr(L, f"ogjk_compute_minimum_distance_{sfx}").argtypes = [vp, i32, vp, vp, vp, vp]
+        getattr(L, f"ogjk_compute_minimum_distance_indexed_{sfx}").argtypes = [vp, i32, i32, vp, vp, vp, vp]
+        getattr(L, f"ogjk_single_rows_{sfx}").argtypes = [vp, i32, vp, i32, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise OpenGJKError(f"opengjk_b200 error {rc}: {lib().ogjk_last_error().decode()}")

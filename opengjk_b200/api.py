@@ -1,0 +1,240 @@
+"""Host-side mirror of the reference's batched Python interface.
+
+Function names, argument meaning and result dictionaries follow
+gpu/examples/python/src/pyopengjk_gpu/opengjk_gpu.py (compute_minimum_distance
+:227-318, compute_minimum_distance_indexed :480-560) so that tests read like
+the reference's own; the work is done by the C ABI (include/opengjk_b200.h).
+Unlike the reference wrapper, no per-polytope ctypes struct is built in a
+Python loop: ragged batches are flattened once with numpy and handed over as
+one pool.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import OpenGJKError, SIMPLEX_F32, SIMPLEX_F64, check  # noqa: F401
+
+_PREC = {np.dtype(np.float32): ("f32", SIMPLEX_F32), np.dtype(np.float64): ("f64", SIMPLEX_F64)}
+
+MODE_AUTO, MODE_THREAD, MODE_WARP = 0, 1, 2
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.data_ptr())  # torch tensor
+
+
+class Engine:
+    """One CUDA device (ogjk_ctx).  Raises OpenGJKError when no GPU is present."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        check(_lib.lib().ogjk_ctx_create(int(device), C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            _lib.lib().ogjk_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self):
+        return int(_lib.lib().ogjk_ctx_launch_count(self._h))
+
+    def set_timing(self, enable=True):
+        check(_lib.lib().ogjk_ctx_set_timing(self._h, int(bool(enable))))
+
+    def last_timing(self):
+        """{classify, thread kernel, warp kernel} milliseconds of the last device call."""
+        ms = (C.c_float * 3)()
+        check(_lib.lib().ogjk_ctx_last_timing(self._h, ms))
+        return {"classify": ms[0], "thread": ms[1], "warp": ms[2]}
+
+    def set_warp_threshold(self, nverts):
+        check(_lib.lib().ogjk_ctx_set_warp_threshold(self._h, int(nverts)))
+
+    # -- device-resident batch (torch CUDA tensors or raw device pointers) ------
+    def gjk_device(self, prec, npairs, coords1, off1, cnt1, idx1, coords2, off2, cnt2, idx2, simplices, distances,
+                   mode=MODE_AUTO, stream=0):
+        fn = getattr(_lib.lib(), f"ogjk_gjk_device_{prec}")
+        check(fn(self._h, int(npairs), _p(coords1), _p(off1), _p(cnt1), _p(idx1), _p(coords2), _p(off2), _p(cnt2),
+                 _p(idx2), _p(simplices), _p(distances), int(mode), C.c_void_p(int(stream))))
+
+    # -- host buffers, one pool shared by both bodies (indexed form) -------------
+    def gjk_host(self, coords, off, cnt, pa, pb, want_simplices=True, out=None):
+        coords = np.ascontiguousarray(coords)
+        prec, sdt = _PREC[coords.dtype]
+        coords = coords.reshape(-1, 3)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        cnt = np.ascontiguousarray(cnt, dtype=np.int32)
+        pa = np.ascontiguousarray(pa, dtype=np.int32)
+        pb = np.ascontiguousarray(pb, dtype=np.int32)
+        n = pa.shape[0]
+        if out is None:
+            dist = np.zeros(n, dtype=coords.dtype)
+            simp = np.zeros(n, dtype=sdt) if want_simplices else None
+        else:
+            dist, simp = out
+        fn = getattr(_lib.lib(), f"ogjk_gjk_host_{prec}")
+        check(fn(self._h, n, _p(coords), _p(off), _p(cnt), cnt.shape[0], coords.shape[0], _p(pa), _p(coords), _p(off),
+                 _p(cnt), cnt.shape[0], coords.shape[0], _p(pb), _p(simp), _p(dist)))
+        return dist, simp
+
+    def run_workload(self, w, want_simplices=True):
+        return self.gjk_host(w.coords, w.off, w.cnt, w.pa, w.pb, want_simplices)
+
+
+_default = {}
+
+
+def default_engine(device=0):
+    if device not in _default:
+        _default[device] = Engine(device)
+    return _default[device]
+
+
+def _flatten(batch, dtype):
+    """(P,V,3) array or list of (V_i,3) arrays -> (coords, off, cnt)."""
+    if isinstance(batch, np.ndarray) and batch.ndim == 3:
+        if batch.shape[2] != 3:
+            raise ValueError(f"Expected 3D array (num_poly, num_verts, 3), got shape {batch.shape}")
+        p, v = batch.shape[0], batch.shape[1]
+        coords = np.ascontiguousarray(batch, dtype=dtype).reshape(-1, 3)
+        cnt = np.full(p, v, dtype=np.int32)
+        off = np.arange(p, dtype=np.int64) * v
+        return coords, off, cnt
+    if isinstance(batch, np.ndarray) and batch.ndim == 2:
+        batch = [batch]
+    arrs = []
+    for a in batch:
+        a = np.asarray(a, dtype=dtype)
+        if a.ndim != 2 or a.shape[1] != 3:
+            raise ValueError(f"Vertices must have shape (n, 3), got {a.shape}")
+        arrs.append(a)
+    cnt = np.array([a.shape[0] for a in arrs], dtype=np.int32)
+    off = np.zeros(len(arrs), dtype=np.int64)
+    np.cumsum(cnt[:-1], out=off[1:])
+    coords = np.concatenate(arrs) if arrs else np.zeros((0, 3), dtype=dtype)
+    return np.ascontiguousarray(coords), off, cnt
+
+
+def _result(dist, simp):
+    return {
+        "distances": dist,
+        "witnesses1": np.ascontiguousarray(simp["witnesses"][:, 0, :]),
+        "witnesses2": np.ascontiguousarray(simp["witnesses"][:, 1, :]),
+        "is_collision": np.abs(dist) < 1e-6,  # opengjk_gpu.py:308
+        "simplex_nvrtx": simp["nvrtx"].copy(),
+        "simplices": simp,
+    }
+
+
+def compute_minimum_distance(vertices1, vertices2, dtype=np.float32, engine=None):
+    """Batched GJK distance (reference: opengjk_gpu.py:227-318).  vertices1/2:
+    (V,3) single pair, (P,V,3) batch, or list of (V_i,3) arrays."""
+    eng = engine or default_engine()
+    c1, o1, k1 = _flatten(vertices1, dtype)
+    c2, o2, k2 = _flatten(vertices2, dtype)
+    if k1.shape[0] != k2.shape[0]:
+        raise ValueError(f"Mismatch: {k1.shape[0]} polytopes in bd1, {k2.shape[0]} in bd2")
+    n = k1.shape[0]
+    coords = np.concatenate([c1, c2])
+    off = np.concatenate([o1, o2 + c1.shape[0]])
+    cnt = np.concatenate([k1, k2])
+    pa = np.arange(n, dtype=np.int32)
+    dist, simp = eng.gjk_host(coords, off, cnt, pa, pa + n)
+    return _result(dist, simp)
+
+
+def compute_minimum_distance_indexed(polytopes, pairs, dtype=np.float32, engine=None):
+    """Indexed batch (reference: opengjk_gpu.py:480-560): `polytopes` is a
+    (P,V,3) array or list of (V_i,3) arrays, `pairs` an (N,2) int array."""
+    eng = engine or default_engine()
+    coords, off, cnt = _flatten(polytopes, dtype)
+    pairs = np.asarray(pairs, dtype=np.int32).reshape(-1, 2)
+    if pairs.size and (pairs.min() < 0 or pairs.max() >= cnt.shape[0]):
+        raise ValueError("pair index out of range")
+    dist, simp = eng.gjk_host(coords, off, cnt, pairs[:, 0], pairs[:, 1])
+    return _result(dist, simp)
+
+
+# ---- struct-array entry points (the exact reference C signatures) -------------
+def _polytope_struct(cf):
+    class gkPolytope(C.Structure):  # gpu/include/openGJK_GPU.h:71-76
+        _fields_ = [("numpoints", C.c_int), ("s", cf * 3), ("s_idx", C.c_int), ("coord", C.POINTER(cf))]
+    return gkPolytope
+
+
+class gkCollisionPair(C.Structure):  # gpu/include/openGJK_GPU.h:89-92
+    _fields_ = [("idx1", C.c_int), ("idx2", C.c_int)]
+
+
+def _struct_array(bodies, dtype):
+    cf = C.c_float if np.dtype(dtype) == np.float32 else C.c_double
+    P = _polytope_struct(cf)
+    arr = (P * len(bodies))()
+    keep = []
+    for i, b in enumerate(bodies):
+        flat = np.ascontiguousarray(np.asarray(b, dtype=dtype).reshape(-1))
+        keep.append(flat)
+        arr[i].numpoints = flat.shape[0] // 3
+        arr[i].s_idx = 0
+        arr[i].coord = flat.ctypes.data_as(C.POINTER(cf))
+    return arr, keep
+
+
+def compute_minimum_distance_structs(bodies1, bodies2, dtype=np.float32, engine=None):
+    """Calls ogjk_compute_minimum_distance_{f32,f64} with arrays of gkPolytope."""
+    eng = engine or default_engine()
+    prec, sdt = _PREC[np.dtype(dtype)]
+    a1, k1 = _struct_array(bodies1, dtype)
+    a2, k2 = _struct_array(bodies2, dtype)
+    n = len(bodies1)
+    simp = np.zeros(n, dtype=sdt)
+    dist = np.zeros(n, dtype=dtype)
+    fn = getattr(_lib.lib(), f"ogjk_compute_minimum_distance_{prec}")
+    check(fn(eng._h, n, C.cast(a1, C.c_void_p), C.cast(a2, C.c_void_p), _p(simp), _p(dist)))
+    return dist, simp
+
+
+def compute_minimum_distance_indexed_structs(bodies, pairs, dtype=np.float32, engine=None):
+    eng = engine or default_engine()
+    prec, sdt = _PREC[np.dtype(dtype)]
+    a, keep = _struct_array(bodies, dtype)
+    pairs = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+    n = pairs.shape[0]
+    simp = np.zeros(n, dtype=sdt)
+    dist = np.zeros(n, dtype=dtype)
+    fn = getattr(_lib.lib(), f"ogjk_compute_minimum_distance_indexed_{prec}")
+    check(fn(eng._h, len(bodies), n, C.cast(a, C.c_void_p), _p(pairs), _p(simp), _p(dist)))
+    return dist, simp
+
+
+def single_query(vertices0, vertices1, dtype=np.float64, engine=None):
+    """One pair through the scalar library's row-pointer layout
+    (scalar/examples/python_ctypes/src/pyopengjk/opengjk.py:60-91)."""
+    eng = engine or default_engine()
+    prec, sdt = _PREC[np.dtype(dtype)]
+    cf = C.c_float if prec == "f32" else C.c_double
+    a = np.ascontiguousarray(np.asarray(vertices0, dtype=dtype).reshape(-1, 3))
+    b = np.ascontiguousarray(np.asarray(vertices1, dtype=dtype).reshape(-1, 3))
+    rows_a = (C.POINTER(cf) * a.shape[0])(*[a[i].ctypes.data_as(C.POINTER(cf)) for i in range(a.shape[0])])
+    rows_b = (C.POINTER(cf) * b.shape[0])(*[b[i].ctypes.data_as(C.POINTER(cf)) for i in range(b.shape[0])])
+    simp = np.zeros(1, dtype=sdt)
+    dist = np.zeros(1, dtype=dtype)
+    fn = getattr(_lib.lib(), f"ogjk_single_rows_{prec}")
+    check(fn(eng._h, a.shape[0], C.cast(rows_a, C.c_void_p), b.shape[0], C.cast(rows_b, C.c_void_p), _p(simp),
+             _p(dist)))
+    return float(dist[0]), simp[0]

@@ -1,0 +1,443 @@
+// abi.cu -- the C ABI declared in include/opengjk_b200.h.
+//
+// Host logic only: context + scratch memory, the two-stage batch scheduler
+// (classify by size, then one launch per kernel flavour), the host-buffer
+// convenience entry points (one bulk H2D per array instead of the reference's
+// one cudaMemcpy per polytope, gpu/opengjk_gpu.cu:3152-3153) and the
+// reference-shaped struct-array wrappers.  No torch types, no C++ types across
+// the boundary, every CUDA call checked.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/opengjk_b200.h"
+#include "gjk_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+
+#define CU(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) {                                                          \
+      snprintf(g_err, sizeof(g_err), "%s failed: %s", #call, cudaGetErrorString(e_)); \
+      return OGJK_ERR_CUDA;                                                           \
+    }                                                                                 \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return OGJK_OK;
+    if (p) { CU(cudaFree(p)); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 4 + 256;
+    CU(cudaMalloc(&p, want));
+    cap = want;
+    return OGJK_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return OGJK_OK;
+    if (p) { CU(cudaFreeHost(p)); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 4 + 256;
+    CU(cudaMallocHost(&p, want));
+    cap = want;
+    return OGJK_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct ogjk_ctx_ {
+  int device = 0;
+  int sm_count = 148;
+  int warp_threshold = 192;  // body1+body2 vertices from which a whole warp scans one pair
+  long long launches = 0;
+  // optional per-kernel timing: events bracket each launch on the caller's stream
+  bool timing = false;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int timed_mask = 0;  // bit k set: phase k (0 classify, 1 thread kernel, 2 warp kernel) was launched
+  cudaStream_t own_stream = nullptr;  // used by the host-buffer entry points
+  DevBuf counters;                    // Q_SLOTS x u64
+  DevBuf small_list, large_list;      // pair ids per bin
+  // staging for the host-buffer paths
+  DevBuf d_coords1, d_coords2, d_off1, d_off2, d_cnt1, d_cnt2, d_idx1, d_idx2, d_simp, d_dist;
+  PinBuf h_stage;
+};
+
+namespace {
+
+using namespace ogjk;
+
+template <typename T>
+int launch_batch(ogjk_ctx* ctx, const BatchArgs<T>& a, int mode, cudaStream_t st) {
+  if (a.npairs <= 0) return OGJK_OK;
+  if (a.npairs > 0x7fffffffll) return fail(OGJK_ERR_ARG, "npairs exceeds 2^31-1 per call%s");
+  int rc = ctx->counters.reserve(Q_SLOTS * sizeof(unsigned long long));
+  if (rc) return rc;
+  auto* counters = static_cast<unsigned long long*>(ctx->counters.p);
+  CU(cudaMemsetAsync(counters, 0, Q_SLOTS * sizeof(unsigned long long), st));
+
+  const int sm = ctx->sm_count;
+  auto thread_grid = [&](long long n) {
+    long long blocks = (n + 127) / 128;
+    long long cap = (long long)sm * 16;
+    return (unsigned)(blocks < cap ? blocks : cap);
+  };
+  auto warp_grid = [&](long long n) {
+    long long blocks = (n + 7) / 8;
+    long long cap = (long long)sm * 8;
+    return (unsigned)(blocks < cap ? blocks : cap);
+  };
+
+  ctx->timed_mask = 0;
+  auto mark = [&](int phase, int edge) {
+    if (ctx->timing) {
+      cudaEventRecord(ctx->ev[2 * phase + edge], st);
+      ctx->timed_mask |= 1 << phase;
+    }
+  };
+
+  if (mode == OGJK_MODE_THREAD_PER_PAIR) {
+    mark(1, 0);
+    gjk_thread_kernel<T><<<thread_grid(a.npairs), 128, 0, st>>>(a, nullptr, nullptr, counters + Q_THREAD_HEAD);
+    mark(1, 1);
+    ctx->launches += 1;
+  } else if (mode == OGJK_MODE_WARP_PER_PAIR) {
+    mark(2, 0);
+    gjk_warp_kernel<T><<<warp_grid(a.npairs), 256, 0, st>>>(a, nullptr, nullptr, counters + Q_WARP_HEAD);
+    mark(2, 1);
+    ctx->launches += 1;
+  } else {
+    rc = ctx->small_list.reserve((size_t)a.npairs * sizeof(int));
+    if (rc) return rc;
+    rc = ctx->large_list.reserve((size_t)a.npairs * sizeof(int));
+    if (rc) return rc;
+    int* sl = static_cast<int*>(ctx->small_list.p);
+    int* ll = static_cast<int*>(ctx->large_list.p);
+    long long cblocks = (a.npairs + 255) / 256;
+    if (cblocks > (long long)sm * 32) cblocks = (long long)sm * 32;
+    mark(0, 0);
+    classify_kernel<T><<<(unsigned)cblocks, 256, 0, st>>>(a, ctx->warp_threshold, sl, ll, counters);
+    mark(0, 1);
+    // Both consumers size their loops from the device-side counts; grids are
+    // bounded by the SM count, so an empty bin costs one short launch.
+    mark(1, 0);
+    gjk_thread_kernel<T><<<thread_grid(a.npairs), 128, 0, st>>>(a, sl, counters + Q_SMALL_COUNT, counters + Q_THREAD_HEAD);
+    mark(1, 1);
+    mark(2, 0);
+    gjk_warp_kernel<T><<<warp_grid(a.npairs), 256, 0, st>>>(a, ll, counters + Q_LARGE_COUNT, counters + Q_WARP_HEAD);
+    mark(2, 1);
+    ctx->launches += 3;
+  }
+  CU(cudaGetLastError());
+  return OGJK_OK;
+}
+
+template <typename T, typename S>
+int gjk_device(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t* off1, const int* cnt1, const int* idx1,
+               const T* coords2, const int64_t* off2, const int* cnt2, const int* idx2, S* simplices, T* distances,
+               int mode, void* stream) {
+  if (!ctx) return fail(OGJK_ERR_ARG, "ctx is NULL%s");
+  if (npairs < 0) return fail(OGJK_ERR_ARG, "npairs < 0%s");
+  if (npairs == 0) return OGJK_OK;
+  if (!coords1 || !off1 || !cnt1 || !coords2 || !off2 || !cnt2 || !distances)
+    return fail(OGJK_ERR_ARG, "NULL device pointer%s");
+  if (mode < OGJK_MODE_AUTO || mode > OGJK_MODE_WARP_PER_PAIR) return fail(OGJK_ERR_ARG, "bad mode%s");
+  CU(cudaSetDevice(ctx->device));
+  BatchArgs<T> a;
+  a.coords1 = coords1; a.off1 = reinterpret_cast<const long long*>(off1); a.cnt1 = cnt1; a.idx1 = idx1;
+  a.coords2 = coords2; a.off2 = reinterpret_cast<const long long*>(off2); a.cnt2 = cnt2; a.idx2 = idx2;
+  a.simplices = reinterpret_cast<GkSimplex<T>*>(simplices);
+  a.distances = distances;
+  a.npairs = npairs;
+  return launch_batch<T>(ctx, a, mode, static_cast<cudaStream_t>(stream));
+}
+
+// Upload one host array into a grow-only device buffer on the context stream.
+int upload(ogjk_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
+  int rc = b.reserve(bytes ? bytes : 1);
+  if (rc) return rc;
+  if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->own_stream));
+  return OGJK_OK;
+}
+
+template <typename T, typename S>
+int gjk_host(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t* off1, const int* cnt1, int64_t npoly1,
+             int64_t nverts1, const int* idx1, const T* coords2, const int64_t* off2, const int* cnt2, int64_t npoly2,
+             int64_t nverts2, const int* idx2, S* simplices, T* distances) {
+  if (!ctx) return fail(OGJK_ERR_ARG, "ctx is NULL%s");
+  if (npairs < 0 || npoly1 < 0 || npoly2 < 0 || nverts1 < 0 || nverts2 < 0) return fail(OGJK_ERR_ARG, "negative count%s");
+  if (npairs == 0) return OGJK_OK;
+  if (!coords1 || !off1 || !cnt1 || !coords2 || !off2 || !cnt2 || !distances) return fail(OGJK_ERR_ARG, "NULL host pointer%s");
+  CU(cudaSetDevice(ctx->device));
+  const bool shared_pool = (coords1 == coords2 && off1 == off2 && cnt1 == cnt2);
+  int rc;
+  if ((rc = upload(ctx, ctx->d_coords1, coords1, (size_t)nverts1 * 3 * sizeof(T)))) return rc;
+  if ((rc = upload(ctx, ctx->d_off1, off1, (size_t)npoly1 * sizeof(int64_t)))) return rc;
+  if ((rc = upload(ctx, ctx->d_cnt1, cnt1, (size_t)npoly1 * sizeof(int)))) return rc;
+  if (idx1 && (rc = upload(ctx, ctx->d_idx1, idx1, (size_t)npairs * sizeof(int)))) return rc;
+  if (!shared_pool) {
+    if ((rc = upload(ctx, ctx->d_coords2, coords2, (size_t)nverts2 * 3 * sizeof(T)))) return rc;
+    if ((rc = upload(ctx, ctx->d_off2, off2, (size_t)npoly2 * sizeof(int64_t)))) return rc;
+    if ((rc = upload(ctx, ctx->d_cnt2, cnt2, (size_t)npoly2 * sizeof(int)))) return rc;
+  }
+  if (idx2 && (rc = upload(ctx, ctx->d_idx2, idx2, (size_t)npairs * sizeof(int)))) return rc;
+  if ((rc = ctx->d_dist.reserve((size_t)npairs * sizeof(T)))) return rc;
+  if (simplices && (rc = ctx->d_simp.reserve((size_t)npairs * sizeof(S)))) return rc;
+
+  rc = gjk_device<T, S>(ctx, npairs, static_cast<const T*>(ctx->d_coords1.p),
+                        static_cast<const int64_t*>(ctx->d_off1.p), static_cast<const int*>(ctx->d_cnt1.p),
+                        idx1 ? static_cast<const int*>(ctx->d_idx1.p) : nullptr,
+                        static_cast<const T*>(shared_pool ? ctx->d_coords1.p : ctx->d_coords2.p),
+                        static_cast<const int64_t*>(shared_pool ? ctx->d_off1.p : ctx->d_off2.p),
+                        static_cast<const int*>(shared_pool ? ctx->d_cnt1.p : ctx->d_cnt2.p),
+                        idx2 ? static_cast<const int*>(ctx->d_idx2.p) : nullptr,
+                        simplices ? static_cast<S*>(ctx->d_simp.p) : nullptr, static_cast<T*>(ctx->d_dist.p),
+                        OGJK_MODE_AUTO, ctx->own_stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(distances, ctx->d_dist.p, (size_t)npairs * sizeof(T), cudaMemcpyDeviceToHost, ctx->own_stream));
+  if (simplices)
+    CU(cudaMemcpyAsync(simplices, ctx->d_simp.p, (size_t)npairs * sizeof(S), cudaMemcpyDeviceToHost, ctx->own_stream));
+  CU(cudaStreamSynchronize(ctx->own_stream));
+  return OGJK_OK;
+}
+
+// Flatten an array of reference-shaped polytope structs (each with its own
+// host `coord` block) into one pinned pool: [coords | off | cnt].
+template <typename T, typename P>
+int flatten(ogjk_ctx* ctx, size_t base, int n, const P* bd, size_t* bytes_used, T** coords, int64_t** off, int** cnt,
+            int64_t* nverts) {
+  int64_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    if (bd[i].numpoints < 1 || !bd[i].coord) return fail(OGJK_ERR_ARG, "polytope with no vertices%s");
+    total += bd[i].numpoints;
+  }
+  size_t need = (size_t)total * 3 * sizeof(T) + (size_t)n * (sizeof(int64_t) + sizeof(int)) + 64;
+  char* p = static_cast<char*>(ctx->h_stage.p) + base;
+  (void)need;
+  T* c = reinterpret_cast<T*>(p);
+  size_t cbytes = ((size_t)total * 3 * sizeof(T) + 15) & ~(size_t)15;
+  int64_t* o = reinterpret_cast<int64_t*>(p + cbytes);
+  int* k = reinterpret_cast<int*>(p + cbytes + (size_t)n * sizeof(int64_t));
+  int64_t at = 0;
+  for (int i = 0; i < n; ++i) {
+    o[i] = at;
+    k[i] = bd[i].numpoints;
+    memcpy(c + 3 * at, bd[i].coord, (size_t)bd[i].numpoints * 3 * sizeof(T));
+    at += bd[i].numpoints;
+  }
+  *coords = c; *off = o; *cnt = k; *nverts = total;
+  *bytes_used = ((cbytes + (size_t)n * (sizeof(int64_t) + sizeof(int))) + 63) & ~(size_t)63;
+  return OGJK_OK;
+}
+
+template <typename P> size_t flat_bytes(int n, const P* bd, size_t tsize) {
+  size_t total = 0;
+  for (int i = 0; i < n; ++i) total += bd[i].numpoints > 0 ? (size_t)bd[i].numpoints : 0;
+  return ((((total * 3 * tsize + 15) & ~(size_t)15) + (size_t)n * 12 + 128) + 63) & ~(size_t)63;
+}
+
+template <typename T, typename P, typename S>
+int compute_min_dist(ogjk_ctx* ctx, int n, const P* bd1, const P* bd2, S* simplices, T* distances) {
+  if (n <= 0) return OGJK_OK;  // reference: silent return (gpu/opengjk_gpu.cu:2984)
+  if (!ctx || !bd1 || !bd2 || !distances) return fail(OGJK_ERR_ARG, "NULL argument%s");
+  CU(cudaSetDevice(ctx->device));
+  size_t b1 = flat_bytes(n, bd1, sizeof(T)), b2 = flat_bytes(n, bd2, sizeof(T));
+  int rc = ctx->h_stage.reserve(b1 + b2);
+  if (rc) return rc;
+  T *c1, *c2; int64_t *o1, *o2; int *k1, *k2; int64_t nv1, nv2; size_t used1, used2;
+  if ((rc = flatten<T, P>(ctx, 0, n, bd1, &used1, &c1, &o1, &k1, &nv1))) return rc;
+  if ((rc = flatten<T, P>(ctx, b1, n, bd2, &used2, &c2, &o2, &k2, &nv2))) return rc;
+  return gjk_host<T, S>(ctx, n, c1, o1, k1, n, nv1, nullptr, c2, o2, k2, n, nv2, nullptr, simplices, distances);
+}
+
+template <typename T, typename P, typename S>
+int compute_min_dist_indexed(ogjk_ctx* ctx, int npoly, int npairs, const P* polys, const ogjk_pair* pairs, S* simplices,
+                             T* distances) {
+  if (npairs <= 0 || npoly <= 0) return OGJK_OK;  // reference: silent return (:3292)
+  if (!ctx || !polys || !pairs || !distances) return fail(OGJK_ERR_ARG, "NULL argument%s");
+  CU(cudaSetDevice(ctx->device));
+  size_t b1 = flat_bytes(npoly, polys, sizeof(T));
+  size_t ib = ((size_t)npairs * sizeof(int) + 63) & ~(size_t)63;
+  int rc = ctx->h_stage.reserve(b1 + 2 * ib);
+  if (rc) return rc;
+  T* c; int64_t* o; int* k; int64_t nv; size_t used;
+  if ((rc = flatten<T, P>(ctx, 0, npoly, polys, &used, &c, &o, &k, &nv))) return rc;
+  int* i1 = reinterpret_cast<int*>(static_cast<char*>(ctx->h_stage.p) + b1);
+  int* i2 = reinterpret_cast<int*>(static_cast<char*>(ctx->h_stage.p) + b1 + ib);
+  for (int p = 0; p < npairs; ++p) {
+    if (pairs[p].idx1 < 0 || pairs[p].idx1 >= npoly || pairs[p].idx2 < 0 || pairs[p].idx2 >= npoly)
+      return fail(OGJK_ERR_ARG, "pair index out of range%s");
+    i1[p] = pairs[p].idx1;
+    i2[p] = pairs[p].idx2;
+  }
+  return gjk_host<T, S>(ctx, npairs, c, o, k, npoly, nv, i1, c, o, k, npoly, nv, i2, simplices, distances);
+}
+
+template <typename T, typename S>
+int single_rows(ogjk_ctx* ctx, int n1, T* const* rows1, int n2, T* const* rows2, S* s, T* distance) {
+  if (!ctx || !rows1 || !rows2 || !s || !distance) return fail(OGJK_ERR_ARG, "NULL argument%s");
+  if (n1 < 1 || n2 < 1) return fail(OGJK_ERR_ARG, "polytope with no vertices%s");
+  std::vector<T> c((size_t)(n1 + n2) * 3);
+  for (int i = 0; i < n1; ++i) for (int t = 0; t < 3; ++t) c[3 * (size_t)i + t] = rows1[i][t];
+  for (int i = 0; i < n2; ++i) for (int t = 0; t < 3; ++t) c[3 * (size_t)(n1 + i) + t] = rows2[i][t];
+  int64_t off[2] = {0, n1};
+  int cnt[2] = {n1, n2};
+  int i1 = 0, i2 = 1;
+  return gjk_host<T, S>(ctx, 1, c.data(), off, cnt, 2, n1 + n2, &i1, c.data(), off, cnt, 2, n1 + n2, &i2, s, distance);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ogjk_last_error(void) { return g_err; }
+const char* ogjk_version(void) { return "opengjk_b200 0.1 (sm_100a)"; }
+
+int ogjk_ctx_create(int device, ogjk_ctx** out) {
+  if (!out) return fail(OGJK_ERR_ARG, "out is NULL%s");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    snprintf(g_err, sizeof(g_err), "no CUDA device available (%s); this library has no CPU fallback",
+             e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return OGJK_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) return fail(OGJK_ERR_ARG, "device ordinal out of range%s");
+  CU(cudaSetDevice(device));
+  ogjk_ctx* c = new (std::nothrow) ogjk_ctx_();
+  if (!c) return fail(OGJK_ERR_ALLOC, "out of host memory%s");
+  c->device = device;
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete c;
+    snprintf(g_err, sizeof(g_err), "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    return OGJK_ERR_CUDA;
+  }
+  *out = c;
+  return OGJK_OK;
+}
+
+void ogjk_ctx_destroy(ogjk_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  DevBuf* bufs[] = {&c->counters, &c->small_list, &c->large_list, &c->d_coords1, &c->d_coords2, &c->d_off1, &c->d_off2,
+                    &c->d_cnt1,   &c->d_cnt2,     &c->d_idx1,     &c->d_idx2,    &c->d_simp,    &c->d_dist};
+  for (DevBuf* b : bufs) b->release();
+  c->h_stage.release();
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  delete c;
+}
+
+int ogjk_ctx_device(const ogjk_ctx* c) { return c ? c->device : -1; }
+int64_t ogjk_ctx_launch_count(const ogjk_ctx* c) { return c ? c->launches : 0; }
+int ogjk_ctx_set_timing(ogjk_ctx* c, int enable) {
+  if (!c) return fail(OGJK_ERR_ARG, "ctx is NULL%s");
+  CU(cudaSetDevice(c->device));
+  if (enable && !c->ev[0])
+    for (int i = 0; i < 6; ++i) CU(cudaEventCreate(&c->ev[i]));
+  c->timing = enable != 0;
+  c->timed_mask = 0;
+  return OGJK_OK;
+}
+int ogjk_ctx_last_timing(ogjk_ctx* c, float* ms3) {
+  if (!c || !ms3) return fail(OGJK_ERR_ARG, "NULL argument%s");
+  if (!c->timing) return fail(OGJK_ERR_ARG, "timing not enabled%s");
+  for (int k = 0; k < 3; ++k) {
+    ms3[k] = 0.f;
+    if (c->timed_mask & (1 << k)) {
+      CU(cudaEventSynchronize(c->ev[2 * k + 1]));
+      CU(cudaEventElapsedTime(&ms3[k], c->ev[2 * k], c->ev[2 * k + 1]));
+    }
+  }
+  return OGJK_OK;
+}
+int ogjk_ctx_set_warp_threshold(ogjk_ctx* c, int nverts) {
+  if (!c || nverts < 2) return fail(OGJK_ERR_ARG, "bad threshold%s");
+  c->warp_threshold = nverts;
+  return OGJK_OK;
+}
+
+int ogjk_gjk_device_f32(ogjk_ctx* ctx, int64_t npairs, const float* coords1, const int64_t* off1, const int* cnt1,
+                        const int* idx1, const float* coords2, const int64_t* off2, const int* cnt2, const int* idx2,
+                        ogjk_simplex_f32* simplices, float* distances, int mode, void* stream) {
+  return gjk_device<float, ogjk_simplex_f32>(ctx, npairs, coords1, off1, cnt1, idx1, coords2, off2, cnt2, idx2, simplices,
+                                             distances, mode, stream);
+}
+int ogjk_gjk_device_f64(ogjk_ctx* ctx, int64_t npairs, const double* coords1, const int64_t* off1, const int* cnt1,
+                        const int* idx1, const double* coords2, const int64_t* off2, const int* cnt2, const int* idx2,
+                        ogjk_simplex_f64* simplices, double* distances, int mode, void* stream) {
+  return gjk_device<double, ogjk_simplex_f64>(ctx, npairs, coords1, off1, cnt1, idx1, coords2, off2, cnt2, idx2,
+                                              simplices, distances, mode, stream);
+}
+
+int ogjk_gjk_host_f32(ogjk_ctx* ctx, int64_t npairs, const float* coords1, const int64_t* off1, const int* cnt1,
+                      int64_t npoly1, int64_t nverts1, const int* idx1, const float* coords2, const int64_t* off2,
+                      const int* cnt2, int64_t npoly2, int64_t nverts2, const int* idx2, ogjk_simplex_f32* simplices,
+                      float* distances) {
+  return gjk_host<float, ogjk_simplex_f32>(ctx, npairs, coords1, off1, cnt1, npoly1, nverts1, idx1, coords2, off2, cnt2,
+                                           npoly2, nverts2, idx2, simplices, distances);
+}
+int ogjk_gjk_host_f64(ogjk_ctx* ctx, int64_t npairs, const double* coords1, const int64_t* off1, const int* cnt1,
+                      int64_t npoly1, int64_t nverts1, const int* idx1, const double* coords2, const int64_t* off2,
+                      const int* cnt2, int64_t npoly2, int64_t nverts2, const int* idx2, ogjk_simplex_f64* simplices,
+                      double* distances) {
+  return gjk_host<double, ogjk_simplex_f64>(ctx, npairs, coords1, off1, cnt1, npoly1, nverts1, idx1, coords2, off2, cnt2,
+                                            npoly2, nverts2, idx2, simplices, distances);
+}
+
+int ogjk_compute_minimum_distance_f32(ogjk_ctx* ctx, int n, const ogjk_polytope_f32* bd1, const ogjk_polytope_f32* bd2,
+                                      ogjk_simplex_f32* simplices, float* distances) {
+  return compute_min_dist<float, ogjk_polytope_f32, ogjk_simplex_f32>(ctx, n, bd1, bd2, simplices, distances);
+}
+int ogjk_compute_minimum_distance_f64(ogjk_ctx* ctx, int n, const ogjk_polytope_f64* bd1, const ogjk_polytope_f64* bd2,
+                                      ogjk_simplex_f64* simplices, double* distances) {
+  return compute_min_dist<double, ogjk_polytope_f64, ogjk_simplex_f64>(ctx, n, bd1, bd2, simplices, distances);
+}
+int ogjk_compute_minimum_distance_indexed_f32(ogjk_ctx* ctx, int num_polytopes, int num_pairs,
+                                              const ogjk_polytope_f32* polytopes, const ogjk_pair* pairs,
+                                              ogjk_simplex_f32* simplices, float* distances) {
+  return compute_min_dist_indexed<float, ogjk_polytope_f32, ogjk_simplex_f32>(ctx, num_polytopes, num_pairs, polytopes,
+                                                                              pairs, simplices, distances);
+}
+int ogjk_compute_minimum_distance_indexed_f64(ogjk_ctx* ctx, int num_polytopes, int num_pairs,
+                                              const ogjk_polytope_f64* polytopes, const ogjk_pair* pairs,
+                                              ogjk_simplex_f64* simplices, double* distances) {
+  return compute_min_dist_indexed<double, ogjk_polytope_f64, ogjk_simplex_f64>(ctx, num_polytopes, num_pairs, polytopes,
+                                                                               pairs, simplices, distances);
+}
+
+int ogjk_single_rows_f32(ogjk_ctx* ctx, int n1, float* const* rows1, int n2, float* const* rows2, ogjk_simplex_f32* s,
+                         float* distance) {
+  return single_rows<float, ogjk_simplex_f32>(ctx, n1, rows1, n2, rows2, s, distance);
+}
+int ogjk_single_rows_f64(ogjk_ctx* ctx, int n1, double* const* rows1, int n2, double* const* rows2,
+                         ogjk_simplex_f64* s, double* distance) {
+  return single_rows<double, ogjk_simplex_f64>(ctx, n1, rows1, n2, rows2, s, distance);
+}
+
+}  // extern "C"

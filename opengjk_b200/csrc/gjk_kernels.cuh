@@ -1,0 +1,250 @@
+// gjk_kernels.cuh -- batched GJK distance kernels for sm_100a.
+//
+// Replaces the reference's compute_minimum_distance_kernel and
+// compute_minimum_distance_indexed_kernel (gpu/opengjk_gpu.cu:1257-1631) with
+// two kernels over one addressing scheme (pool + optional per-pair indices):
+//
+//   gjk_thread_kernel : one pair per thread  -- small hulls; the whole GJK
+//                       state (simplex, search direction, carried supports)
+//                       is register resident and nothing is exchanged
+//                       between lanes.
+//   gjk_warp_kernel   : one pair per warp    -- large hulls; the support scan
+//                       is lane-strided over the vertex stream and reduced with
+//                       a (value, lowest-index) butterfly of __shfl_xor; the
+//                       sub-solver then runs redundantly (and convergently) in
+//                       every lane, so no broadcast is needed.
+//
+// Both pull work from a device-side queue in warp-sized chunks so that the
+// 1..25-iteration spread of GJK does not leave SMs idle at the tail.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "gjk_core.cuh"
+
+namespace ogjk {
+
+template <typename T> struct BatchArgs {
+  const T* coords1; const long long* off1; const int* cnt1; const int* idx1;
+  const T* coords2; const long long* off2; const int* cnt2; const int* idx2;
+  GkSimplex<T>* simplices;  // may be null
+  T* distances;
+  long long npairs;
+};
+
+// ---- support functions (openGJK.c:607-630) ------------------------------------
+// `cur`/`cur_i` carry the previous support point of the body: the scan starts
+// from its dot product, takes vertex i only when strictly larger, lowest index
+// first, and leaves the carried point alone when nothing beats it.
+
+template <typename T> struct ThreadBody {
+  const T* c; int n;
+  OGJK_DI V3<T> vertex(int i) const {
+    const T* p = c + 3 * (size_t)i;
+    return V3<T>{p[0], p[1], p[2]};
+  }
+  OGJK_DI void support(T dx, T dy, T dz, V3<T>& cur, int& cur_i) const {
+    T best = dot3(cur.x, cur.y, cur.z, dx, dy, dz);
+    int better = -1;
+    const T* p = c;
+#pragma unroll 4
+    for (int i = 0; i < n; ++i, p += 3) {
+      const T sc = dot3(p[0], p[1], p[2], dx, dy, dz);
+      if (sc > best) { best = sc; better = i; }
+    }
+    if (better >= 0) { cur = vertex(better); cur_i = better; }
+  }
+};
+
+template <typename T> struct WarpBody {
+  const T* c; int n; int lane;
+  OGJK_DI V3<T> vertex(int i) const {
+    const T* p = c + 3 * (size_t)i;
+    return V3<T>{p[0], p[1], p[2]};
+  }
+  OGJK_DI void support(T dx, T dy, T dz, V3<T>& cur, int& cur_i) const {
+    T best = dot3(cur.x, cur.y, cur.z, dx, dy, dz);
+    int better = 0x7fffffff;
+#pragma unroll 4
+    for (int i = lane; i < n; i += 32) {
+      const T* p = c + 3 * (size_t)i;
+      const T sc = dot3(p[0], p[1], p[2], dx, dy, dz);
+      if (sc > best) { best = sc; better = i; }
+    }
+    // butterfly argmax: larger value wins, equal values -> lower index
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      const T ob = __shfl_xor_sync(0xffffffffu, best, m);
+      const int oi = __shfl_xor_sync(0xffffffffu, better, m);
+      if (ob > best || (ob == best && oi < better)) { best = ob; better = oi; }
+    }
+    if (better != 0x7fffffff) { cur = vertex(better); cur_i = better; }
+  }
+};
+
+// ---- one GJK query (openGJK.c:941-1046) ---------------------------------------
+// Returns the distance; fills `s` (post-witness simplex) and the witnesses.
+template <typename T, typename Body>
+OGJK_DI T gjk_query(const Body& b1, const Body& b2, Splx<T>& s, V3<T>& wit1, V3<T>& wit2) {
+  V3<T> sa = b1.vertex(0), sb = b2.vertex(0);
+  int ia = 0, ib = 0;
+  V3<T> v = sub(sa, sb);
+  const MV<T> zero = MV<T>{(T)0, (T)0, (T)0, 0, 0};
+  s.n = 1;
+  s.q0 = MV<T>{v.x, v.y, v.z, 0, 0};
+  s.q1 = zero; s.q2 = zero; s.q3 = zero;
+
+  const T er = eps_rel<T>(), ea = eps_abs<T>();
+  const T er2 = er * er;
+  T wmax2 = (T)0;
+  int k = 0;
+  do {
+    k++;
+    b1.support(-v.x, -v.y, -v.z, sa, ia);
+    b2.support(v.x, v.y, v.z, sb, ib);
+    const V3<T> w = sub(sa, sb);
+
+    const T vv = nrm2(v.x, v.y, v.z);
+    const T gap = vv - dot3(v, w);
+    if (gap <= (er * vv) || gap < ea) break;   // :1002-1006
+    if (vv < er2) break;                         // :1008-1010
+
+    push_and_solve(s, MV<T>{w.x, w.y, w.z, ia, ib}, v);
+
+    wmax2 = update_wmax(s, wmax2);
+    if (nrm2(v.x, v.y, v.z) <= (ea * ea * wmax2)) break;  // :1032
+  } while (s.n != 4 && k != kMaxIter);
+
+  const Wts<T> a = witness_weights(s);
+  const V3<T> p0 = b1.vertex(s.q0.ia), r0 = b2.vertex(s.q0.ib);
+  if (a.terms == 1) {
+    wit1 = p0; wit2 = r0;
+  } else {
+    const V3<T> p1 = b1.vertex(s.q1.ia), r1 = b2.vertex(s.q1.ib);
+    if (a.terms == 2) {
+      wit1 = V3<T>{p0.x * a.a0 + p1.x * a.a1, p0.y * a.a0 + p1.y * a.a1, p0.z * a.a0 + p1.z * a.a1};
+      wit2 = V3<T>{r0.x * a.a0 + r1.x * a.a1, r0.y * a.a0 + r1.y * a.a1, r0.z * a.a0 + r1.z * a.a1};
+    } else {
+      const V3<T> p2 = b1.vertex(s.q2.ia), r2 = b2.vertex(s.q2.ib);
+      if (a.terms == 3) {
+        wit1 = V3<T>{p0.x * a.a0 + p1.x * a.a1 + p2.x * a.a2, p0.y * a.a0 + p1.y * a.a1 + p2.y * a.a2,
+                     p0.z * a.a0 + p1.z * a.a1 + p2.z * a.a2};
+        wit2 = V3<T>{r0.x * a.a0 + r1.x * a.a1 + r2.x * a.a2, r0.y * a.a0 + r1.y * a.a1 + r2.y * a.a2,
+                     r0.z * a.a0 + r1.z * a.a1 + r2.z * a.a2};
+      } else {
+        const V3<T> p3 = b1.vertex(s.q3.ia), r3 = b2.vertex(s.q3.ib);
+        wit1 = V3<T>{p0.x * a.a0 + p1.x * a.a1 + p2.x * a.a2 + p3.x * a.a3,
+                     p0.y * a.a0 + p1.y * a.a1 + p2.y * a.a2 + p3.y * a.a3,
+                     p0.z * a.a0 + p1.z * a.a1 + p2.z * a.a2 + p3.z * a.a3};
+        wit2 = V3<T>{r0.x * a.a0 + r1.x * a.a1 + r2.x * a.a2 + r3.x * a.a3,
+                     r0.y * a.a0 + r1.y * a.a1 + r2.y * a.a2 + r3.y * a.a3,
+                     r0.z * a.a0 + r1.z * a.a1 + r2.z * a.a2 + r3.z * a.a3};
+      }
+    }
+  }
+  return sqrt(nrm2(v.x, v.y, v.z));  // :1045 (IEEE sqrt; double rounding via double is innocuous)
+}
+
+template <typename T>
+OGJK_DI void store_simplex(GkSimplex<T>* o, const Splx<T>& s, const V3<T>& w1, const V3<T>& w2) {
+  o->nvrtx = s.n;
+  o->vrtx[0][0] = s.q0.x; o->vrtx[0][1] = s.q0.y; o->vrtx[0][2] = s.q0.z;
+  o->vrtx[1][0] = s.q1.x; o->vrtx[1][1] = s.q1.y; o->vrtx[1][2] = s.q1.z;
+  o->vrtx[2][0] = s.q2.x; o->vrtx[2][1] = s.q2.y; o->vrtx[2][2] = s.q2.z;
+  o->vrtx[3][0] = s.q3.x; o->vrtx[3][1] = s.q3.y; o->vrtx[3][2] = s.q3.z;
+  o->vrtx_idx[0][0] = s.q0.ia; o->vrtx_idx[0][1] = s.q0.ib;
+  o->vrtx_idx[1][0] = s.q1.ia; o->vrtx_idx[1][1] = s.q1.ib;
+  o->vrtx_idx[2][0] = s.q2.ia; o->vrtx_idx[2][1] = s.q2.ib;
+  o->vrtx_idx[3][0] = s.q3.ia; o->vrtx_idx[3][1] = s.q3.ib;
+  o->witnesses[0][0] = w1.x; o->witnesses[0][1] = w1.y; o->witnesses[0][2] = w1.z;
+  o->witnesses[1][0] = w2.x; o->witnesses[1][1] = w2.y; o->witnesses[1][2] = w2.z;
+}
+
+// Work queue slots inside the context's counter block.
+enum { Q_THREAD_HEAD = 0, Q_WARP_HEAD = 1, Q_SMALL_COUNT = 2, Q_LARGE_COUNT = 3, Q_SLOTS = 8 };
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+gjk_thread_kernel(BatchArgs<T> a, const int* __restrict__ list, const unsigned long long* __restrict__ list_count,
+                  unsigned long long* __restrict__ head) {
+  const int lane = threadIdx.x & 31;
+  const long long total = list_count ? (long long)*list_count : a.npairs;
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(head, 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if ((long long)base >= total) break;
+    const long long slot = (long long)base + lane;
+    if (slot < total) {
+      const long long p = list ? (long long)list[slot] : slot;
+      const long long h1 = a.idx1 ? (long long)a.idx1[p] : p;
+      const long long h2 = a.idx2 ? (long long)a.idx2[p] : p;
+      ThreadBody<T> b1{a.coords1 + 3 * a.off1[h1], a.cnt1[h1]};
+      ThreadBody<T> b2{a.coords2 + 3 * a.off2[h2], a.cnt2[h2]};
+      Splx<T> s;
+      V3<T> w1, w2;
+      const T d = gjk_query<T>(b1, b2, s, w1, w2);
+      a.distances[p] = d;
+      if (a.simplices) store_simplex(a.simplices + p, s, w1, w2);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gjk_warp_kernel(BatchArgs<T> a, const int* __restrict__ list, const unsigned long long* __restrict__ list_count,
+                unsigned long long* __restrict__ head) {
+  const int lane = threadIdx.x & 31;
+  const long long total = list_count ? (long long)*list_count : a.npairs;
+  for (;;) {
+    unsigned long long slot = 0;
+    if (lane == 0) slot = atomicAdd(head, 1ull);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if ((long long)slot >= total) break;
+    const long long p = list ? (long long)list[slot] : (long long)slot;
+    const long long h1 = a.idx1 ? (long long)a.idx1[p] : p;
+    const long long h2 = a.idx2 ? (long long)a.idx2[p] : p;
+    WarpBody<T> b1{a.coords1 + 3 * a.off1[h1], a.cnt1[h1], lane};
+    WarpBody<T> b2{a.coords2 + 3 * a.off2[h2], a.cnt2[h2], lane};
+    Splx<T> s;
+    V3<T> w1, w2;
+    const T d = gjk_query<T>(b1, b2, s, w1, w2);
+    if (lane == 0) {
+      a.distances[p] = d;
+      if (a.simplices) store_simplex(a.simplices + p, s, w1, w2);
+    }
+  }
+}
+
+// Batch scheduler, stage 1: split the pair list by total vertex count so that
+// thread-per-pair warps do not wait on one large hull (north_star item 5).
+// Warp-aggregated appends keep the in-warp pair order.
+template <typename T>
+__global__ void __launch_bounds__(256)
+classify_kernel(BatchArgs<T> a, int threshold, int* __restrict__ small_list, int* __restrict__ large_list,
+                unsigned long long* __restrict__ counters) {
+  const int lane = threadIdx.x & 31;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long rounded = (a.npairs + 31) & ~31ll;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < rounded; p += stride) {
+    bool valid = p < a.npairs, big = false;
+    if (valid) {
+      const long long h1 = a.idx1 ? (long long)a.idx1[p] : p;
+      const long long h2 = a.idx2 ? (long long)a.idx2[p] : p;
+      big = (a.cnt1[h1] + a.cnt2[h2]) >= threshold;
+    }
+    const unsigned mb = __ballot_sync(0xffffffffu, valid && big);
+    const unsigned ms = __ballot_sync(0xffffffffu, valid && !big);
+    unsigned long long bb = 0, bs = 0;
+    if (lane == 0) {
+      if (mb) bb = atomicAdd(&counters[Q_LARGE_COUNT], (unsigned long long)__popc(mb));
+      if (ms) bs = atomicAdd(&counters[Q_SMALL_COUNT], (unsigned long long)__popc(ms));
+    }
+    bb = __shfl_sync(0xffffffffu, bb, 0);
+    bs = __shfl_sync(0xffffffffu, bs, 0);
+    const unsigned below = (1u << lane) - 1u;
+    if (valid && big) large_list[bb + __popc(mb & below)] = (int)p;
+    if (valid && !big) small_list[bs + __popc(ms & below)] = (int)p;
+  }
+}
+
+}  // namespace ogjk

@@ -169,7 +169,7 @@ def tiny_bodies(npairs_per_shape=200, seed=7, scale=1.0, dtype=np.float64):
     off = _offsets(cnt)
     pts = scale * rng.random((int(cnt.sum()), 3))
     pa = np.arange(0, cnt.shape[0], 2, dtype=np.int32)
-    return Workload("tiny", pts.astype(dtype), off, cnt, pa, pa + 1)
+    return Workload(f"tiny_s{scale:g}", pts.astype(dtype), off, cnt, pa, pa + 1)
 
 
 def from_bodies(bodies_a, bodies_b, dtype=np.float64, name="explicit"):

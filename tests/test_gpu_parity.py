@@ -1,0 +1,195 @@
+"""GPU parity: the CUDA kernels, called through the C ABI, against the CPU
+oracle and the committed outputs of the unmodified reference.
+
+Bar (BASELINE.json north_star): distance/witness within 1e-10 (fp64) / 1e-5
+(fp32) relative, flags and support indices bit-exact.  Because the kernels keep
+the reference's operation order un-fused, the tests assert the stronger
+property: every byte of distance and gkSimplex equal."""
+import os
+
+import numpy as np
+import pytest
+
+from opengjk_b200 import api, workloads as W
+from oracle.pyoracle import Oracle, Reference
+from tests.golden.make_golden import checksum, golden_workloads
+from tests.test_oracle import ANALYTIC, rotated_cubes
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+PRECS = [("f64", np.float64), ("f32", np.float32)]
+REL = {"f64": 1e-10, "f32": 1e-5}
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = api.Engine(0)
+    yield e
+    e.close()
+
+
+def _assert_same(name, d, s, dref, sref, prec):
+    # tolerance form of the bar first (readable failure), then byte equality
+    ok = ~np.isnan(dref)
+    np.testing.assert_allclose(d[ok], dref[ok], rtol=REL[prec], atol=0, err_msg=name)
+    assert np.array_equal(s["nvrtx"], sref["nvrtx"]), name
+    assert np.array_equal((d > np.finfo(d.dtype).eps), (dref > np.finfo(d.dtype).eps)), name  # EPA gate flag
+    assert d.tobytes() == dref.tobytes(), f"{name}: distance bits differ"
+    bad = np.nonzero((s.view(np.uint8).reshape(len(s), -1) != sref.view(np.uint8).reshape(len(s), -1)).any(1))[0]
+    assert bad.size == 0, f"{name}: {bad.size} simplices differ, first {bad[:5]}"
+
+
+def _gpu(eng, w, mode=api.MODE_AUTO, threshold=None):
+    """Device-resident call through ogjk_gjk_device_* (torch only holds the memory)."""
+    import torch
+    prec = "f64" if w.coords.dtype == np.float64 else "f32"
+    sdt = api.SIMPLEX_F64 if prec == "f64" else api.SIMPLEX_F32
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    coords, off, cnt, pa, pb = t(w.coords.reshape(-1)), t(w.off), t(w.cnt), t(w.pa), t(w.pb)
+    simp = torch.zeros(w.npairs * sdt.itemsize, dtype=torch.uint8, device=dev)
+    dist = torch.zeros(w.npairs, dtype=coords.dtype, device=dev)
+    if threshold:
+        eng.set_warp_threshold(threshold)
+    eng.gjk_device(prec, w.npairs, coords, off, cnt, pa, coords, off, cnt, pb, simp, dist, mode,
+                   torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    if threshold:
+        eng.set_warp_threshold(192)
+    return dist.cpu().numpy(), simp.cpu().numpy().view(sdt).reshape(-1)
+
+
+@pytest.mark.parametrize("prec,dt", PRECS)
+def test_committed_reference_outputs(eng, prec, dt):
+    gold = np.load(os.path.join(GOLD, f"gjk_golden_{prec}.npz"))
+    for w in golden_workloads(dt):
+        assert checksum(w) == bytes(gold[w.name + "/sha"]).decode()
+        sref = gold[w.name + "/simplex"].copy().view(api.SIMPLEX_F64 if prec == "f64" else api.SIMPLEX_F32).reshape(-1)
+        for mode in (api.MODE_AUTO, api.MODE_THREAD, api.MODE_WARP):
+            d, s = _gpu(eng, w, mode)
+            _assert_same(f"{w.name}/mode{mode}", d, s, gold[w.name + "/dist"], sref, prec)
+
+
+@pytest.mark.parametrize("prec,dt", PRECS)
+def test_config1_example(eng, prec, dt):
+    d, s = api.single_query(W.USER_P, W.USER_Q, dt, eng)
+    assert f"{d:f}" == "3.653650"  # README.md:55-59
+    assert int(s["nvrtx"]) == 2 and s["vrtx_idx"][:2].tolist() == [[6, 6], [1, 1]]
+    if prec == "f64":
+        assert d == 3.6536497222945008
+    else:
+        assert np.float32(d) == np.float32(3.6536495685577393)
+
+
+@pytest.mark.parametrize("prec,dt", PRECS)
+@pytest.mark.parametrize("maker", [
+    lambda dt: W.mixed_hulls(200000, seed=101, dtype=dt),
+    lambda dt: W.boxes(200000, True, 102, dtype=dt),
+    lambda dt: W.boxes(200000, False, 103, dtype=dt),
+    lambda dt: W.random_hulls(100000, 8, 64, 104, 1.0, dt, 0.5),
+    lambda dt: W.tiny_bodies(400, 105, 1.0, dt),
+    lambda dt: W.tiny_bodies(400, 106, 1e4, dt),
+    lambda dt: W.large_hull_pool(2000, 64, 1000, 4000, 107, dtype=dt),
+    lambda dt: W.random_hulls(20000, 1, 300, 108, 3.0, dt),
+], ids=["mixed", "boxes_oriented", "boxes_aligned", "intersecting", "tiny", "tiny_1e4", "large_pool", "ragged_1_300"])
+def test_random_batches_vs_oracle(eng, prec, dt, maker):
+    w = maker(dt)
+    o = Oracle(prec)
+    dref, sref = o.batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1)
+    d, s = _gpu(eng, w)
+    _assert_same(w.name, d, s, dref, sref, prec)
+
+
+@pytest.mark.parametrize("prec,dt", PRECS)
+def test_scheduler_threshold_does_not_change_results(eng, prec, dt):
+    w = W.random_hulls(30000, 4, 200, 55, 3.0, dt)
+    base = _gpu(eng, w, api.MODE_THREAD)
+    for thr in (2, 64, 150, 100000):
+        d, s = _gpu(eng, w, api.MODE_AUTO, threshold=thr)
+        _assert_same(f"thr{thr}", d, s, base[0], base[1], prec)
+
+
+def test_live_reference_library_if_present(eng):
+    if not Reference.available("f64"):
+        pytest.skip("oracle/_ref not shipped")
+    for prec, dt in PRECS:
+        w = W.mixed_hulls(50000, seed=77, dtype=dt)
+        dref, sref = Reference(prec).batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1)
+        d, s = _gpu(eng, w)
+        _assert_same("live_ref", d, s, dref, sref, prec)
+
+
+@pytest.mark.parametrize("case", ANALYTIC, ids=lambda c: c[0])
+def test_analytic_distances_fp64(eng, case):
+    _, a, b, exp, _ = case
+    d, _ = api.single_query(a, b, np.float64, eng)
+    assert np.isclose(d, exp, atol=1e-12)
+
+
+def test_rotated_cubes_gap_sweep(eng):
+    cubes = rotated_cubes()
+    A, B, want = [], [], []
+    for c0 in range(4):
+        for c1 in range(4):
+            dx = cubes[c0][:, 0].max() - cubes[c1][:, 0].min()
+            for delta in (1e8, 1.0, 1e-4, 1e-8, 1e-12):
+                A.append(cubes[c0]); B.append(cubes[c1] + np.array([dx + delta, 0, 0])); want.append(delta)
+    r = api.compute_minimum_distance(np.stack(A), np.stack(B), np.float64, eng)
+    assert np.allclose(r["distances"], want)
+
+
+@pytest.mark.parametrize("prec,dt", PRECS)
+def test_host_entry_points_agree(eng, prec, dt):
+    """Flat host API, struct-array API (plain + indexed) and the reference-style
+    dict API all give the oracle's bytes."""
+    w = W.mixed_hulls(3000, seed=9, dtype=dt)
+    o = Oracle(prec)
+    dref, sref = o.batch(w.coords, w.off, w.cnt, w.pa, w.pb)
+    d, s = eng.run_workload(w)
+    _assert_same("flat_host", d, s, dref, sref, prec)
+    A = [w.polytope(h) for h in w.pa]
+    B = [w.polytope(h) for h in w.pb]
+    d, s = api.compute_minimum_distance_structs(A, B, dt, eng)
+    _assert_same("struct_arrays", d, s, dref, sref, prec)
+    bodies = [w.polytope(h) for h in range(w.npoly)]
+    d, s = api.compute_minimum_distance_indexed_structs(bodies, np.stack([w.pa, w.pb], 1), dt, eng)
+    _assert_same("struct_indexed", d, s, dref, sref, prec)
+    r = api.compute_minimum_distance(A, B, dt, eng)
+    assert r["distances"].tobytes() == dref.tobytes()
+    assert np.array_equal(r["simplex_nvrtx"], sref["nvrtx"])
+    r = api.compute_minimum_distance_indexed(bodies, np.stack([w.pa, w.pb], 1), dt, eng)
+    assert r["distances"].tobytes() == dref.tobytes()
+
+
+def test_empty_and_degenerate_batches(eng):
+    # n == 0 is a silent no-op like the reference (gpu/opengjk_gpu.cu:2984)
+    r = api.compute_minimum_distance(np.zeros((0, 4, 3), np.float32), np.zeros((0, 4, 3), np.float32), engine=eng)
+    assert r["distances"].shape == (0,)
+    # identical single points: distance 0
+    d, s = api.single_query([[1, 2, 3]], [[1, 2, 3]], np.float64, eng)
+    assert d == 0.0 and int(s["nvrtx"]) == 1
+    # one big hull vs a point (ragged extremes in one batch)
+    rng = np.random.default_rng(0)
+    big = rng.normal(size=(5000, 3)); big /= np.linalg.norm(big, axis=1, keepdims=True)
+    o = Oracle("f64")
+    dref, sref, _ = o.gjk(big, [[3.0, 0, 0]])
+    d, s = api.single_query(big, [[3.0, 0, 0]], np.float64, eng)
+    assert d == dref and s.tobytes() == sref.tobytes()
+
+
+def test_full_size_config2_properties(eng):
+    """BASELINE config #2 at full size (1 M pairs, fp64): size-independent
+    properties -- witness gap equals distance, distances of separated/overlapping
+    slices have the right sign structure -- plus oracle equality on a strided sample."""
+    w = W.mixed_hulls(1_000_000, seed=42, dtype=np.float64)
+    d, s = _gpu(eng, w)
+    gap = np.linalg.norm(s["witnesses"][:, 0] - s["witnesses"][:, 1], axis=1)
+    ok = ~np.isnan(d)
+    assert ok.mean() > 0.999
+    assert np.all(np.abs(gap[ok] - d[ok]) <= 1e-9)
+    assert np.all(d[900_000:] > 2.0)            # centre scale 10: all separated
+    assert (s["nvrtx"][800_000:900_000] == 4).mean() > 0.95   # centre scale 1: intersecting
+    sel = np.arange(0, w.npairs, 37)
+    o = Oracle("f64")
+    dref, sref = o.batch(w.coords, w.off, w.cnt, w.pa[sel], w.pb[sel], nthreads=os.cpu_count() or 1)
+    _assert_same("config2_sample", d[sel], s[sel], dref, sref, "f64")
