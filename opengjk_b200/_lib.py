@@ -33,6 +33,8 @@ assert SIMPLEX_F32.itemsize == 108 and SIMPLEX_F64.itemsize == 184
 EXPORTS = [
     "ogjk_last_error", "ogjk_version", "ogjk_ctx_create", "ogjk_ctx_destroy", "ogjk_ctx_device",
     "ogjk_ctx_launch_count", "ogjk_ctx_set_warp_threshold", "ogjk_ctx_set_timing", "ogjk_ctx_last_timing",
+    "ogjk_ctx_set_classes", "ogjk_store_create_f32", "ogjk_store_create_f64", "ogjk_store_destroy", "ogjk_store_bytes",
+    "ogjk_store_num_polytopes", "ogjk_store_gjk_f32", "ogjk_store_gjk_f64",
     "ogjk_gjk_device_f32", "ogjk_gjk_device_f64", "ogjk_gjk_host_f32", "ogjk_gjk_host_f64",
     "ogjk_compute_minimum_distance_f32", "ogjk_compute_minimum_distance_f64",
     "ogjk_compute_minimum_distance_indexed_f32", "ogjk_compute_minimum_distance_indexed_f64",
@@ -60,9 +62,19 @@ def lib():
     L.ogjk_ctx_set_warp_threshold.argtypes = [C.c_void_p, C.c_int]
     L.ogjk_ctx_set_timing.argtypes = [C.c_void_p, C.c_int]
     L.ogjk_ctx_last_timing.argtypes = [C.c_void_p, C.c_void_p]
+    L.ogjk_ctx_set_classes.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.ogjk_store_destroy.argtypes = [C.c_void_p]
+    L.ogjk_store_destroy.restype = None
+    L.ogjk_store_bytes.argtypes = [C.c_void_p]
+    L.ogjk_store_bytes.restype = C.c_int64
+    L.ogjk_store_num_polytopes.argtypes = [C.c_void_p]
+    L.ogjk_store_num_polytopes.restype = C.c_int64
     vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
     for sfx in ("f32", "f64"):
-        getattr(L, f"ogjk_gjk_device_{sfx}").argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
+        getattr(L, f"ogjk_gjk_device_{sfx}").argtypes = [vp, i64, vp, vp, vp, i64, i64, vp, vp, vp, vp, i64, i64, vp,
+                                                         vp, vp, i32, vp]
+        getattr(L, f"ogjk_store_create_{sfx}").argtypes = [vp, i64, i64, vp, vp, vp, i32, vp, C.POINTER(vp)]
+        getattr(L, f"ogjk_store_gjk_{sfx}").argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp]
         getattr(L, f"ogjk_gjk_host_{sfx}").argtypes = [vp, i64, vp, vp, vp, i64, i64, vp, vp, vp, vp, i64, i64, vp,
                                                        vp, vp]
         getattr(L, f"ogjk_compute_minimum_distance_{sfx}").argtypes = [vp, i32, vp, vp, vp, vp]

@@ -57,20 +57,56 @@ class Engine:
         check(_lib.lib().ogjk_ctx_set_timing(self._h, int(bool(enable))))
 
     def last_timing(self):
-        """{classify, thread kernel, warp kernel} milliseconds of the last device call."""
-        ms = (C.c_float * 3)()
+        """Milliseconds of the last device call: repack, sort, and one entry per size class."""
+        ms = (C.c_float * 8)()
         check(_lib.lib().ogjk_ctx_last_timing(self._h, ms))
-        return {"classify": ms[0], "thread": ms[1], "warp": ms[2]}
+        return {"repack": ms[0], "sort": ms[1], "classes": [ms[i] for i in range(2, 8)]}
 
     def set_warp_threshold(self, nverts):
         check(_lib.lib().ogjk_ctx_set_warp_threshold(self._h, int(nverts)))
 
-    # -- device-resident batch (torch CUDA tensors or raw device pointers) ------
+    def set_classes(self, table):
+        """table: list of (hi_key, lanes); see ogjk_ctx_set_classes."""
+        n = len(table)
+        hi = (C.c_int * n)(*[int(t[0]) for t in table])
+        ln = (C.c_int * n)(*[int(t[1]) for t in table])
+        check(_lib.lib().ogjk_ctx_set_classes(self._h, n, hi, ln))
+
+    # -- device-resident batch over raw xyz-interleaved pools (torch CUDA tensors or raw pointers)
     def gjk_device(self, prec, npairs, coords1, off1, cnt1, idx1, coords2, off2, cnt2, idx2, simplices, distances,
-                   mode=MODE_AUTO, stream=0):
+                   mode=MODE_AUTO, stream=0, npoly1=None, nverts1=None, npoly2=None, nverts2=None):
+        def size(t, given, div=1):
+            if given is not None:
+                return int(given)
+            return int(t.numel() if hasattr(t, "numel") else t.size) // div
         fn = getattr(_lib.lib(), f"ogjk_gjk_device_{prec}")
-        check(fn(self._h, int(npairs), _p(coords1), _p(off1), _p(cnt1), _p(idx1), _p(coords2), _p(off2), _p(cnt2),
-                 _p(idx2), _p(simplices), _p(distances), int(mode), C.c_void_p(int(stream))))
+        check(fn(self._h, int(npairs), _p(coords1), _p(off1), _p(cnt1), size(cnt1, npoly1), size(coords1, nverts1, 3),
+                 _p(idx1), _p(coords2), _p(off2), _p(cnt2), size(cnt2, npoly2), size(coords2, nverts2, 3), _p(idx2),
+                 _p(simplices), _p(distances), int(mode), C.c_void_p(int(stream))))
+
+    # -- packed store -------------------------------------------------------------
+    def store_create(self, coords, off, cnt, stream=0):
+        """coords/off/cnt: numpy arrays (host) or torch CUDA tensors (device)."""
+        on_device = not isinstance(coords, np.ndarray)
+        if on_device:
+            prec = "f64" if coords.element_size() == 8 else "f32"
+            npoly, nverts = int(cnt.numel()), int(coords.numel()) // 3
+        else:
+            coords = np.ascontiguousarray(coords)
+            prec = _PREC[coords.dtype][0]
+            off = np.ascontiguousarray(off, dtype=np.int64)
+            cnt = np.ascontiguousarray(cnt, dtype=np.int32)
+            npoly, nverts = int(cnt.shape[0]), int(coords.size) // 3
+        h = C.c_void_p()
+        fn = getattr(_lib.lib(), f"ogjk_store_create_{prec}")
+        check(fn(self._h, npoly, nverts, _p(coords), _p(off), _p(cnt), int(on_device), C.c_void_p(int(stream)),
+                 C.byref(h)))
+        return Store(h, prec)
+
+    def store_gjk(self, s1, idx1, s2, idx2, npairs, simplices, distances, stream=0):
+        fn = getattr(_lib.lib(), f"ogjk_store_gjk_{s1.prec}")
+        check(fn(self._h, s1._h, _p(idx1), s2._h, _p(idx2), int(npairs), _p(simplices), _p(distances),
+                 C.c_void_p(int(stream))))
 
     # -- host buffers, one pool shared by both bodies (indexed form) -------------
     def gjk_host(self, coords, off, cnt, pa, pb, want_simplices=True, out=None):
@@ -94,6 +130,32 @@ class Engine:
 
     def run_workload(self, w, want_simplices=True):
         return self.gjk_host(w.coords, w.off, w.cnt, w.pa, w.pb, want_simplices)
+
+
+class Store:
+    """Handle of a packed device-resident polytope pool (ogjk_store)."""
+
+    def __init__(self, handle, prec):
+        self._h, self.prec = handle, prec
+
+    @property
+    def nbytes(self):
+        return int(_lib.lib().ogjk_store_bytes(self._h))
+
+    @property
+    def num_polytopes(self):
+        return int(_lib.lib().ogjk_store_num_polytopes(self._h))
+
+    def close(self):
+        if self._h:
+            _lib.lib().ogjk_store_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _default = {}

@@ -65,18 +65,37 @@ struct PinBuf {
 
 }  // namespace
 
+constexpr int kPhases = 8;   // timing slots: pack, sort, then up to six size classes
+constexpr int kMaxClasses = 6;
+
+struct ogjk_store_ {
+  int device = 0;
+  int prec = 0;  // 4 = fp32, 8 = fp64
+  long long npoly = 0;
+  long long nverts = 0;       // true vertices
+  long long capacity = 0;     // elements allocated in `data`
+  DevBuf data, boff, cnt, scan_tmp;
+};
+
 struct ogjk_ctx_ {
   int device = 0;
   int sm_count = 148;
-  int warp_threshold = 192;  // body1+body2 vertices from which a whole warp scans one pair
+  int warp_threshold = 192;  // raw modes only
   long long launches = 0;
-  // optional per-kernel timing: events bracket each launch on the caller's stream
+  // scheduler classes: pairs with sort key <= hi[c] (and > hi[c-1]) run with lanes[c]
+  // cooperating lanes per pair; lanes 0 = register-resident thread-per-pair kernel.
+  int nclasses = 5;
+  int class_hi[kMaxClasses] = {4, 24, 64, 192, 2048, 2048};
+  int class_lanes[kMaxClasses] = {0, 4, 8, 16, 32, 32};
   bool timing = false;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  int timed_mask = 0;  // bit k set: phase k (0 classify, 1 thread kernel, 2 warp kernel) was launched
+  cudaEvent_t ev[2 * kPhases] = {};
+  int timed_mask = 0;
   cudaStream_t own_stream = nullptr;  // used by the host-buffer entry points
-  DevBuf counters;                    // Q_SLOTS x u64
-  DevBuf small_list, large_list;      // pair ids per bin
+  DevBuf counters;                    // 16 x u64 work-queue heads
+  DevBuf sort_tmp;                    // hist | start | cursor (u32 each, kMaxKey+2)
+  DevBuf sorted_list;                 // pair ids, size-sorted
+  DevBuf small_list, large_list;      // raw modes
+  ogjk_store_ scratch1, scratch2;     // raw device arrays are repacked into these
   // staging for the host-buffer paths
   DevBuf d_coords1, d_coords2, d_off1, d_off2, d_cnt1, d_cnt2, d_idx1, d_idx2, d_simp, d_dist;
   PinBuf h_stage;
@@ -86,75 +105,153 @@ namespace {
 
 using namespace ogjk;
 
+void mark(ogjk_ctx* ctx, cudaStream_t st, int phase, int edge) {
+  if (ctx->timing) {
+    cudaEventRecord(ctx->ev[2 * phase + edge], st);
+    ctx->timed_mask |= 1 << phase;
+  }
+}
+
+int reset_counters(ogjk_ctx* ctx, cudaStream_t st, unsigned long long** out) {
+  int rc = ctx->counters.reserve(16 * sizeof(unsigned long long));
+  if (rc) return rc;
+  *out = static_cast<unsigned long long*>(ctx->counters.p);
+  CU(cudaMemsetAsync(*out, 0, 16 * sizeof(unsigned long long), st));
+  return OGJK_OK;
+}
+
+// Raw modes: the first-generation kernels that read xyz-interleaved blocks directly.
 template <typename T>
-int launch_batch(ogjk_ctx* ctx, const BatchArgs<T>& a, int mode, cudaStream_t st) {
+int launch_raw(ogjk_ctx* ctx, const BatchArgs<T>& a, int mode, cudaStream_t st) {
+  unsigned long long* counters = nullptr;
+  int rc = reset_counters(ctx, st, &counters);
+  if (rc) return rc;
+  const int sm = ctx->sm_count;
+  if (mode == OGJK_MODE_THREAD_PER_PAIR) {
+    long long blocks = (a.npairs + 127) / 128, cap = (long long)sm * 16;
+    mark(ctx, st, 2, 0);
+    gjk_thread_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, nullptr, nullptr, counters + 0);
+    mark(ctx, st, 2, 1);
+  } else {
+    long long blocks = (a.npairs + 7) / 8, cap = (long long)sm * 8;
+    mark(ctx, st, 3, 0);
+    gjk_warp_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(a, nullptr, nullptr, counters + 1);
+    mark(ctx, st, 3, 1);
+  }
+  ctx->launches += 1;
+  CU(cudaGetLastError());
+  return OGJK_OK;
+}
+
+// Build a packed store from xyz-interleaved DEVICE arrays.  `exact` sizes the
+// allocation from the scanned total (one stream sync); otherwise an upper bound
+// (every polytope padded by 3 vertices) keeps the call asynchronous.
+template <typename T>
+int store_build(ogjk_ctx* ctx, ogjk_store_* s, long long npoly, long long nverts, const T* coords, const int64_t* off,
+                const int* cnt, bool exact, cudaStream_t st) {
+  s->device = ctx->device;
+  s->prec = (int)sizeof(T);
+  s->npoly = npoly;
+  s->nverts = nverts;
+  int rc;
+  if ((rc = s->boff.reserve((size_t)npoly * sizeof(long long)))) return rc;
+  if ((rc = s->cnt.reserve((size_t)npoly * sizeof(int)))) return rc;
+  const long long nblocks = (npoly + kScanBlock - 1) / kScanBlock;
+  if ((rc = s->scan_tmp.reserve((size_t)(nblocks + 1) * sizeof(long long)))) return rc;
+  CU(cudaMemcpyAsync(s->cnt.p, cnt, (size_t)npoly * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  auto* sums = static_cast<long long*>(s->scan_tmp.p);
+  auto* boff = static_cast<long long*>(s->boff.p);
+  scan_block_sums_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(cnt, npoly, sums);
+  scan_spine_kernel<<<1, 1024, 0, st>>>(sums, nblocks, sums + nblocks);
+  scan_finish_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(cnt, npoly, sums, boff);
+  long long elems = 3 * (nverts + 3 * npoly);
+  if (exact) {
+    long long total = 0;
+    CU(cudaMemcpyAsync(&total, sums + nblocks, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    elems = total;
+  }
+  if ((rc = s->data.reserve((size_t)(elems > 0 ? elems : 4) * sizeof(T)))) return rc;
+  s->capacity = elems;
+  long long pblocks = (npoly * 8 + 255) / 256, cap = (long long)ctx->sm_count * 32;
+  pack_kernel<T><<<(unsigned)(pblocks < cap ? pblocks : cap), 256, 0, st>>>(
+      coords, reinterpret_cast<const long long*>(off), cnt, npoly, boff, static_cast<T*>(s->data.p));
+  ctx->launches += 4;
+  CU(cudaGetLastError());
+  return OGJK_OK;
+}
+
+template <typename T> StoreView<T> view_of(const ogjk_store_* s) {
+  return StoreView<T>{static_cast<const T*>(s->data.p), static_cast<const long long*>(s->boff.p),
+                      static_cast<const int*>(s->cnt.p)};
+}
+
+template <typename T, int G>
+void launch_group(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const unsigned* b, const unsigned* e,
+                  unsigned long long* head, cudaStream_t st) {
+  long long blocks = (a.npairs * G + 127) / 128, cap = (long long)ctx->sm_count * 16;
+  gjk_group_kernel<T, G><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, list, b, e, head);
+}
+
+// The batch scheduler: counting sort by size, then one launch per size class.
+template <typename T>
+int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
   if (a.npairs <= 0) return OGJK_OK;
   if (a.npairs > 0x7fffffffll) return fail(OGJK_ERR_ARG, "npairs exceeds 2^31-1 per call%s");
-  int rc = ctx->counters.reserve(Q_SLOTS * sizeof(unsigned long long));
+  unsigned long long* counters = nullptr;
+  int rc = reset_counters(ctx, st, &counters);
   if (rc) return rc;
-  auto* counters = static_cast<unsigned long long*>(ctx->counters.p);
-  CU(cudaMemsetAsync(counters, 0, Q_SLOTS * sizeof(unsigned long long), st));
+  const size_t nkeys = kMaxKey + 2;
+  if ((rc = ctx->sort_tmp.reserve(3 * nkeys * sizeof(unsigned)))) return rc;
+  if ((rc = ctx->sorted_list.reserve((size_t)a.npairs * sizeof(int)))) return rc;
+  unsigned* hist = static_cast<unsigned*>(ctx->sort_tmp.p);
+  unsigned* start = hist + nkeys;
+  unsigned* cursor = start + nkeys;
+  int* sorted = static_cast<int*>(ctx->sorted_list.p);
 
-  const int sm = ctx->sm_count;
-  auto thread_grid = [&](long long n) {
-    long long blocks = (n + 127) / 128;
-    long long cap = (long long)sm * 16;
-    return (unsigned)(blocks < cap ? blocks : cap);
-  };
-  auto warp_grid = [&](long long n) {
-    long long blocks = (n + 7) / 8;
-    long long cap = (long long)sm * 8;
-    return (unsigned)(blocks < cap ? blocks : cap);
-  };
+  mark(ctx, st, 1, 0);
+  CU(cudaMemsetAsync(hist, 0, nkeys * sizeof(unsigned), st));
+  const long long per_block = (long long)kSortBlock * kSortItems;
+  const unsigned sblocks = (unsigned)((a.npairs + per_block - 1) / per_block);
+  sort_hist_kernel<T><<<sblocks, kSortBlock, 0, st>>>(a.s1, a.s2, a.idx1, a.idx2, a.npairs, hist);
+  sort_scan_kernel<<<1, 1024, 0, st>>>(hist, start, cursor);
+  sort_scatter_kernel<T><<<sblocks, kSortBlock, 0, st>>>(a.s1, a.s2, a.idx1, a.idx2, a.npairs, start, cursor, sorted);
+  mark(ctx, st, 1, 1);
+  ctx->launches += 3;
 
-  ctx->timed_mask = 0;
-  auto mark = [&](int phase, int edge) {
-    if (ctx->timing) {
-      cudaEventRecord(ctx->ev[2 * phase + edge], st);
-      ctx->timed_mask |= 1 << phase;
+  // start[k] = number of pairs with key > k  =>  class (lo, hi] occupies [start[hi], start[lo])
+  int lo = 0;
+  for (int c = 0; c < ctx->nclasses; ++c) {
+    const int hi = ctx->class_hi[c] > kMaxKey ? kMaxKey : ctx->class_hi[c];
+    if (hi <= lo) continue;
+    const unsigned* b = start + hi;
+    const unsigned* e = start + lo;
+    unsigned long long* head = counters + c;
+    mark(ctx, st, 2 + c, 0);
+    switch (ctx->class_lanes[c]) {
+      case 0: {
+        long long blocks = (a.npairs + 127) / 128, cap = (long long)ctx->sm_count * 16;
+        gjk_small_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, sorted, b, e, head);
+      } break;
+      case 1: launch_group<T, 1>(ctx, a, sorted, b, e, head, st); break;
+      case 2: launch_group<T, 2>(ctx, a, sorted, b, e, head, st); break;
+      case 4: launch_group<T, 4>(ctx, a, sorted, b, e, head, st); break;
+      case 8: launch_group<T, 8>(ctx, a, sorted, b, e, head, st); break;
+      case 16: launch_group<T, 16>(ctx, a, sorted, b, e, head, st); break;
+      default: launch_group<T, 32>(ctx, a, sorted, b, e, head, st); break;
     }
-  };
-
-  if (mode == OGJK_MODE_THREAD_PER_PAIR) {
-    mark(1, 0);
-    gjk_thread_kernel<T><<<thread_grid(a.npairs), 128, 0, st>>>(a, nullptr, nullptr, counters + Q_THREAD_HEAD);
-    mark(1, 1);
+    mark(ctx, st, 2 + c, 1);
     ctx->launches += 1;
-  } else if (mode == OGJK_MODE_WARP_PER_PAIR) {
-    mark(2, 0);
-    gjk_warp_kernel<T><<<warp_grid(a.npairs), 256, 0, st>>>(a, nullptr, nullptr, counters + Q_WARP_HEAD);
-    mark(2, 1);
-    ctx->launches += 1;
-  } else {
-    rc = ctx->small_list.reserve((size_t)a.npairs * sizeof(int));
-    if (rc) return rc;
-    rc = ctx->large_list.reserve((size_t)a.npairs * sizeof(int));
-    if (rc) return rc;
-    int* sl = static_cast<int*>(ctx->small_list.p);
-    int* ll = static_cast<int*>(ctx->large_list.p);
-    long long cblocks = (a.npairs + 255) / 256;
-    if (cblocks > (long long)sm * 32) cblocks = (long long)sm * 32;
-    mark(0, 0);
-    classify_kernel<T><<<(unsigned)cblocks, 256, 0, st>>>(a, ctx->warp_threshold, sl, ll, counters);
-    mark(0, 1);
-    // Both consumers size their loops from the device-side counts; grids are
-    // bounded by the SM count, so an empty bin costs one short launch.
-    mark(1, 0);
-    gjk_thread_kernel<T><<<thread_grid(a.npairs), 128, 0, st>>>(a, sl, counters + Q_SMALL_COUNT, counters + Q_THREAD_HEAD);
-    mark(1, 1);
-    mark(2, 0);
-    gjk_warp_kernel<T><<<warp_grid(a.npairs), 256, 0, st>>>(a, ll, counters + Q_LARGE_COUNT, counters + Q_WARP_HEAD);
-    mark(2, 1);
-    ctx->launches += 3;
+    lo = hi;
   }
   CU(cudaGetLastError());
   return OGJK_OK;
 }
 
 template <typename T, typename S>
-int gjk_device(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t* off1, const int* cnt1, const int* idx1,
-               const T* coords2, const int64_t* off2, const int* cnt2, const int* idx2, S* simplices, T* distances,
-               int mode, void* stream) {
+int gjk_device(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t* off1, const int* cnt1, int64_t npoly1,
+               int64_t nverts1, const int* idx1, const T* coords2, const int64_t* off2, const int* cnt2, int64_t npoly2,
+               int64_t nverts2, const int* idx2, S* simplices, T* distances, int mode, void* stream) {
   if (!ctx) return fail(OGJK_ERR_ARG, "ctx is NULL%s");
   if (npairs < 0) return fail(OGJK_ERR_ARG, "npairs < 0%s");
   if (npairs == 0) return OGJK_OK;
@@ -162,13 +259,34 @@ int gjk_device(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t* o
     return fail(OGJK_ERR_ARG, "NULL device pointer%s");
   if (mode < OGJK_MODE_AUTO || mode > OGJK_MODE_WARP_PER_PAIR) return fail(OGJK_ERR_ARG, "bad mode%s");
   CU(cudaSetDevice(ctx->device));
-  BatchArgs<T> a;
-  a.coords1 = coords1; a.off1 = reinterpret_cast<const long long*>(off1); a.cnt1 = cnt1; a.idx1 = idx1;
-  a.coords2 = coords2; a.off2 = reinterpret_cast<const long long*>(off2); a.cnt2 = cnt2; a.idx2 = idx2;
-  a.simplices = reinterpret_cast<GkSimplex<T>*>(simplices);
-  a.distances = distances;
-  a.npairs = npairs;
-  return launch_batch<T>(ctx, a, mode, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ctx->timed_mask = 0;
+  if (mode != OGJK_MODE_AUTO) {
+    BatchArgs<T> a;
+    a.coords1 = coords1; a.off1 = reinterpret_cast<const long long*>(off1); a.cnt1 = cnt1; a.idx1 = idx1;
+    a.coords2 = coords2; a.off2 = reinterpret_cast<const long long*>(off2); a.cnt2 = cnt2; a.idx2 = idx2;
+    a.simplices = reinterpret_cast<GkSimplex<T>*>(simplices);
+    a.distances = distances;
+    a.npairs = npairs;
+    if (npairs > 0x7fffffffll) return fail(OGJK_ERR_ARG, "npairs exceeds 2^31-1 per call%s");
+    return launch_raw<T>(ctx, a, mode, st);
+  }
+  // AUTO: repack the raw pools into the context's scratch stores, then schedule.
+  if (npoly1 <= 0 || npoly2 <= 0) return fail(OGJK_ERR_ARG, "AUTO mode needs the pool sizes (npoly, nverts)%s");
+  const bool shared_pool = (coords1 == coords2 && off1 == off2 && cnt1 == cnt2);
+  int rc;
+  mark(ctx, st, 0, 0);
+  if ((rc = store_build<T>(ctx, &ctx->scratch1, npoly1, nverts1, coords1, off1, cnt1, false, st))) return rc;
+  if (!shared_pool && (rc = store_build<T>(ctx, &ctx->scratch2, npoly2, nverts2, coords2, off2, cnt2, false, st))) return rc;
+  mark(ctx, st, 0, 1);
+  StoreArgs<T> sa;
+  sa.s1 = view_of<T>(&ctx->scratch1);
+  sa.s2 = shared_pool ? sa.s1 : view_of<T>(&ctx->scratch2);
+  sa.idx1 = idx1; sa.idx2 = idx2;
+  sa.simplices = reinterpret_cast<GkSimplex<T>*>(simplices);
+  sa.distances = distances;
+  sa.npairs = npairs;
+  return run_store_batch<T>(ctx, sa, st);
 }
 
 // Upload one host array into a grow-only device buffer on the context stream.
@@ -204,11 +322,12 @@ int gjk_host(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t* off
   if (simplices && (rc = ctx->d_simp.reserve((size_t)npairs * sizeof(S)))) return rc;
 
   rc = gjk_device<T, S>(ctx, npairs, static_cast<const T*>(ctx->d_coords1.p),
-                        static_cast<const int64_t*>(ctx->d_off1.p), static_cast<const int*>(ctx->d_cnt1.p),
+                        static_cast<const int64_t*>(ctx->d_off1.p), static_cast<const int*>(ctx->d_cnt1.p), npoly1, nverts1,
                         idx1 ? static_cast<const int*>(ctx->d_idx1.p) : nullptr,
                         static_cast<const T*>(shared_pool ? ctx->d_coords1.p : ctx->d_coords2.p),
                         static_cast<const int64_t*>(shared_pool ? ctx->d_off1.p : ctx->d_off2.p),
                         static_cast<const int*>(shared_pool ? ctx->d_cnt1.p : ctx->d_cnt2.p),
+                        shared_pool ? npoly1 : npoly2, shared_pool ? nverts1 : nverts2,
                         idx2 ? static_cast<const int*>(ctx->d_idx2.p) : nullptr,
                         simplices ? static_cast<S*>(ctx->d_simp.p) : nullptr, static_cast<T*>(ctx->d_dist.p),
                         OGJK_MODE_AUTO, ctx->own_stream);
@@ -305,6 +424,69 @@ int single_rows(ogjk_ctx* ctx, int n1, T* const* rows1, int n2, T* const* rows2,
   return gjk_host<T, S>(ctx, 1, c.data(), off, cnt, 2, n1 + n2, &i1, c.data(), off, cnt, 2, n1 + n2, &i2, s, distance);
 }
 
+
+template <typename T>
+int store_create(ogjk_ctx* ctx, int64_t npoly, int64_t nverts, const T* coords, const int64_t* off, const int* cnt,
+                 int on_device, void* stream, ogjk_store** out) {
+  if (!ctx || !out) return fail(OGJK_ERR_ARG, "NULL argument%s");
+  *out = nullptr;
+  if (npoly < 1 || nverts < 1 || !coords || !off || !cnt) return fail(OGJK_ERR_ARG, "empty polytope pool%s");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ogjk_store_* s = new (std::nothrow) ogjk_store_();
+  if (!s) return fail(OGJK_ERR_ALLOC, "out of host memory%s");
+  int rc = OGJK_OK;
+  if (on_device) {
+    rc = store_build<T>(ctx, s, npoly, nverts, coords, off, cnt, true, st);
+  } else {
+    DevBuf dc, doff, dcnt;
+    if (!(rc = dc.reserve((size_t)nverts * 3 * sizeof(T))) && !(rc = doff.reserve((size_t)npoly * sizeof(int64_t))) &&
+        !(rc = dcnt.reserve((size_t)npoly * sizeof(int)))) {
+      cudaError_t e = cudaMemcpyAsync(dc.p, coords, (size_t)nverts * 3 * sizeof(T), cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(doff.p, off, (size_t)npoly * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(dcnt.p, cnt, (size_t)npoly * sizeof(int), cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "store upload failed: %s", cudaGetErrorString(e));
+        rc = OGJK_ERR_CUDA;
+      } else {
+        rc = store_build<T>(ctx, s, npoly, nverts, static_cast<const T*>(dc.p), static_cast<const int64_t*>(doff.p),
+                            static_cast<const int*>(dcnt.p), true, st);
+        if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(OGJK_ERR_CUDA, "store pack failed%s");
+      }
+    }
+    dc.release(); doff.release(); dcnt.release();
+  }
+  if (rc) {
+    s->data.release(); s->boff.release(); s->cnt.release(); s->scan_tmp.release();
+    delete s;
+    return rc;
+  }
+  *out = s;
+  return OGJK_OK;
+}
+
+template <typename T, typename S>
+int store_gjk(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_store* s2, const int* idx2, int64_t npairs,
+              S* simplices, T* distances, void* stream) {
+  if (!ctx || !s1 || !s2 || !distances) return fail(OGJK_ERR_ARG, "NULL argument%s");
+  if (npairs < 0) return fail(OGJK_ERR_ARG, "npairs < 0%s");
+  if (npairs == 0) return OGJK_OK;
+  if (s1->prec != (int)sizeof(T) || s2->prec != (int)sizeof(T)) return fail(OGJK_ERR_ARG, "store precision mismatch%s");
+  if (s1->device != ctx->device || s2->device != ctx->device) return fail(OGJK_ERR_ARG, "store lives on another device%s");
+  if ((!idx1 && npairs > s1->npoly) || (!idx2 && npairs > s2->npoly))
+    return fail(OGJK_ERR_ARG, "npairs exceeds the pool size in un-indexed mode%s");
+  CU(cudaSetDevice(ctx->device));
+  ctx->timed_mask = 0;
+  StoreArgs<T> sa;
+  sa.s1 = view_of<T>(s1);
+  sa.s2 = view_of<T>(s2);
+  sa.idx1 = idx1; sa.idx2 = idx2;
+  sa.simplices = reinterpret_cast<GkSimplex<T>*>(simplices);
+  sa.distances = distances;
+  sa.npairs = npairs;
+  return run_store_batch<T>(ctx, sa, static_cast<cudaStream_t>(stream));
+}
+
 }  // namespace
 
 extern "C" {
@@ -344,12 +526,15 @@ void ogjk_ctx_destroy(ogjk_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  ogjk_store_* ss[] = {&c->scratch1, &c->scratch2};
+  for (ogjk_store_* q : ss) { q->data.release(); q->boff.release(); q->cnt.release(); q->scan_tmp.release(); }
+  c->sort_tmp.release(); c->sorted_list.release();
   DevBuf* bufs[] = {&c->counters, &c->small_list, &c->large_list, &c->d_coords1, &c->d_coords2, &c->d_off1, &c->d_off2,
                     &c->d_cnt1,   &c->d_cnt2,     &c->d_idx1,     &c->d_idx2,    &c->d_simp,    &c->d_dist};
   for (DevBuf* b : bufs) b->release();
   c->h_stage.release();
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
-  for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 2 * kPhases; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   delete c;
 }
 
@@ -359,21 +544,36 @@ int ogjk_ctx_set_timing(ogjk_ctx* c, int enable) {
   if (!c) return fail(OGJK_ERR_ARG, "ctx is NULL%s");
   CU(cudaSetDevice(c->device));
   if (enable && !c->ev[0])
-    for (int i = 0; i < 6; ++i) CU(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 2 * kPhases; ++i) CU(cudaEventCreate(&c->ev[i]));
   c->timing = enable != 0;
   c->timed_mask = 0;
   return OGJK_OK;
 }
-int ogjk_ctx_last_timing(ogjk_ctx* c, float* ms3) {
-  if (!c || !ms3) return fail(OGJK_ERR_ARG, "NULL argument%s");
+int ogjk_ctx_last_timing(ogjk_ctx* c, float* ms8) {
+  if (!c || !ms8) return fail(OGJK_ERR_ARG, "NULL argument%s");
   if (!c->timing) return fail(OGJK_ERR_ARG, "timing not enabled%s");
-  for (int k = 0; k < 3; ++k) {
-    ms3[k] = 0.f;
+  for (int k = 0; k < kPhases; ++k) {
+    ms8[k] = 0.f;
     if (c->timed_mask & (1 << k)) {
       CU(cudaEventSynchronize(c->ev[2 * k + 1]));
-      CU(cudaEventElapsedTime(&ms3[k], c->ev[2 * k], c->ev[2 * k + 1]));
+      CU(cudaEventElapsedTime(&ms8[k], c->ev[2 * k], c->ev[2 * k + 1]));
     }
   }
+  return OGJK_OK;
+}
+int ogjk_ctx_set_classes(ogjk_ctx* c, int n, const int* hi_keys, const int* lanes) {
+  if (!c || !hi_keys || !lanes || n < 1 || n > kMaxClasses) return fail(OGJK_ERR_ARG, "bad class table%s");
+  int prev = 0;
+  for (int i = 0; i < n; ++i) {
+    const int l = lanes[i];
+    if (!(l == 0 || l == 1 || l == 2 || l == 4 || l == 8 || l == 16 || l == 32)) return fail(OGJK_ERR_ARG, "lanes must be 0 or a power of two <= 32%s");
+    if (l == 0 && hi_keys[i] > kSmallKeyMax) return fail(OGJK_ERR_ARG, "register-resident class is limited to key <= 4%s");
+    if (hi_keys[i] <= prev) return fail(OGJK_ERR_ARG, "class keys must increase%s");
+    prev = hi_keys[i];
+  }
+  c->nclasses = n;
+  for (int i = 0; i < n; ++i) { c->class_hi[i] = hi_keys[i]; c->class_lanes[i] = lanes[i]; }
+  c->class_hi[n - 1] = kMaxKey;  // the last class always takes everything above
   return OGJK_OK;
 }
 int ogjk_ctx_set_warp_threshold(ogjk_ctx* c, int nverts) {
@@ -383,17 +583,44 @@ int ogjk_ctx_set_warp_threshold(ogjk_ctx* c, int nverts) {
 }
 
 int ogjk_gjk_device_f32(ogjk_ctx* ctx, int64_t npairs, const float* coords1, const int64_t* off1, const int* cnt1,
-                        const int* idx1, const float* coords2, const int64_t* off2, const int* cnt2, const int* idx2,
-                        ogjk_simplex_f32* simplices, float* distances, int mode, void* stream) {
-  return gjk_device<float, ogjk_simplex_f32>(ctx, npairs, coords1, off1, cnt1, idx1, coords2, off2, cnt2, idx2, simplices,
-                                             distances, mode, stream);
+                        int64_t npoly1, int64_t nverts1, const int* idx1, const float* coords2, const int64_t* off2,
+                        const int* cnt2, int64_t npoly2, int64_t nverts2, const int* idx2, ogjk_simplex_f32* simplices,
+                        float* distances, int mode, void* stream) {
+  return gjk_device<float, ogjk_simplex_f32>(ctx, npairs, coords1, off1, cnt1, npoly1, nverts1, idx1, coords2, off2, cnt2,
+                                             npoly2, nverts2, idx2, simplices, distances, mode, stream);
 }
 int ogjk_gjk_device_f64(ogjk_ctx* ctx, int64_t npairs, const double* coords1, const int64_t* off1, const int* cnt1,
-                        const int* idx1, const double* coords2, const int64_t* off2, const int* cnt2, const int* idx2,
-                        ogjk_simplex_f64* simplices, double* distances, int mode, void* stream) {
-  return gjk_device<double, ogjk_simplex_f64>(ctx, npairs, coords1, off1, cnt1, idx1, coords2, off2, cnt2, idx2,
-                                              simplices, distances, mode, stream);
+                        int64_t npoly1, int64_t nverts1, const int* idx1, const double* coords2, const int64_t* off2,
+                        const int* cnt2, int64_t npoly2, int64_t nverts2, const int* idx2, ogjk_simplex_f64* simplices,
+                        double* distances, int mode, void* stream) {
+  return gjk_device<double, ogjk_simplex_f64>(ctx, npairs, coords1, off1, cnt1, npoly1, nverts1, idx1, coords2, off2, cnt2,
+                                              npoly2, nverts2, idx2, simplices, distances, mode, stream);
 }
+
+// ---- packed polytope store ------------------------------------------------------
+
+#define OGJK_STORE_IMPL(SFX, T, S)                                                                                   \
+  int ogjk_store_create_##SFX(ogjk_ctx* ctx, int64_t npoly, int64_t nverts, const T* coords, const int64_t* off,        \
+                              const int* cnt, int on_device, void* stream, ogjk_store** out) {                           \
+    return store_create<T>(ctx, npoly, nverts, coords, off, cnt, on_device, stream, out);                               \
+  }                                                                                                                  \
+  int ogjk_store_gjk_##SFX(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_store* s2, const int* idx2,  \
+                           int64_t npairs, S* simplices, T* distances, void* stream) {                                  \
+    return store_gjk<T, S>(ctx, s1, idx1, s2, idx2, npairs, simplices, distances, stream);                              \
+  }
+OGJK_STORE_IMPL(f32, float, ogjk_simplex_f32)
+OGJK_STORE_IMPL(f64, double, ogjk_simplex_f64)
+
+void ogjk_store_destroy(ogjk_store* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  s->data.release(); s->boff.release(); s->cnt.release(); s->scan_tmp.release();
+  delete s;
+}
+int64_t ogjk_store_bytes(const ogjk_store* s) {
+  return s ? (int64_t)(s->capacity * s->prec + s->npoly * 12) : 0;
+}
+int64_t ogjk_store_num_polytopes(const ogjk_store* s) { return s ? s->npoly : 0; }
 
 int ogjk_gjk_host_f32(ogjk_ctx* ctx, int64_t npairs, const float* coords1, const int64_t* off1, const int* cnt1,
                       int64_t npoly1, int64_t nverts1, const int* idx1, const float* coords2, const int64_t* off2,

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include "gjk_core.cuh"
+#include "store.cuh"
 
 namespace ogjk {
 
@@ -147,6 +148,7 @@ OGJK_DI T gjk_query(const Body& b1, const Body& b2, Splx<T>& s, V3<T>& wit1, V3<
 template <typename T>
 OGJK_DI void store_simplex(GkSimplex<T>* o, const Splx<T>& s, const V3<T>& w1, const V3<T>& w2) {
   o->nvrtx = s.n;
+  if (sizeof(T) == 8) reinterpret_cast<int*>(o)[1] = 0;  // fp64 layout pads nvrtx to 8 B: keep output bytes deterministic
   o->vrtx[0][0] = s.q0.x; o->vrtx[0][1] = s.q0.y; o->vrtx[0][2] = s.q0.z;
   o->vrtx[1][0] = s.q1.x; o->vrtx[1][1] = s.q1.y; o->vrtx[1][2] = s.q1.z;
   o->vrtx[2][0] = s.q2.x; o->vrtx[2][1] = s.q2.y; o->vrtx[2][2] = s.q2.z;
@@ -209,6 +211,173 @@ gjk_warp_kernel(BatchArgs<T> a, const int* __restrict__ list, const unsigned lon
     V3<T> w1, w2;
     const T d = gjk_query<T>(b1, b2, s, w1, w2);
     if (lane == 0) {
+      a.distances[p] = d;
+      if (a.simplices) store_simplex(a.simplices + p, s, w1, w2);
+    }
+  }
+}
+
+// =============================================================================
+// Kernels over the packed polytope store (store.cuh)
+// =============================================================================
+
+template <typename T> struct StoreArgs {
+  StoreView<T> s1, s2;
+  const int* idx1; const int* idx2;
+  GkSimplex<T>* simplices;  // may be null
+  T* distances;
+  long long npairs;
+};
+
+// One 16-byte chunk of a coordinate array: 4 fp32 or 2 fp64 vertices.
+template <typename T> struct Chunk;
+template <> struct Chunk<float> {
+  static constexpr int kVerts = 4;
+  float v[4];
+  OGJK_DI void load(const float* p) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+};
+template <> struct Chunk<double> {
+  static constexpr int kVerts = 2;
+  double v[2];
+  OGJK_DI void load(const double* p) {
+    const double2 t = *reinterpret_cast<const double2*>(p);
+    v[0] = t.x; v[1] = t.y;
+  }
+};
+
+// G cooperating lanes (a power of two, 1..32) scan one polytope block:
+// lane g takes chunks g, g+G, ... (ascending vertex index within the lane), then
+// the group reduces with a (value, lowest index) butterfly.  Every lane of the
+// group ends with the same support point, so the rest of the GJK iteration runs
+// convergently inside the group and nothing has to be broadcast.
+template <typename T, int G> struct GroupBody {
+  const T* blk; int n; int np; int g; unsigned mask;
+  OGJK_DI V3<T> vertex(int i) const { return V3<T>{blk[i], blk[np + i], blk[2 * np + i]}; }
+  OGJK_DI void support(T dx, T dy, T dz, V3<T>& cur, int& cur_i) const {
+    constexpr int CV = Chunk<T>::kVerts;
+    T best = dot3(cur.x, cur.y, cur.z, dx, dy, dz);
+    int better = 0x7fffffff;
+    const int nchunks = np / CV;
+#pragma unroll 2
+    for (int c = g; c < nchunks; c += G) {
+      Chunk<T> X, Y, Z;
+      X.load(blk + CV * c);
+      Y.load(blk + np + CV * c);
+      Z.load(blk + 2 * np + CV * c);
+#pragma unroll
+      for (int t = 0; t < CV; ++t) {
+        const T sc = dot3(X.v[t], Y.v[t], Z.v[t], dx, dy, dz);
+        if (sc > best) { best = sc; better = CV * c + t; }
+      }
+    }
+#pragma unroll
+    for (int m = G / 2; m > 0; m >>= 1) {
+      const T ob = __shfl_xor_sync(mask, best, m);
+      const int oi = __shfl_xor_sync(mask, better, m);
+      if (ob > best || (ob == best && oi < better)) { best = ob; better = oi; }
+    }
+    if (better != 0x7fffffff) { cur = vertex(better); cur_i = better; }
+  }
+};
+
+// Segment [*seg_begin, *seg_end) of the size-sorted pair list (or the identity
+// list when `list` is null) is consumed through a device-side work queue, 32/G
+// pairs per grab.
+template <typename T, int G>
+__global__ void __launch_bounds__(128)
+gjk_group_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* __restrict__ seg_begin,
+                 const unsigned* __restrict__ seg_end, unsigned long long* __restrict__ head) {
+  constexpr int PER_WARP = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int g = lane % G;
+  const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - g));
+  const long long begin = seg_begin ? (long long)*seg_begin : 0;
+  const long long end = seg_end ? (long long)*seg_end : a.npairs;
+  for (;;) {
+    unsigned long long got = 0;
+    if (lane == 0) got = atomicAdd(head, (unsigned long long)PER_WARP);
+    got = __shfl_sync(0xffffffffu, got, 0);
+    const long long base = begin + (long long)got;
+    if (base >= end) break;
+    const long long slot = base + lane / G;
+    if (slot < end) {
+      const long long p = list ? (long long)list[slot] : slot;
+      const long long h1 = a.idx1 ? (long long)a.idx1[p] : p;
+      const long long h2 = a.idx2 ? (long long)a.idx2[p] : p;
+      const int n1 = a.s1.cnt[h1], n2 = a.s2.cnt[h2];
+      GroupBody<T, G> b1{a.s1.data + a.s1.boff[h1], n1, pad4(n1), g, mask};
+      GroupBody<T, G> b2{a.s2.data + a.s2.boff[h2], n2, pad4(n2), g, mask};
+      Splx<T> s;
+      V3<T> w1, w2;
+      const T d = gjk_query<T>(b1, b2, s, w1, w2);
+      if (g == 0) {
+        a.distances[p] = d;
+        if (a.simplices) store_simplex(a.simplices + p, s, w1, w2);
+      }
+    }
+  }
+}
+
+// Thread-per-pair kernel for pairs whose two polytopes have at most 8 vertices
+// each (boxes, tetrahedra, the reference's tiny random bodies): all 16 vertices
+// live in registers for the whole query, so global memory is touched once per
+// pair.  The support scan is fully unrolled over register slots; the winning
+// vertex is carried by value, so no register array is ever indexed dynamically.
+template <typename T> struct RegBody {
+  T x[8], y[8], z[8];
+  const T* blk; int np;
+  OGJK_DI void load(const T* b, int np_) {
+    constexpr int CV = Chunk<T>::kVerts;
+    blk = b; np = np_;
+#pragma unroll
+    for (int c = 0; c < 8 / CV; ++c) {
+      // a 4-vertex polytope has np == 4: its upper register slots repeat chunk 0
+      const int cc = (CV * c < np_) ? c : 0;
+      Chunk<T> X, Y, Z;
+      X.load(b + CV * cc); Y.load(b + np_ + CV * cc); Z.load(b + 2 * np_ + CV * cc);
+#pragma unroll
+      for (int t = 0; t < CV; ++t) { x[CV * c + t] = X.v[t]; y[CV * c + t] = Y.v[t]; z[CV * c + t] = Z.v[t]; }
+    }
+  }
+  OGJK_DI V3<T> vertex(int i) const { return V3<T>{blk[i], blk[np + i], blk[2 * np + i]}; }
+  OGJK_DI void support(T dx, T dy, T dz, V3<T>& cur, int& cur_i) const {
+    T best = dot3(cur.x, cur.y, cur.z, dx, dy, dz);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const T sc = dot3(x[i], y[i], z[i], dx, dy, dz);
+      // slots >= np replicate lower-index vertices: equal value, never strictly larger
+      if (sc > best) { best = sc; cur_i = i; cur.x = x[i]; cur.y = y[i]; cur.z = z[i]; }
+    }
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+gjk_small_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* __restrict__ seg_begin,
+                 const unsigned* __restrict__ seg_end, unsigned long long* __restrict__ head) {
+  const int lane = threadIdx.x & 31;
+  const long long begin = seg_begin ? (long long)*seg_begin : 0;
+  const long long end = seg_end ? (long long)*seg_end : a.npairs;
+  for (;;) {
+    unsigned long long got = 0;
+    if (lane == 0) got = atomicAdd(head, 32ull);
+    got = __shfl_sync(0xffffffffu, got, 0);
+    const long long base = begin + (long long)got;
+    if (base >= end) break;
+    const long long slot = base + lane;
+    if (slot < end) {
+      const long long p = list ? (long long)list[slot] : slot;
+      const long long h1 = a.idx1 ? (long long)a.idx1[p] : p;
+      const long long h2 = a.idx2 ? (long long)a.idx2[p] : p;
+      RegBody<T> b1, b2;
+      b1.load(a.s1.data + a.s1.boff[h1], pad4(a.s1.cnt[h1]));
+      b2.load(a.s2.data + a.s2.boff[h2], pad4(a.s2.cnt[h2]));
+      Splx<T> s;
+      V3<T> w1, w2;
+      const T d = gjk_query<T>(b1, b2, s, w1, w2);
       a.distances[p] = d;
       if (a.simplices) store_simplex(a.simplices + p, s, w1, w2);
     }

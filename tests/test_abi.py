@@ -58,7 +58,8 @@ def test_argument_errors_do_not_need_a_device():
     assert L.ogjk_ctx_create(0, None) == -1
     assert b"NULL" in L.ogjk_last_error()
     z = np.zeros(1, dtype=np.float32)
-    rc = L.ogjk_gjk_device_f32(None, 1, z.ctypes.data, None, None, None, None, None, None, None, None, None, 0, None)
+    rc = L.ogjk_gjk_device_f32(None, 1, z.ctypes.data, None, None, 1, 1, None, None, None, None, 1, 1, None, None, None, 0,
+                                None)
     assert rc == -1
 
 

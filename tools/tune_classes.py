@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""GPU-side sweep: time ogjk_store_gjk_* with every uniform lanes-per-pair choice
+on the bench workloads (device-resident store, CUDA events).  Prints one line per
+(workload, lanes).  Usage: python tools/tune_classes.py [workload ...]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import WORKLOADS  # noqa: E402
+from opengjk_b200 import api  # noqa: E402
+
+names = sys.argv[1:] or ["hulls64_f64", "hulls64_f32", "boxes_f32", "hulls1k_f32"]
+eng = api.Engine(0)
+dev = torch.device("cuda:0")
+for name in names:
+    desc, dt, maker, pairs = WORKLOADS[name]
+    pairs = min(pairs, 2_000_000)
+    w = maker(pairs, 42)
+    prec = "f64" if dt == np.float64 else "f32"
+    sdt = api.SIMPLEX_F64 if prec == "f64" else api.SIMPLEX_F32
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    coords, off, cnt, pa, pb = t(w.coords.reshape(-1)), t(w.off), t(w.cnt), t(w.pa), t(w.pb)
+    simp = torch.empty(w.npairs * sdt.itemsize, dtype=torch.uint8, device=dev)
+    dist = torch.empty(w.npairs, dtype=coords.dtype, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    store = eng.store_create(coords, off, cnt, st)
+    tables = {"small+g": None}
+    small_ok = int(w.cnt.max()) <= 8
+    for g in ([0] if small_ok else []) + [1, 2, 4, 8, 16, 32]:
+        eng.set_classes([(4, 0), (2048, 1)] if g == 0 else [(2048, g)])
+        for _ in range(3):
+            eng.store_gjk(store, pa, store, pb, w.npairs, simp, dist, st)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            eng.store_gjk(store, pa, store, pb, w.npairs, simp, dist, st)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print(f"{name:14s} lanes={g:2d}  {ms:8.3f} ms  {w.npairs / ms / 1e3:10.1f} Mpairs/s", flush=True)
+    store.close()
