@@ -5,7 +5,7 @@
 // /root/reference/scalar/openGJK.c (cited per function); the structure does
 // not: the simplex lives in four named register slots (no dynamic indexing,
 // so nothing spills to local memory), slot permutations are selects, and the
-// S3D region tree is resolved to a small "decision" that is applied once.
+// S3D region tree is a table-driven automaton with a single hff2 instance.
 //
 // Bit-parity contract: this translation unit is compiled with -fmad=false and
 // the default IEEE div/sqrt/denormal modes, and every expression keeps the
@@ -118,19 +118,16 @@ template <typename T> OGJK_DI void sub_2d(Splx<T>& s, V3<T>& v) {
   const V3<T> a = pos(s.q2), b = pos(s.q1), c = pos(s.q0);
   const bool ab = hf1(a, b);
   const bool ac = hf1(a, c);
-  // outcome: 0 = face abc, 1 = edge ab (region12), 2 = edge ac (region13), 3 = vertex a
-  int out;
+  // outcome: 0 = face abc, 1 = edge ab (region12), 2 = edge ac (region13), 3 = vertex a.
+  // At most two hf2 tests are needed on any path: t1 = hf2(a,b,c) when ab, t2 = hf2(a,c,b) when ac.
+  int out = 3;
+  bool need2 = ac;
   if (ab) {
-    if (!hf2(a, b, c)) {
-      out = (ac && hf2(a, c, b)) ? 2 : 0;
-    } else {
-      out = 1;
-    }
+    if (hf2(a, b, c)) { out = 1; need2 = false; } else { out = 0; }
   } else if (ac) {
-    out = hf2(a, c, b) ? 2 : 0;
-  } else {
-    out = 3;
+    out = 0;
   }
+  if (need2 && hf2(a, c, b)) out = 2;
   if (out == 0) {
     v = proj_plane(a, b, c);
   } else if (out == 3) {
@@ -146,11 +143,53 @@ template <typename T> OGJK_DI void sub_2d(Splx<T>& s, V3<T>& v) {
 }
 
 // ---- S3D: openGJK.c:337-605 --------------------------------------------------
-// Decision produced by the region tree of the "one plane" / "no plane" arms:
-//   kind 0: nothing (reference leaves simplex and v untouched)
-//   kind 1: segment {newest, A}           -> v = proj_line(s1, A)
-//   kind 2: triangle {newest, A, B}       -> v = proj_plane(s1, P, Q)  (P,Q = A,B or B,A)
-template <typename T> OGJK_DI void sub_3d(Splx<T>& s, V3<T>& v) {
+// The reference resolves the "one plane" / "no plane" arms with a tree of up to
+// four hff2 tests whose operands depend on the branch taken.  Here the tree is a
+// table-driven automaton: every node names the two operands (i, j or k) of one
+// hff2(s1, X, Y) test and where to go on true / false; leaves carry the outcome
+// (which vertices survive, which projection).  One hff2 instance serves every
+// region, so lanes of a warp that sit in different regions still share the
+// instruction stream, and the code stays small enough for the instruction cache.
+//
+// entry = x | y<<2 | on_true<<4 | on_false<<16 ; next values >= kLeaf are leaves:
+//   leaf payload = kind | a<<2 | b<<4 | swap<<6   (kind 0 none, 1 segment{new,a}, 2 triangle{new,a,b})
+constexpr unsigned kLeaf = 0x800;
+constexpr unsigned S3I = 0, S3J = 1, S3K = 2;
+constexpr unsigned leaf(unsigned kind, unsigned a, unsigned b, unsigned sw) { return kLeaf | kind | (a << 2) | (b << 4) | (sw << 6); }
+constexpr unsigned node(unsigned x, unsigned y, unsigned t, unsigned f) { return x | (y << 2) | (t << 4) | (f << 16); }
+constexpr unsigned L_TRI_IK = leaf(2, S3I, S3K, 0), L_TRI_JK = leaf(2, S3J, S3K, 0), L_TRI_IJ = leaf(2, S3I, S3J, 0);
+constexpr unsigned L_TRI_IK_SW = leaf(2, S3I, S3K, 1), L_TRI_JK_SW = leaf(2, S3J, S3K, 1);
+constexpr unsigned L_SEG_I = leaf(1, S3I, 0, 0), L_SEG_J = leaf(1, S3J, 0, 0), L_SEG_K = leaf(1, S3K, 0, 0);
+constexpr unsigned L_NONE = leaf(0, 0, 0, 0);
+// Branch is on r = hff2(s1, X, Y) (the reference mostly tests !hff2; true/false are swapped accordingly).
+__device__ const unsigned kS3Table[20] = {
+    /* 0  :436 */ node(S3K, S3I, 1, L_TRI_IK),        /* 1  :439 */ node(S3K, S3J, L_SEG_K, L_TRI_JK),
+    /* 2  :447 */ node(S3I, S3K, L_SEG_I, L_TRI_IK),  /* 3  :455 */ node(S3J, S3K, L_SEG_J, L_TRI_JK),
+    /* 4  :465 */ node(S3K, S3I, 6, 5),               /* 5  :466 */ node(S3I, S3K, L_SEG_K, L_TRI_IK),
+    /* 6  :474 */ node(S3K, S3J, L_SEG_K, L_TRI_JK),  /* 7  :483 */ node(S3K, S3J, 9, 8),
+    /* 8  :484 */ node(S3J, S3K, L_SEG_J, L_TRI_JK),  /* 9  :492 */ node(S3K, S3I, L_SEG_K, L_TRI_IK),
+    /* 10 :505 */ node(S3K, S3I, 11, 13),             /* 11 :506 */ node(S3K, S3J, L_SEG_K, 12),
+    /* 12 :504 */ node(S3J, S3K, L_SEG_J, L_TRI_JK_SW), /* 13 :503 */ node(S3I, S3K, L_SEG_I, L_TRI_IK_SW),
+    /* 14 :553 */ node(S3I, S3J, 15, L_TRI_IJ),       /* 15 :556 */ node(S3I, S3K, L_SEG_I, L_TRI_IK),
+    /* 16 :582 */ node(S3J, S3K, 19, 17),             /* 17 :583 */ node(S3K, S3J, 18, L_TRI_JK),
+    /* 18 :586 */ node(S3K, S3I, L_SEG_K, L_TRI_IK_SW), /* 19 :593 */ node(S3J, S3I, L_SEG_J, L_TRI_IJ)};
+
+template <typename T> OGJK_DI MV<T> pick3(unsigned c, const MV<T>& i, const MV<T>& j, const MV<T>& k) {
+  MV<T> r;
+  r.x = c == S3I ? i.x : (c == S3J ? j.x : k.x);
+  r.y = c == S3I ? i.y : (c == S3J ? j.y : k.y);
+  r.z = c == S3I ? i.z : (c == S3J ? j.z : k.z);
+  r.ia = c == S3I ? i.ia : (c == S3J ? j.ia : k.ia);
+  r.ib = c == S3I ? i.ib : (c == S3J ? j.ib : k.ib);
+  return r;
+}
+template <typename T> OGJK_DI V3<T> pick3v(unsigned c, const MV<T>& i, const MV<T>& j, const MV<T>& k) {
+  return V3<T>{c == S3I ? i.x : (c == S3J ? j.x : k.x), c == S3I ? i.y : (c == S3J ? j.y : k.y),
+               c == S3I ? i.z : (c == S3J ? j.z : k.z)};
+}
+
+// Returns true when the reference falls through to S2D (plane-sum 2, :382-413).
+template <typename T> OGJK_DI bool sub_3d(Splx<T>& s, V3<T>& v) {
   const MV<T> m1 = s.q3, m2 = s.q2, m3 = s.q1, m4 = s.q0;
   const V3<T> s1 = pos(m1), s2 = pos(m2), s3 = pos(m3), s4 = pos(m4);
 
@@ -163,7 +202,7 @@ template <typename T> OGJK_DI void sub_3d(Splx<T>& s, V3<T>& v) {
     v = s1;
     s.n = 1;
     s.q0 = m1;
-    return;
+    return false;
   }
 
   const V3<T> e12 = sub(s2, s1), e13 = sub(s3, s1), e14 = sub(s4, s1);
@@ -177,9 +216,9 @@ template <typename T> OGJK_DI void sub_3d(Splx<T>& s, V3<T>& v) {
   if (npl == 3) {  // S3Dregion1234 :61-65
     v = V3<T>{(T)0, (T)0, (T)0};
     s.n = 4;
-    return;
+    return false;
   }
-  if (npl == 2) {  // :382-413
+  if (npl == 2) {  // :382-413; S2D itself is run by the caller (single instance)
     s.n = 3;
     if (!pl2) {
       s.q2 = m1;                    // q1 = s3, q0 = s4 stay
@@ -188,110 +227,67 @@ template <typename T> OGJK_DI void sub_3d(Splx<T>& s, V3<T>& v) {
     } else {
       s.q0 = m3; s.q1 = m2; s.q2 = m1;
     }
-    sub_2d(s, v);
-    return;
+    return true;
   }
 
   // slot order is [0]=s4, [1]=s3, [2]=s2.  (k,i,j) is one of three rotations:
   //   rot 0: k=2,i=1,j=0   rot 1: k=1,i=0,j=2   rot 2: k=0,i=2,j=1
-  int kind = 0;
-  bool swapPQ = false;      // projection argument order (B,A) instead of (A,B)
-  MV<T> A = m2, B = m2;     // chosen survivors (besides the newest vertex)
-
+  int rot;
+  unsigned at;  // automaton start node, or a leaf
   if (npl == 1) {  // :414-532
     s.n = 3;       // set before any region is known, as the reference does
-    const int rot = pl2 ? 0 : (pl3 ? 1 : 2);
-    const MV<T> mk = rot == 0 ? m2 : (rot == 1 ? m3 : m4);
-    const MV<T> mi = rot == 0 ? m3 : (rot == 1 ? m4 : m2);
-    const MV<T> mj = rot == 0 ? m4 : (rot == 1 ? m2 : m3);
+    rot = pl2 ? 0 : (pl3 ? 1 : 2);
     const bool hk = rot == 0 ? h2 : (rot == 1 ? h3 : h4);
     const bool hi = rot == 0 ? h3 : (rot == 1 ? h4 : h2);
     const bool hj = rot == 0 ? h4 : (rot == 1 ? h2 : h3);
-    const V3<T> sk = pos(mk), si = pos(mi), sj = pos(mj);
-    // what[]: 1 = tri(i,k) 2 = tri(j,k) 3 = seg(k) 4 = seg(i) 5 = seg(j)
-    //         6 = tri(j,k) with plane(s1,sk,sj)   7 = tri(i,k) with plane(s1,sk,si)
-    int what = 0;
-    if (ndot == 1) {
-      if (hk) {
-        if (!hf2(s1, sk, si)) what = 1;
-        else if (!hf2(s1, sk, sj)) what = 2;
-        else what = 3;
-      } else if (hi) {
-        what = !hf2(s1, si, sk) ? 1 : 4;
-      } else {
-        what = !hf2(s1, sj, sk) ? 2 : 5;
-      }
-    } else if (ndot == 2) {
-      if (hi) {
-        if (!hf2(s1, sk, si)) what = !hf2(s1, si, sk) ? 1 : 3;
-        else                  what = !hf2(s1, sk, sj) ? 2 : 3;
-      } else if (hj) {
-        if (!hf2(s1, sk, sj)) what = !hf2(s1, sj, sk) ? 2 : 5;
-        else                  what = !hf2(s1, sk, si) ? 1 : 3;
-      }
-    } else {  // ndot == 3 :502-531
-      const bool f_ik = hf2(s1, si, sk);
-      const bool f_jk = hf2(s1, sj, sk);
-      const bool f_ki = hf2(s1, sk, si);
-      const bool f_kj = hf2(s1, sk, sj);
-      if (f_ki && f_kj) what = 3;
-      else if (f_ki)    what = f_jk ? 5 : 6;
-      else              what = f_ik ? 4 : 7;
-    }
-    switch (what) {
-      case 1: kind = 2; A = mi; B = mk; break;
-      case 2: kind = 2; A = mj; B = mk; break;
-      case 3: kind = 1; A = mk; break;
-      case 4: kind = 1; A = mi; break;
-      case 5: kind = 1; A = mj; break;
-      case 6: kind = 2; A = mj; B = mk; swapPQ = true; break;
-      case 7: kind = 2; A = mi; B = mk; swapPQ = true; break;
-      default: break;
-    }
-  } else {  // npl == 0 :534-601
-    if (ndot == 1) {
-      const int rot = h3 ? 0 : (h4 ? 1 : 2);
-      const MV<T> mk = rot == 0 ? m2 : (rot == 1 ? m3 : m4);
-      const MV<T> mi = rot == 0 ? m3 : (rot == 1 ? m4 : m2);
-      const MV<T> mj = rot == 0 ? m4 : (rot == 1 ? m2 : m3);
-      const V3<T> sk = pos(mk), si = pos(mi), sj = pos(mj);
-      if (!hf2(s1, si, sj))      { kind = 2; A = mi; B = mj; }
-      else if (!hf2(s1, si, sk)) { kind = 2; A = mi; B = mk; }
-      else                       { kind = 1; A = mi; }
-    } else if (ndot == 2) {
-      s.n = 3;
-      const int rot = !h3 ? 0 : (!h4 ? 1 : 2);
-      const MV<T> mk = rot == 0 ? m2 : (rot == 1 ? m3 : m4);
-      const MV<T> mi = rot == 0 ? m3 : (rot == 1 ? m4 : m2);
-      const MV<T> mj = rot == 0 ? m4 : (rot == 1 ? m2 : m3);
-      const V3<T> sk = pos(mk), si = pos(mi), sj = pos(mj);
-      if (!hf2(s1, sj, sk)) {
-        if (!hf2(s1, sk, sj))      { kind = 2; A = mj; B = mk; }
-        else if (!hf2(s1, sk, si)) { kind = 2; A = mi; B = mk; swapPQ = true; }
-        else                       { kind = 1; A = mk; }
-      } else if (!hf2(s1, sj, si)) { kind = 2; A = mi; B = mj; }
-      else                         { kind = 1; A = mj; }
-    }
-    // ndot == 3: the reference does nothing (simplex stays at 4 vertices, v unchanged)
+    if (ndot == 1)      at = hk ? 0u : (hi ? 2u : 3u);
+    else if (ndot == 2) at = hi ? 4u : (hj ? 7u : L_NONE);
+    else                at = 10u;
+  } else {         // npl == 0 :534-601
+    if (ndot == 1)      { rot = h3 ? 0 : (h4 ? 1 : 2); at = 14u; }
+    else if (ndot == 2) { s.n = 3; rot = !h3 ? 0 : (!h4 ? 1 : 2); at = 16u; }
+    else                { rot = 0; at = L_NONE; }  // reference does nothing: simplex stays at 4, v unchanged
   }
+  const MV<T> mk = rot == 0 ? m2 : (rot == 1 ? m3 : m4);
+  const MV<T> mi = rot == 0 ? m3 : (rot == 1 ? m4 : m2);
+  const MV<T> mj = rot == 0 ? m4 : (rot == 1 ? m2 : m3);
 
-  if (kind == 2) {          // select_1xy :67-92
-    s.n = 3;
-    s.q2 = m1; s.q1 = A; s.q0 = B;
-    const V3<T> pa = pos(A), pb = pos(B);
-    v = swapPQ ? proj_plane(s1, pb, pa) : proj_plane(s1, pa, pb);
-  } else if (kind == 1) {   // select_1x :94-113
-    s.n = 2;
-    s.q1 = m1; s.q0 = A;
-    v = proj_line(s1, pos(A));
+#pragma unroll 1
+  while (at < kLeaf) {
+    const unsigned e = kS3Table[at];
+    const V3<T> X = pick3v(e & 3u, mi, mj, mk);
+    const V3<T> Y = pick3v((e >> 2) & 3u, mi, mj, mk);
+    at = hf2(s1, X, Y) ? ((e >> 4) & 0xfffu) : (e >> 16);
   }
+  const unsigned kind = at & 3u;
+  if (kind != 0) {
+    const MV<T> A = pick3((at >> 2) & 3u, mi, mj, mk);
+    if (kind == 2) {          // select_1xy :67-92
+      const MV<T> B = pick3((at >> 4) & 3u, mi, mj, mk);
+      const bool sw = (at >> 6) & 1u;
+      s.n = 3;
+      s.q2 = m1; s.q1 = A; s.q0 = B;
+      const V3<T> pa = pos(A), pb = pos(B);
+      v = proj_plane(s1, sw ? pb : pa, sw ? pa : pb);
+    } else {                  // select_1x :94-113
+      s.n = 2;
+      s.q1 = m1; s.q0 = A;
+      v = proj_line(s1, pos(A));
+    }
+  }
+  return false;
 }
 
-// openGJK.c:632-646 after the push at :1013-1019.  `w` goes to slot s.n.
+// openGJK.c:632-646 after the push at :1013-1019.  `w` goes to slot s.n.  S3D
+// runs first so that its fall-through into S2D shares the one S2D instance with
+// the lanes that arrived with three vertices.
 template <typename T> OGJK_DI void push_and_solve(Splx<T>& s, const MV<T>& w, V3<T>& v) {
-  if (s.n == 1)      { s.q1 = w; s.n = 2; sub_1d(s, v); }
-  else if (s.n == 2) { s.q2 = w; s.n = 3; sub_2d(s, v); }
-  else               { s.q3 = w; s.n = 4; sub_3d(s, v); }
+  int todo;  // which lower-dimensional solver still has to run: 0 none, 1 S1D, 2 S2D
+  if (s.n == 3)      { s.q3 = w; s.n = 4; todo = sub_3d(s, v) ? 2 : 0; }
+  else if (s.n == 2) { s.q2 = w; s.n = 3; todo = 2; }
+  else               { s.q1 = w; s.n = 2; todo = 1; }
+  if (todo == 2) sub_2d(s, v);
+  else if (todo == 1) sub_1d(s, v);
 }
 
 // openGJK.c:1025-1030: running max of |vertex|^2 over the current simplex.
@@ -310,10 +306,9 @@ template <typename T> OGJK_DI T update_wmax(const Splx<T>& s, T wmax2) {
 // higher-dimensional blend overwrites the lower one using the already
 // shuffled slots; only the slot shuffles and nvrtx survive.  That is what is
 // reproduced here: `wts` are the weights of the *outermost* routine, applied
-// to the final slot contents.
+// to the final slot contents.  W1D never changes slots, so calls made into it
+// only for their side effects vanish.
 template <typename T> struct Wts { T a0, a1, a2, a3; int terms; };
-
-template <typename T> OGJK_DI void wit_1d_shuffle(Splx<T>&) {}  // W1D never reshuffles
 
 template <typename T> OGJK_DI Wts<T> wit_1d(const Splx<T>& s) {
   const V3<T> p = pos(s.q0), q = pos(s.q1);
@@ -344,45 +339,53 @@ template <typename T> OGJK_DI Wts<T> wit_2d(Splx<T>& s) {
   return Wts<T>{a0, a1, a2, (T)0, 3};
 }
 
-template <typename T> OGJK_DI Wts<T> wit_3d(Splx<T>& s) {
-  const V3<T> p = pos(s.q0), q = pos(s.q1), r = pos(s.q2), u = pos(s.q3);
-  const V3<T> pq = sub(q, p), pr = sub(r, p), ps = sub(u, p);
-  const V3<T> po = V3<T>{-p.x, -p.y, -p.z};
-  const T T00 = dot3(pq, pq), T01 = dot3(pq, pr), T02 = dot3(pq, ps);
-  const T T11 = dot3(pr, pr), T12 = dot3(pr, ps), T22 = dot3(ps, ps);
-  const T det00 = T11 * T22 - T12 * T12;
-  const T det01 = T01 * T22 - T02 * T12;
-  const T det02 = T01 * T12 - T02 * T11;
-  const T det = T00 * det00 - T01 * det01 + T02 * det02;
-  bool reduced = false;
-  if (det == 0.0) {  // :845-848 W2D is called for its side effects, then falls through
-    (void)wit_2d(s);
-    reduced = true;
-  }
-  const T b0 = dot3(pq, po), b1 = dot3(pr, po), b2 = dot3(ps, po);
-  const T det11 = T00 * T22 - T02 * T02;
-  const T det12 = T00 * T12 - T01 * T02;
-  const T det22 = T00 * T11 - T01 * T01;
-  const T I00 = det00 / det, I01 = -det01 / det, I02 = det02 / det;
-  const T I11 = det11 / det, I12 = -det12 / det, I22 = det22 / det;
-  const T a1 = I00 * b0 + I01 * b1 + I02 * b2;
-  const T a2 = I01 * b0 + I11 * b1 + I12 * b2;
-  const T a3 = I02 * b0 + I12 * b1 + I22 * b2;
-  const T a0 = 1.0 - a1 - a2 - a3;  // evaluated in double, rounded once
-  (void)reduced;
-  if (a0 < Lim<T>::eps())      { s.n = 3; s.q0 = s.q3; (void)wit_2d(s); }
-  else if (a1 < Lim<T>::eps()) { s.n = 3; s.q1 = s.q3; (void)wit_2d(s); }
-  else if (a2 < Lim<T>::eps()) { s.n = 3; s.q2 = s.q3; (void)wit_2d(s); }
-  else if (a3 < Lim<T>::eps()) { s.n = 3; (void)wit_2d(s); }
-  return Wts<T>{a0, a1, a2, a3, 4};
-}
-
-// Dispatch of compute_witnesses (:921-939) on the final simplex size.
+// compute_witnesses (:921-939).  For a tetrahedron the reference may run W2D
+// twice for its side effects (once when det == 0, :845-848, once after dropping
+// the vertex whose weight is below eps, :873-900); both runs and the direct
+// three-vertex case go through the single W2D instance in the loop below.
 template <typename T> OGJK_DI Wts<T> witness_weights(Splx<T>& s) {
-  if (s.n == 4) return wit_3d(s);
-  if (s.n == 3) return wit_2d(s);
-  if (s.n == 2) return wit_1d(s);
-  return Wts<T>{(T)1, (T)0, (T)0, (T)0, 1};
+  Wts<T> w = Wts<T>{(T)1, (T)0, (T)0, (T)0, s.n};
+  bool run0 = (s.n == 3), run1 = false;
+  int drop = -1;
+  if (s.n == 4) {
+    const V3<T> p = pos(s.q0), q = pos(s.q1), r = pos(s.q2), u = pos(s.q3);
+    const V3<T> pq = sub(q, p), pr = sub(r, p), ps = sub(u, p);
+    const V3<T> po = V3<T>{-p.x, -p.y, -p.z};
+    const T T00 = dot3(pq, pq), T01 = dot3(pq, pr), T02 = dot3(pq, ps);
+    const T T11 = dot3(pr, pr), T12 = dot3(pr, ps), T22 = dot3(ps, ps);
+    const T det00 = T11 * T22 - T12 * T12;
+    const T det01 = T01 * T22 - T02 * T12;
+    const T det02 = T01 * T12 - T02 * T11;
+    const T det = T00 * det00 - T01 * det01 + T02 * det02;
+    const T b0 = dot3(pq, po), b1 = dot3(pr, po), b2 = dot3(ps, po);
+    const T det11 = T00 * T22 - T02 * T02;
+    const T det12 = T00 * T12 - T01 * T02;
+    const T det22 = T00 * T11 - T01 * T01;
+    const T I00 = det00 / det, I01 = -det01 / det, I02 = det02 / det;
+    const T I11 = det11 / det, I12 = -det12 / det, I22 = det22 / det;
+    w.a1 = I00 * b0 + I01 * b1 + I02 * b2;
+    w.a2 = I01 * b0 + I11 * b1 + I12 * b2;
+    w.a3 = I02 * b0 + I12 * b1 + I22 * b2;
+    w.a0 = 1.0 - w.a1 - w.a2 - w.a3;  // evaluated in double, rounded once
+    run0 = (det == 0.0);
+    drop = w.a0 < Lim<T>::eps() ? 0 : (w.a1 < Lim<T>::eps() ? 1 : (w.a2 < Lim<T>::eps() ? 2 : (w.a3 < Lim<T>::eps() ? 3 : -1)));
+    run1 = drop >= 0;
+  }
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1 && run1) {
+      s.n = 3;
+      if (drop == 0) s.q0 = s.q3;
+      else if (drop == 1) s.q1 = s.q3;
+      else if (drop == 2) s.q2 = s.q3;
+    }
+    if (pass == 0 ? run0 : run1) {
+      const Wts<T> w2 = wit_2d(s);
+      if (w.terms == 3) w = w2;
+    }
+  }
+  if (w.terms == 2) w = wit_1d(s);
+  return w;
 }
 
 // Same memory layout as the reference gkSimplex (openGJK.h:84-94):
