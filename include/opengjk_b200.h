@@ -161,6 +161,49 @@ OGJK_API int ogjk_single_rows_f32(ogjk_ctx* ctx, int n1, float* const* rows1, in
 OGJK_API int ogjk_single_rows_f64(ogjk_ctx* ctx, int n1, double* const* rows1, int n2, double* const* rows2,
                                   ogjk_simplex_f64* s, double* distance);
 
+/* ---- EPA: penetration depth and witness points for intersecting pairs.
+ * Replaces compute_epa_kernel / compute_epa_device / compute_epa / compute_gjk_epa
+ * (gpu/opengjk_gpu.cu:2022-2971, 3204-3224, 3007-3053, 3055-3099;
+ * gpu/include/openGJK_GPU.h:161-206, 244-264).  Semantics as the reference: pairs
+ * whose GJK distance exceeds gkEpsilon keep their GJK witnesses; the others get
+ * distance = -depth, witness points on the closest polytope face, and the face
+ * normal.  `simplices` are the GJK results (not modified by EPA); `normals` may
+ * be NULL.  Exits on which the reference writes nothing keep the GJK distance and
+ * witnesses. */
+OGJK_API int ogjk_store_epa_f32(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_store* s2, const int* idx2,
+                                int64_t npairs, const ogjk_simplex_f32* simplices, float* distances, float* witness1,
+                                float* witness2, float* normals, void* stream);
+OGJK_API int ogjk_store_epa_f64(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_store* s2, const int* idx2,
+                                int64_t npairs, const ogjk_simplex_f64* simplices, double* distances, double* witness1,
+                                double* witness2, double* normals, void* stream);
+OGJK_API int ogjk_store_gjk_epa_f32(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_store* s2, const int* idx2,
+                                    int64_t npairs, ogjk_simplex_f32* simplices, float* distances, float* witness1,
+                                    float* witness2, float* normals, void* stream);
+OGJK_API int ogjk_store_gjk_epa_f64(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_store* s2, const int* idx2,
+                                    int64_t npairs, ogjk_simplex_f64* simplices, double* distances, double* witness1,
+                                    double* witness2, double* normals, void* stream);
+/* host buffers, flat pools (as ogjk_gjk_host_*) */
+OGJK_API int ogjk_gjk_epa_host_f32(ogjk_ctx* ctx, int64_t npairs,
+                                   const float* coords1, const int64_t* off1, const int* cnt1, int64_t npoly1, int64_t nverts1, const int* idx1,
+                                   const float* coords2, const int64_t* off2, const int* cnt2, int64_t npoly2, int64_t nverts2, const int* idx2,
+                                   ogjk_simplex_f32* simplices, float* distances, float* witness1, float* witness2, float* normals);
+OGJK_API int ogjk_gjk_epa_host_f64(ogjk_ctx* ctx, int64_t npairs,
+                                   const double* coords1, const int64_t* off1, const int* cnt1, int64_t npoly1, int64_t nverts1, const int* idx1,
+                                   const double* coords2, const int64_t* off2, const int* cnt2, int64_t npoly2, int64_t nverts2, const int* idx2,
+                                   ogjk_simplex_f64* simplices, double* distances, double* witness1, double* witness2, double* normals);
+/* reference-shaped struct arrays: compute_gjk_epa (openGJK_GPU.h:198-206) and
+ * compute_epa (openGJK_GPU.h:175-184; simplices/distances are inputs and outputs) */
+OGJK_API int ogjk_compute_gjk_epa_f32(ogjk_ctx* ctx, int n, const ogjk_polytope_f32* bd1, const ogjk_polytope_f32* bd2,
+                                      ogjk_simplex_f32* simplices, float* distances, float* witness1, float* witness2);
+OGJK_API int ogjk_compute_gjk_epa_f64(ogjk_ctx* ctx, int n, const ogjk_polytope_f64* bd1, const ogjk_polytope_f64* bd2,
+                                      ogjk_simplex_f64* simplices, double* distances, double* witness1, double* witness2);
+OGJK_API int ogjk_compute_epa_f32(ogjk_ctx* ctx, int n, const ogjk_polytope_f32* bd1, const ogjk_polytope_f32* bd2,
+                                  ogjk_simplex_f32* simplices, float* distances, float* witness1, float* witness2,
+                                  float* contact_normals);
+OGJK_API int ogjk_compute_epa_f64(ogjk_ctx* ctx, int n, const ogjk_polytope_f64* bd1, const ogjk_polytope_f64* bd2,
+                                  ogjk_simplex_f64* simplices, double* distances, double* witness1, double* witness2,
+                                  double* contact_normals);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,9 @@ EXPORTS = [
     "ogjk_ctx_launch_count", "ogjk_ctx_set_warp_threshold", "ogjk_ctx_set_timing", "ogjk_ctx_last_timing",
     "ogjk_ctx_set_classes", "ogjk_store_create_f32", "ogjk_store_create_f64", "ogjk_store_destroy", "ogjk_store_bytes",
     "ogjk_store_num_polytopes", "ogjk_store_gjk_f32", "ogjk_store_gjk_f64",
+    "ogjk_store_epa_f32", "ogjk_store_epa_f64", "ogjk_store_gjk_epa_f32", "ogjk_store_gjk_epa_f64",
+    "ogjk_gjk_epa_host_f32", "ogjk_gjk_epa_host_f64", "ogjk_compute_gjk_epa_f32", "ogjk_compute_gjk_epa_f64",
+    "ogjk_compute_epa_f32", "ogjk_compute_epa_f64",
     "ogjk_gjk_device_f32", "ogjk_gjk_device_f64", "ogjk_gjk_host_f32", "ogjk_gjk_host_f64",
     "ogjk_compute_minimum_distance_f32", "ogjk_compute_minimum_distance_f64",
     "ogjk_compute_minimum_distance_indexed_f32", "ogjk_compute_minimum_distance_indexed_f64",
@@ -75,6 +78,12 @@ def lib():
                                                          vp, vp, i32, vp]
         getattr(L, f"ogjk_store_create_{sfx}").argtypes = [vp, i64, i64, vp, vp, vp, i32, vp, C.POINTER(vp)]
         getattr(L, f"ogjk_store_gjk_{sfx}").argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp]
+        getattr(L, f"ogjk_store_epa_{sfx}").argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
+        getattr(L, f"ogjk_store_gjk_epa_{sfx}").argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
+        getattr(L, f"ogjk_gjk_epa_host_{sfx}").argtypes = [vp, i64, vp, vp, vp, i64, i64, vp, vp, vp, vp, i64, i64, vp,
+                                                           vp, vp, vp, vp, vp]
+        getattr(L, f"ogjk_compute_gjk_epa_{sfx}").argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
+        getattr(L, f"ogjk_compute_epa_{sfx}").argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
         getattr(L, f"ogjk_gjk_host_{sfx}").argtypes = [vp, i64, vp, vp, vp, i64, i64, vp, vp, vp, vp, i64, i64, vp,
                                                        vp, vp]
         getattr(L, f"ogjk_compute_minimum_distance_{sfx}").argtypes = [vp, i32, vp, vp, vp, vp]

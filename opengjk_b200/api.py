@@ -128,6 +128,37 @@ class Engine:
                  _p(cnt), cnt.shape[0], coords.shape[0], _p(pb), _p(simp), _p(dist)))
         return dist, simp
 
+    def store_epa(self, s1, idx1, s2, idx2, npairs, simplices, distances, witness1, witness2, normals=None, stream=0):
+        fn = getattr(_lib.lib(), f"ogjk_store_epa_{s1.prec}")
+        check(fn(self._h, s1._h, _p(idx1), s2._h, _p(idx2), int(npairs), _p(simplices), _p(distances), _p(witness1),
+                 _p(witness2), _p(normals), C.c_void_p(int(stream))))
+
+    def store_gjk_epa(self, s1, idx1, s2, idx2, npairs, simplices, distances, witness1, witness2, normals=None,
+                      stream=0):
+        fn = getattr(_lib.lib(), f"ogjk_store_gjk_epa_{s1.prec}")
+        check(fn(self._h, s1._h, _p(idx1), s2._h, _p(idx2), int(npairs), _p(simplices), _p(distances), _p(witness1),
+                 _p(witness2), _p(normals), C.c_void_p(int(stream))))
+
+    def gjk_epa_host(self, coords, off, cnt, pa, pb, want_normals=True):
+        """GJK + EPA over host buffers (one shared pool).  Returns a dict of arrays."""
+        coords = np.ascontiguousarray(coords)
+        prec, sdt = _PREC[coords.dtype]
+        coords = coords.reshape(-1, 3)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        cnt = np.ascontiguousarray(cnt, dtype=np.int32)
+        pa = np.ascontiguousarray(pa, dtype=np.int32)
+        pb = np.ascontiguousarray(pb, dtype=np.int32)
+        n = pa.shape[0]
+        dist = np.zeros(n, dtype=coords.dtype)
+        simp = np.zeros(n, dtype=sdt)
+        w1 = np.zeros((n, 3), dtype=coords.dtype)
+        w2 = np.zeros((n, 3), dtype=coords.dtype)
+        nr = np.zeros((n, 3), dtype=coords.dtype) if want_normals else None
+        fn = getattr(_lib.lib(), f"ogjk_gjk_epa_host_{prec}")
+        check(fn(self._h, n, _p(coords), _p(off), _p(cnt), cnt.shape[0], coords.shape[0], _p(pa), _p(coords), _p(off),
+                 _p(cnt), cnt.shape[0], coords.shape[0], _p(pb), _p(simp), _p(dist), _p(w1), _p(w2), _p(nr)))
+        return {"distances": dist, "simplices": simp, "witness1": w1, "witness2": w2, "normals": nr}
+
     def run_workload(self, w, want_simplices=True):
         return self.gjk_host(w.coords, w.off, w.cnt, w.pa, w.pb, want_simplices)
 
@@ -230,6 +261,71 @@ def compute_minimum_distance_indexed(polytopes, pairs, dtype=np.float32, engine=
         raise ValueError("pair index out of range")
     dist, simp = eng.gjk_host(coords, off, cnt, pairs[:, 0], pairs[:, 1])
     return _result(dist, simp)
+
+
+def _pair_pool(vertices1, vertices2, dtype):
+    c1, o1, k1 = _flatten(vertices1, dtype)
+    c2, o2, k2 = _flatten(vertices2, dtype)
+    if k1.shape[0] != k2.shape[0]:
+        raise ValueError(f"Mismatch: {k1.shape[0]} polytopes in bd1, {k2.shape[0]} in bd2")
+    n = k1.shape[0]
+    pa = np.arange(n, dtype=np.int32)
+    return np.concatenate([c1, c2]), np.concatenate([o1, o2 + c1.shape[0]]), np.concatenate([k1, k2]), pa, pa + n
+
+
+def compute_gjk_epa(vertices1, vertices2, dtype=np.float32, engine=None):
+    """GJK then EPA for colliding pairs (reference: opengjk_gpu.py:393-465).  Distances
+    are negative penetration depths for intersecting pairs."""
+    eng = engine or default_engine()
+    r = eng.gjk_epa_host(*_pair_pool(vertices1, vertices2, dtype), want_normals=False)
+    return {"distances": r["distances"], "is_collision": np.abs(r["distances"]) < 1e-6, "witnesses1": r["witness1"],
+            "witnesses2": r["witness2"], "simplex_nvrtx": r["simplices"]["nvrtx"].copy(), "simplices": r["simplices"]}
+
+
+def compute_epa(vertices1, vertices2, return_normals=False, dtype=np.float32, engine=None):
+    """Penetration depth, contact points and (optionally) contact normals
+    (reference: opengjk_gpu.py:319-390).  Unlike the reference wrapper, which feeds
+    the EPA kernel zero-initialised simplices, GJK is run first."""
+    eng = engine or default_engine()
+    r = eng.gjk_epa_host(*_pair_pool(vertices1, vertices2, dtype), want_normals=return_normals)
+    out = {"penetration_depths": r["distances"], "witnesses1": r["witness1"], "witnesses2": r["witness2"]}
+    if return_normals:
+        out["contact_normals"] = r["normals"]
+    return out
+
+
+def compute_gjk_epa_structs(bodies1, bodies2, dtype=np.float32, engine=None):
+    """ogjk_compute_gjk_epa_* followed by ogjk_compute_epa_* semantics check helper:
+    returns (dist, simp, w1, w2) of the fused call."""
+    eng = engine or default_engine()
+    prec, sdt = _PREC[np.dtype(dtype)]
+    a1, k1 = _struct_array(bodies1, dtype)
+    a2, k2 = _struct_array(bodies2, dtype)
+    n = len(bodies1)
+    simp = np.zeros(n, dtype=sdt)
+    dist = np.zeros(n, dtype=dtype)
+    w1 = np.zeros((n, 3), dtype=dtype)
+    w2 = np.zeros((n, 3), dtype=dtype)
+    fn = getattr(_lib.lib(), f"ogjk_compute_gjk_epa_{prec}")
+    check(fn(eng._h, n, C.cast(a1, C.c_void_p), C.cast(a2, C.c_void_p), _p(simp), _p(dist), _p(w1), _p(w2)))
+    return dist, simp, w1, w2
+
+
+def compute_epa_structs(bodies1, bodies2, simplices, distances, dtype=np.float32, engine=None):
+    """ogjk_compute_epa_*: EPA on caller-provided GJK results (simplices, distances)."""
+    eng = engine or default_engine()
+    prec, sdt = _PREC[np.dtype(dtype)]
+    a1, k1 = _struct_array(bodies1, dtype)
+    a2, k2 = _struct_array(bodies2, dtype)
+    n = len(bodies1)
+    simp = np.ascontiguousarray(simplices, dtype=sdt).copy()
+    dist = np.ascontiguousarray(distances, dtype=dtype).copy()
+    w1 = np.zeros((n, 3), dtype=dtype)
+    w2 = np.zeros((n, 3), dtype=dtype)
+    nr = np.zeros((n, 3), dtype=dtype)
+    fn = getattr(_lib.lib(), f"ogjk_compute_epa_{prec}")
+    check(fn(eng._h, n, C.cast(a1, C.c_void_p), C.cast(a2, C.c_void_p), _p(simp), _p(dist), _p(w1), _p(w2), _p(nr)))
+    return dist, w1, w2, nr
 
 
 # ---- struct-array entry points (the exact reference C signatures) -------------

@@ -16,6 +16,7 @@
 
 #include "../../include/opengjk_b200.h"
 #include "gjk_kernels.cuh"
+#include "epa_kernels.cuh"
 
 namespace {
 
@@ -94,6 +95,8 @@ struct ogjk_ctx_ {
   DevBuf counters;                    // 16 x u64 work-queue heads
   DevBuf sort_tmp;                    // hist | start | cursor (u32 each, kMaxKey+2)
   DevBuf sorted_list;                 // pair ids, size-sorted
+  DevBuf epa_list;                    // pair ids that need EPA (distance <= eps)
+  DevBuf d_w1, d_w2, d_nrm;           // EPA outputs of the host-buffer paths
   DevBuf small_list, large_list;      // raw modes
   ogjk_store_ scratch1, scratch2;     // raw device arrays are repacked into these
   // staging for the host-buffer paths
@@ -248,6 +251,29 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
   return OGJK_OK;
 }
 
+// EPA over a batch whose GJK results are on the device: pre-pass (defaults + work
+// list of penetrating pairs), then one warp per listed pair.  Timing slot 7.
+template <typename T>
+int run_store_epa(ogjk_ctx* ctx, const EpaArgs<T>& a, cudaStream_t st) {
+  if (a.npairs <= 0) return OGJK_OK;
+  if (a.npairs > 0x7fffffffll) return fail(OGJK_ERR_ARG, "npairs exceeds 2^31-1 per call%s");
+  int rc = ctx->counters.reserve(16 * sizeof(unsigned long long));
+  if (rc) return rc;
+  if ((rc = ctx->epa_list.reserve((size_t)a.npairs * sizeof(int)))) return rc;
+  auto* counters = static_cast<unsigned long long*>(ctx->counters.p);
+  CU(cudaMemsetAsync(counters + 8, 0, 2 * sizeof(unsigned long long), st));
+  int* list = static_cast<int*>(ctx->epa_list.p);
+  mark(ctx, st, 7, 0);
+  long long pb = (a.npairs + 255) / 256, pcap = (long long)ctx->sm_count * 16;
+  epa_prepass_kernel<T><<<(unsigned)(pb < pcap ? pb : pcap), 256, 0, st>>>(a, list, counters + 8);
+  long long eb = (a.npairs + kEpaWarps - 1) / kEpaWarps, ecap = (long long)ctx->sm_count * 8;
+  epa_warp_kernel<T><<<(unsigned)(eb < ecap ? eb : ecap), 32 * kEpaWarps, 0, st>>>(a, list, counters + 8, counters + 9);
+  mark(ctx, st, 7, 1);
+  ctx->launches += 2;
+  CU(cudaGetLastError());
+  return OGJK_OK;
+}
+
 template <typename T, typename S>
 int gjk_device(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t* off1, const int* cnt1, int64_t npoly1,
                int64_t nverts1, const int* idx1, const T* coords2, const int64_t* off2, const int* cnt2, int64_t npoly2,
@@ -297,16 +323,25 @@ int upload(ogjk_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
   return OGJK_OK;
 }
 
+// Host-buffer pipeline shared by every host entry point: upload the pools, repack
+// them into the scratch stores, run GJK and/or EPA, download.  With run_gjk ==
+// false the caller's simplices/distances are inputs (the reference's compute_epa).
 template <typename T, typename S>
-int gjk_host(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t* off1, const int* cnt1, int64_t npoly1,
-             int64_t nverts1, const int* idx1, const T* coords2, const int64_t* off2, const int* cnt2, int64_t npoly2,
-             int64_t nverts2, const int* idx2, S* simplices, T* distances) {
+int host_pipeline(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t* off1, const int* cnt1, int64_t npoly1,
+                  int64_t nverts1, const int* idx1, const T* coords2, const int64_t* off2, const int* cnt2, int64_t npoly2,
+                  int64_t nverts2, const int* idx2, S* simplices, T* distances, T* w1, T* w2, T* normals, bool run_gjk,
+                  bool run_epa) {
   if (!ctx) return fail(OGJK_ERR_ARG, "ctx is NULL%s");
   if (npairs < 0 || npoly1 < 0 || npoly2 < 0 || nverts1 < 0 || nverts2 < 0) return fail(OGJK_ERR_ARG, "negative count%s");
   if (npairs == 0) return OGJK_OK;
   if (!coords1 || !off1 || !cnt1 || !coords2 || !off2 || !cnt2 || !distances) return fail(OGJK_ERR_ARG, "NULL host pointer%s");
+  if (run_epa && (!w1 || !w2)) return fail(OGJK_ERR_ARG, "EPA needs witness output arrays%s");
+  if (!run_gjk && !simplices) return fail(OGJK_ERR_ARG, "EPA-only needs the GJK simplices%s");
+  if (npoly1 < 1 || npoly2 < 1) return fail(OGJK_ERR_ARG, "empty polytope pool%s");
   CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->own_stream;
   const bool shared_pool = (coords1 == coords2 && off1 == off2 && cnt1 == cnt2);
+  const bool need_simp = simplices != nullptr || run_epa;
   int rc;
   if ((rc = upload(ctx, ctx->d_coords1, coords1, (size_t)nverts1 * 3 * sizeof(T)))) return rc;
   if ((rc = upload(ctx, ctx->d_off1, off1, (size_t)npoly1 * sizeof(int64_t)))) return rc;
@@ -319,24 +354,63 @@ int gjk_host(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t* off
   }
   if (idx2 && (rc = upload(ctx, ctx->d_idx2, idx2, (size_t)npairs * sizeof(int)))) return rc;
   if ((rc = ctx->d_dist.reserve((size_t)npairs * sizeof(T)))) return rc;
-  if (simplices && (rc = ctx->d_simp.reserve((size_t)npairs * sizeof(S)))) return rc;
-
-  rc = gjk_device<T, S>(ctx, npairs, static_cast<const T*>(ctx->d_coords1.p),
-                        static_cast<const int64_t*>(ctx->d_off1.p), static_cast<const int*>(ctx->d_cnt1.p), npoly1, nverts1,
-                        idx1 ? static_cast<const int*>(ctx->d_idx1.p) : nullptr,
-                        static_cast<const T*>(shared_pool ? ctx->d_coords1.p : ctx->d_coords2.p),
-                        static_cast<const int64_t*>(shared_pool ? ctx->d_off1.p : ctx->d_off2.p),
-                        static_cast<const int*>(shared_pool ? ctx->d_cnt1.p : ctx->d_cnt2.p),
-                        shared_pool ? npoly1 : npoly2, shared_pool ? nverts1 : nverts2,
-                        idx2 ? static_cast<const int*>(ctx->d_idx2.p) : nullptr,
-                        simplices ? static_cast<S*>(ctx->d_simp.p) : nullptr, static_cast<T*>(ctx->d_dist.p),
-                        OGJK_MODE_AUTO, ctx->own_stream);
-  if (rc) return rc;
-  CU(cudaMemcpyAsync(distances, ctx->d_dist.p, (size_t)npairs * sizeof(T), cudaMemcpyDeviceToHost, ctx->own_stream));
-  if (simplices)
-    CU(cudaMemcpyAsync(simplices, ctx->d_simp.p, (size_t)npairs * sizeof(S), cudaMemcpyDeviceToHost, ctx->own_stream));
-  CU(cudaStreamSynchronize(ctx->own_stream));
+  if (need_simp && (rc = ctx->d_simp.reserve((size_t)npairs * sizeof(S)))) return rc;
+  if (!run_gjk) {
+    CU(cudaMemcpyAsync(ctx->d_simp.p, simplices, (size_t)npairs * sizeof(S), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_dist.p, distances, (size_t)npairs * sizeof(T), cudaMemcpyHostToDevice, st));
+  }
+  ctx->timed_mask = 0;
+  if ((rc = store_build<T>(ctx, &ctx->scratch1, npoly1, nverts1, static_cast<const T*>(ctx->d_coords1.p),
+                           static_cast<const int64_t*>(ctx->d_off1.p), static_cast<const int*>(ctx->d_cnt1.p), false, st)))
+    return rc;
+  if (!shared_pool &&
+      (rc = store_build<T>(ctx, &ctx->scratch2, npoly2, nverts2, static_cast<const T*>(ctx->d_coords2.p),
+                           static_cast<const int64_t*>(ctx->d_off2.p), static_cast<const int*>(ctx->d_cnt2.p), false, st)))
+    return rc;
+  const int* di1 = idx1 ? static_cast<const int*>(ctx->d_idx1.p) : nullptr;
+  const int* di2 = idx2 ? static_cast<const int*>(ctx->d_idx2.p) : nullptr;
+  if (run_gjk) {
+    StoreArgs<T> sa;
+    sa.s1 = view_of<T>(&ctx->scratch1);
+    sa.s2 = shared_pool ? sa.s1 : view_of<T>(&ctx->scratch2);
+    sa.idx1 = di1; sa.idx2 = di2;
+    sa.simplices = need_simp ? static_cast<GkSimplex<T>*>(ctx->d_simp.p) : nullptr;
+    sa.distances = static_cast<T*>(ctx->d_dist.p);
+    sa.npairs = npairs;
+    if ((rc = run_store_batch<T>(ctx, sa, st))) return rc;
+  }
+  if (run_epa) {
+    if ((rc = ctx->d_w1.reserve((size_t)npairs * 3 * sizeof(T)))) return rc;
+    if ((rc = ctx->d_w2.reserve((size_t)npairs * 3 * sizeof(T)))) return rc;
+    if (normals && (rc = ctx->d_nrm.reserve((size_t)npairs * 3 * sizeof(T)))) return rc;
+    EpaArgs<T> ea;
+    ea.s1 = view_of<T>(&ctx->scratch1);
+    ea.s2 = shared_pool ? ea.s1 : view_of<T>(&ctx->scratch2);
+    ea.idx1 = di1; ea.idx2 = di2;
+    ea.simplices = static_cast<const GkSimplex<T>*>(ctx->d_simp.p);
+    ea.distances = static_cast<T*>(ctx->d_dist.p);
+    ea.witness1 = static_cast<T*>(ctx->d_w1.p);
+    ea.witness2 = static_cast<T*>(ctx->d_w2.p);
+    ea.normals = normals ? static_cast<T*>(ctx->d_nrm.p) : nullptr;
+    ea.npairs = npairs;
+    if ((rc = run_store_epa<T>(ctx, ea, st))) return rc;
+    CU(cudaMemcpyAsync(w1, ctx->d_w1.p, (size_t)npairs * 3 * sizeof(T), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(w2, ctx->d_w2.p, (size_t)npairs * 3 * sizeof(T), cudaMemcpyDeviceToHost, st));
+    if (normals) CU(cudaMemcpyAsync(normals, ctx->d_nrm.p, (size_t)npairs * 3 * sizeof(T), cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaMemcpyAsync(distances, ctx->d_dist.p, (size_t)npairs * sizeof(T), cudaMemcpyDeviceToHost, st));
+  if (simplices && run_gjk)
+    CU(cudaMemcpyAsync(simplices, ctx->d_simp.p, (size_t)npairs * sizeof(S), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
   return OGJK_OK;
+}
+
+template <typename T, typename S>
+int gjk_host(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t* off1, const int* cnt1, int64_t npoly1,
+             int64_t nverts1, const int* idx1, const T* coords2, const int64_t* off2, const int* cnt2, int64_t npoly2,
+             int64_t nverts2, const int* idx2, S* simplices, T* distances) {
+  return host_pipeline<T, S>(ctx, npairs, coords1, off1, cnt1, npoly1, nverts1, idx1, coords2, off2, cnt2, npoly2, nverts2,
+                             idx2, simplices, distances, nullptr, nullptr, nullptr, true, false);
 }
 
 // Flatten an array of reference-shaped polytope structs (each with its own
@@ -386,6 +460,23 @@ int compute_min_dist(ogjk_ctx* ctx, int n, const P* bd1, const P* bd2, S* simpli
   if ((rc = flatten<T, P>(ctx, 0, n, bd1, &used1, &c1, &o1, &k1, &nv1))) return rc;
   if ((rc = flatten<T, P>(ctx, b1, n, bd2, &used2, &c2, &o2, &k2, &nv2))) return rc;
   return gjk_host<T, S>(ctx, n, c1, o1, k1, n, nv1, nullptr, c2, o2, k2, n, nv2, nullptr, simplices, distances);
+}
+
+// compute_gjk_epa (gpu/opengjk_gpu.cu:3055-3099) and compute_epa (:3007-3053) over struct arrays.
+template <typename T, typename P, typename S>
+int compute_epa_structs(ogjk_ctx* ctx, int n, const P* bd1, const P* bd2, S* simplices, T* distances, T* w1, T* w2,
+                        T* normals, bool run_gjk) {
+  if (n <= 0) return OGJK_OK;
+  if (!ctx || !bd1 || !bd2 || !simplices || !distances || !w1 || !w2) return fail(OGJK_ERR_ARG, "NULL argument%s");
+  CU(cudaSetDevice(ctx->device));
+  size_t b1 = flat_bytes(n, bd1, sizeof(T)), b2 = flat_bytes(n, bd2, sizeof(T));
+  int rc = ctx->h_stage.reserve(b1 + b2);
+  if (rc) return rc;
+  T *c1, *c2; int64_t *o1, *o2; int *k1, *k2; int64_t nv1, nv2; size_t used1, used2;
+  if ((rc = flatten<T, P>(ctx, 0, n, bd1, &used1, &c1, &o1, &k1, &nv1))) return rc;
+  if ((rc = flatten<T, P>(ctx, b1, n, bd2, &used2, &c2, &o2, &k2, &nv2))) return rc;
+  return host_pipeline<T, S>(ctx, n, c1, o1, k1, n, nv1, nullptr, c2, o2, k2, n, nv2, nullptr, simplices, distances, w1, w2,
+                             normals, run_gjk, true);
 }
 
 template <typename T, typename P, typename S>
@@ -487,6 +578,28 @@ int store_gjk(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_s
   return run_store_batch<T>(ctx, sa, static_cast<cudaStream_t>(stream));
 }
 
+template <typename T, typename S>
+int store_epa(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_store* s2, const int* idx2, int64_t npairs,
+              const S* simplices, T* distances, T* w1, T* w2, T* normals, void* stream) {
+  if (!ctx || !s1 || !s2 || !simplices || !distances || !w1 || !w2) return fail(OGJK_ERR_ARG, "NULL argument%s");
+  if (npairs < 0) return fail(OGJK_ERR_ARG, "npairs < 0%s");
+  if (npairs == 0) return OGJK_OK;
+  if (s1->prec != (int)sizeof(T) || s2->prec != (int)sizeof(T)) return fail(OGJK_ERR_ARG, "store precision mismatch%s");
+  if (s1->device != ctx->device || s2->device != ctx->device) return fail(OGJK_ERR_ARG, "store lives on another device%s");
+  if ((!idx1 && npairs > s1->npoly) || (!idx2 && npairs > s2->npoly))
+    return fail(OGJK_ERR_ARG, "npairs exceeds the pool size in un-indexed mode%s");
+  CU(cudaSetDevice(ctx->device));
+  EpaArgs<T> ea;
+  ea.s1 = view_of<T>(s1);
+  ea.s2 = view_of<T>(s2);
+  ea.idx1 = idx1; ea.idx2 = idx2;
+  ea.simplices = reinterpret_cast<const GkSimplex<T>*>(simplices);
+  ea.distances = distances;
+  ea.witness1 = w1; ea.witness2 = w2; ea.normals = normals;
+  ea.npairs = npairs;
+  return run_store_epa<T>(ctx, ea, static_cast<cudaStream_t>(stream));
+}
+
 }  // namespace
 
 extern "C" {
@@ -528,7 +641,8 @@ void ogjk_ctx_destroy(ogjk_ctx* c) {
   cudaDeviceSynchronize();
   ogjk_store_* ss[] = {&c->scratch1, &c->scratch2};
   for (ogjk_store_* q : ss) { q->data.release(); q->boff.release(); q->cnt.release(); q->scan_tmp.release(); }
-  c->sort_tmp.release(); c->sorted_list.release();
+  c->sort_tmp.release(); c->sorted_list.release(); c->epa_list.release();
+  c->d_w1.release(); c->d_w2.release(); c->d_nrm.release();
   DevBuf* bufs[] = {&c->counters, &c->small_list, &c->large_list, &c->d_coords1, &c->d_coords2, &c->d_off1, &c->d_off2,
                     &c->d_cnt1,   &c->d_cnt2,     &c->d_idx1,     &c->d_idx2,    &c->d_simp,    &c->d_dist};
   for (DevBuf* b : bufs) b->release();
@@ -666,5 +780,38 @@ int ogjk_single_rows_f64(ogjk_ctx* ctx, int n1, double* const* rows1, int n2, do
                          ogjk_simplex_f64* s, double* distance) {
   return single_rows<double, ogjk_simplex_f64>(ctx, n1, rows1, n2, rows2, s, distance);
 }
+
+#define OGJK_EPA_IMPL(SFX, T, P, S)                                                                                    \
+  int ogjk_store_epa_##SFX(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_store* s2, const int* idx2,   \
+                           int64_t npairs, const S* simplices, T* distances, T* witness1, T* witness2, T* normals,       \
+                           void* stream) {                                                                              \
+    return store_epa<T, S>(ctx, s1, idx1, s2, idx2, npairs, simplices, distances, witness1, witness2, normals, stream);  \
+  }                                                                                                                    \
+  int ogjk_store_gjk_epa_##SFX(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_store* s2,                \
+                               const int* idx2, int64_t npairs, S* simplices, T* distances, T* witness1, T* witness2,    \
+                               T* normals, void* stream) {                                                              \
+    if (!simplices) return fail(OGJK_ERR_ARG, "GJK+EPA needs the simplex array%s");                                     \
+    int rc = store_gjk<T, S>(ctx, s1, idx1, s2, idx2, npairs, simplices, distances, stream);                            \
+    if (rc) return rc;                                                                                                 \
+    return store_epa<T, S>(ctx, s1, idx1, s2, idx2, npairs, simplices, distances, witness1, witness2, normals, stream);  \
+  }                                                                                                                    \
+  int ogjk_gjk_epa_host_##SFX(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t* off1, const int* cnt1,      \
+                              int64_t npoly1, int64_t nverts1, const int* idx1, const T* coords2, const int64_t* off2,   \
+                              const int* cnt2, int64_t npoly2, int64_t nverts2, const int* idx2, S* simplices,           \
+                              T* distances, T* witness1, T* witness2, T* normals) {                                      \
+    return host_pipeline<T, S>(ctx, npairs, coords1, off1, cnt1, npoly1, nverts1, idx1, coords2, off2, cnt2, npoly2,     \
+                               nverts2, idx2, simplices, distances, witness1, witness2, normals, true, true);           \
+  }                                                                                                                    \
+  int ogjk_compute_gjk_epa_##SFX(ogjk_ctx* ctx, int n, const P* bd1, const P* bd2, S* simplices, T* distances,            \
+                                 T* witness1, T* witness2) {                                                            \
+    return compute_epa_structs<T, P, S>(ctx, n, bd1, bd2, simplices, distances, witness1, witness2, nullptr, true);     \
+  }                                                                                                                    \
+  int ogjk_compute_epa_##SFX(ogjk_ctx* ctx, int n, const P* bd1, const P* bd2, S* simplices, T* distances, T* witness1,   \
+                             T* witness2, T* contact_normals) {                                                         \
+    return compute_epa_structs<T, P, S>(ctx, n, bd1, bd2, simplices, distances, witness1, witness2, contact_normals,    \
+                                        false);                                                                         \
+  }
+OGJK_EPA_IMPL(f32, float, ogjk_polytope_f32, ogjk_simplex_f32)
+OGJK_EPA_IMPL(f64, double, ogjk_polytope_f64, ogjk_simplex_f64)
 
 }  // extern "C"

@@ -94,6 +94,26 @@ class Oracle(_Base):
                     _ptr(simp), _ptr(dist), _ptr(iters), C.c_int(nthreads))
         return (dist, simp, iters) if want_iters else (dist, simp)
 
+    def gjk_epa_batch(self, coords, off, cnt, pa, pb, nthreads=1, simplices=None, distances=None):
+        """GJK + EPA (oracle/epa_oracle.c).  With simplices/distances given, EPA only
+        (the reference's compute_epa).  Returns dict(distances, simplices, witness1,
+        witness2, normals, epa_iters)."""
+        coords, off, cnt, pa, pb, n, simp, dist = self._prep(coords, off, cnt, pa, pb)
+        run_gjk = 1
+        if simplices is not None:
+            simp = np.ascontiguousarray(simplices, dtype=self.sdt).copy()
+            dist = np.ascontiguousarray(distances, dtype=self.npf).copy()
+            run_gjk = 0
+        w1 = np.zeros((n, 3), dtype=self.npf)
+        w2 = np.zeros((n, 3), dtype=self.npf)
+        nr = np.zeros((n, 3), dtype=self.npf)
+        it = np.zeros(n, dtype=np.int32)
+        fn = getattr(self.lib, "oracle_gjk_epa_batch_" + self.prec)
+        fn.restype = None
+        fn(C.c_int64(n), _ptr(coords), _ptr(off), _ptr(cnt), _ptr(pa), _ptr(pb), _ptr(simp), _ptr(dist), _ptr(w1),
+           _ptr(w2), _ptr(nr), _ptr(it), C.c_int(run_gjk), C.c_int(nthreads))
+        return {"distances": dist, "simplices": simp, "witness1": w1, "witness2": w2, "normals": nr, "epa_iters": it}
+
     def sub(self, vrtx, idx=None):
         """Run S1D/S2D/S3D on a simplex given as (nvrtx,3); returns (v, simplex)."""
         vrtx = np.asarray(vrtx, dtype=self.npf).reshape(-1, 3)
