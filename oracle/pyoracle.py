@@ -196,3 +196,74 @@ class Reference(_Base):
         v = np.ones(3, dtype=self.npf)
         self.lib.ref_sub(_ptr(s), _ptr(v))
         return v, s[0]
+
+
+def polytope_dtype(prec):
+    """numpy mirror of the GPU flavour of gkPolytope (gpu/include/openGJK_GPU.h:71-76)."""
+    if prec == "f32":
+        return np.dtype({"names": ["numpoints", "s", "s_idx", "coord"], "formats": [np.int32, (np.float32, 3), np.int32, np.uint64],
+                         "offsets": [0, 4, 16, 24], "itemsize": 32})
+    return np.dtype({"names": ["numpoints", "s", "s_idx", "coord"], "formats": [np.int32, (np.float64, 3), np.int32, np.uint64],
+                     "offsets": [0, 8, 32, 40], "itemsize": 48})
+
+
+class ReferenceGPU(_Base):
+    """The reference's own CUDA library (gpu/opengjk_gpu.cu compiled unmodified, default
+    nvcc flags, by `make -C oracle ref_gpu`): the existing Blackwell-runnable kernels.
+    Used as a loose cross-check (it contracts FMAs, so it is not bit-comparable) and as
+    the "reference GPU kernel" baseline."""
+
+    def __init__(self, prec="f32"):
+        super().__init__(prec, os.path.join(HERE, "_ref", f"libopenGJK_GPU_ref_{prec}.so"))
+        self.pdt = polytope_dtype(prec)
+
+    @staticmethod
+    def available(prec="f32"):
+        return os.path.exists(os.path.join(HERE, "_ref", f"libopenGJK_GPU_ref_{prec}.so"))
+
+    def _bodies(self, coords, off, cnt, which):
+        arr = np.zeros(which.shape[0], dtype=self.pdt)
+        arr["numpoints"] = cnt[which]
+        arr["coord"] = coords.ctypes.data + off[which].astype(np.uint64) * np.uint64(3 * coords.itemsize)
+        return arr
+
+    def gjk(self, coords, off, cnt, pa, pb, epa=False):
+        coords, off, cnt, pa, pb, n, simp, dist = self._prep(coords, off, cnt, pa, pb)
+        b1, b2 = self._bodies(coords, off, cnt, pa), self._bodies(coords, off, cnt, pb)
+        if not epa:
+            self.lib.compute_minimum_distance(C.c_int(n), _ptr(b1), _ptr(b2), _ptr(simp), _ptr(dist))
+            return dist, simp
+        w1 = np.zeros((n, 3), dtype=self.npf)
+        w2 = np.zeros((n, 3), dtype=self.npf)
+        self.lib.compute_gjk_epa(C.c_int(n), _ptr(b1), _ptr(b2), _ptr(simp), _ptr(dist), _ptr(w1), _ptr(w2))
+        return dist, simp, w1, w2
+
+    def time_kernels(self, coords, off, cnt, pa, pb, reps=5, epa=False):
+        """Kernel-only milliseconds through the mid-level API (device arrays built once;
+        compute_*_device synchronises internally, gpu/opengjk_gpu.cu:3198-3201)."""
+        import time
+        coords, off, cnt, pa, pb, n, simp, dist = self._prep(coords, off, cnt, pa, pb)
+        b1, b2 = self._bodies(coords, off, cnt, pa), self._bodies(coords, off, cnt, pb)
+        vp = C.c_void_p
+        d = [vp() for _ in range(6)]
+        L = self.lib
+        L.allocate_and_copy_device_arrays(C.c_int(n), _ptr(b1), _ptr(b2), *[C.byref(x) for x in d])
+        e = [vp() for _ in range(3)]
+        if epa:
+            L.allocate_epa_device_arrays(C.c_int(n), *[C.byref(x) for x in e])
+        out = {}
+        L.compute_minimum_distance_device(C.c_int(n), d[0], d[1], d[4], d[5])
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            L.compute_minimum_distance_device(C.c_int(n), d[0], d[1], d[4], d[5])
+        out["gjk_ms"] = 1e3 * (time.perf_counter() - t0) / reps
+        if epa:
+            L.compute_epa_device(C.c_int(n), d[0], d[1], d[4], d[5], e[0], e[1], e[2])
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                L.compute_minimum_distance_device(C.c_int(n), d[0], d[1], d[4], d[5])
+                L.compute_epa_device(C.c_int(n), d[0], d[1], d[4], d[5], e[0], e[1], e[2])
+            out["gjk_epa_ms"] = 1e3 * (time.perf_counter() - t0) / reps
+            L.free_epa_device_arrays(e[0], e[1], e[2])
+        L.free_device_arrays(*d)
+        return out

@@ -92,7 +92,8 @@ def test_analytic_box_penetration(eng, prec, dt, tol):
     r = api.compute_epa(A, B, True, dt, eng)
     assert np.allclose(-r["penetration_depths"], depths, atol=tol)
     assert np.allclose(np.abs(r["contact_normals"][:, 0]), 1.0, atol=tol)
-    assert np.allclose(np.linalg.norm(r["witnesses1"] - r["witnesses2"], axis=1), depths, atol=10 * tol)
+    # face-face contact: the witness pair is not unique sideways, but its separation along the normal is the depth
+    assert np.allclose(np.abs(r["witnesses1"][:, 0] - r["witnesses2"][:, 0]), depths, atol=10 * tol)
 
 
 def test_reference_suite_ranges(eng):
@@ -117,3 +118,25 @@ def test_reference_suite_ranges(eng):
     assert r["simplex_nvrtx"][0] >= 3 and r["distances"][0] < 0
     assert np.linalg.norm(r["witnesses1"][0]) <= 1.1 and np.linalg.norm(r["witnesses2"][0] - [1.0, 0, 0]) <= 1.1
     assert -1.1 < r["distances"][0] < -0.9
+
+
+def test_loose_agreement_with_reference_cuda_library(eng):
+    """The reference's own CUDA kernels (compiled unmodified into oracle/_ref, FMA
+    contraction on) on the same GPU: GJK distances agree to fp32 rounding; EPA depths
+    agree for the overwhelming majority of pairs (the reference EPA is not
+    bit-reproducible: FMA, and divergent shuffles on degenerate faces)."""
+    from oracle.pyoracle import ReferenceGPU
+    if not ReferenceGPU.available("f32"):
+        pytest.skip("oracle/_ref/libopenGJK_GPU_ref_f32.so not shipped")
+    ref = ReferenceGPU("f32")
+    w = W.mixed_hulls(20000, seed=21, dtype=np.float32)
+    dr, sr = ref.gjk(w.coords, w.off, w.cnt, w.pa, w.pb)
+    d, s = eng.run_workload(w)
+    close = np.isclose(d, dr, rtol=1e-4, atol=1e-5)
+    assert close.mean() > 0.999, close.mean()
+    assert (s["nvrtx"] == sr["nvrtx"]).mean() > 0.97
+    w = W.random_hulls(5000, 8, 64, 23, 1.0, np.float32, 0.5)
+    dr, sr, w1r, w2r = ref.gjk(w.coords, w.off, w.cnt, w.pa, w.pb, epa=True)
+    got = eng.gjk_epa_host(w.coords, w.off, w.cnt, w.pa, w.pb)
+    ok = np.isclose(got["distances"], dr, rtol=1e-3, atol=1e-4)
+    assert ok.mean() > 0.97, ok.mean()
