@@ -36,7 +36,7 @@ from opengjk_b200 import workloads as W  # noqa: E402
 
 L2_BYTES = 126e6
 # scheduler table: (hi_key, lanes per pair); key = (pad4(n1)+pad4(n2))/4; lanes 0 = register-resident kernel
-CLASS_TABLE = [(4, 0), (24, 4), (64, 8), (192, 16), (2048, 32)]
+CLASS_TABLE = [(4, 0), (32, 2), (128, 8), (2048, 32)]
 
 WORKLOADS = {
     # name: (description, dtype, maker(npairs, seed), default pairs per GPU)

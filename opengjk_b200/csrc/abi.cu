@@ -85,9 +85,10 @@ struct ogjk_ctx_ {
   long long launches = 0;
   // scheduler classes: pairs with sort key <= hi[c] (and > hi[c-1]) run with lanes[c]
   // cooperating lanes per pair; lanes 0 = register-resident thread-per-pair kernel.
-  int nclasses = 5;
-  int class_hi[kMaxClasses] = {4, 24, 64, 192, 2048, 2048};
-  int class_lanes[kMaxClasses] = {0, 4, 8, 16, 32, 32};
+  // defaults from the B200 sweep (tools/tune_classes.py, profiles/r1_lanes_sweep.txt)
+  int nclasses = 4;
+  int class_hi[kMaxClasses] = {4, 32, 128, 2048, 2048, 2048};
+  int class_lanes[kMaxClasses] = {0, 2, 8, 32, 32, 32};
   bool timing = false;
   cudaEvent_t ev[2 * kPhases] = {};
   int timed_mask = 0;
@@ -196,6 +197,51 @@ void launch_group(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const u
   gjk_group_kernel<T, G><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, list, b, e, head);
 }
 
+// Shared-memory slot size for a staged class: room for 4*hi_key vertices, rounded so
+// that slot_bytes = 16*G (mod 128) (bank spreading, see gjk_staged_kernel).
+template <typename T> int staged_slot_bytes(int hi_key, int G) {
+  long long bytes = 4ll * hi_key * 3 * (long long)sizeof(T);
+  bytes = (bytes + 127) & ~127ll;
+  if (G < 8) bytes += 16 * G;
+  const long long limit = 227ll * 1024 / (128 / G);  // slots per block = 128 / G
+  return bytes <= limit ? (int)bytes : 0;             // 0: does not fit, do not stage
+}
+
+template <typename T, int G>
+int launch_staged(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const unsigned* b, const unsigned* e,
+                  unsigned long long* head, int hi_key, cudaStream_t st) {
+  const int slot = staged_slot_bytes<T>(hi_key, G);
+  if (slot == 0 || hi_key >= kMaxKey) {  // open-ended or oversized class: read global memory instead
+    launch_group<T, G>(ctx, a, list, b, e, head, st);
+    return OGJK_OK;
+  }
+  const size_t smem = (size_t)(128 / G) * slot;
+  static size_t configured = 0;  // per instantiation
+  if (smem > configured) {
+    CU(cudaFuncSetAttribute(gjk_staged_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  long long blocks = (a.npairs * G + 127) / 128, cap = (long long)ctx->sm_count * 16;
+  gjk_staged_kernel<T, G><<<(unsigned)(blocks < cap ? blocks : cap), 128, smem, st>>>(a, list, b, e, head, slot);
+  return OGJK_OK;
+}
+
+// Persistent-lane flavour: iterate kernel, then (when simplices are wanted) the witness pass
+// over the same list segment.
+template <typename T, int G>
+void launch_persist(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const unsigned* b, const unsigned* e,
+                    unsigned long long* head, cudaStream_t st) {
+  long long blocks = (a.npairs * (G ? G : 1) + 127) / 128, cap = (long long)ctx->sm_count * 16;
+  const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+  if (G == 0) gjk_persist_small_kernel<T><<<grid, 128, 0, st>>>(a, list, b, e, head);
+  else gjk_persist_group_kernel<T, (G ? G : 1)><<<grid, 128, 0, st>>>(a, list, b, e, head);
+  if (a.simplices) {
+    long long wb = (a.npairs + 255) / 256, wcap = (long long)ctx->sm_count * 16;
+    gjk_witness_kernel<T><<<(unsigned)(wb < wcap ? wb : wcap), 256, 0, st>>>(a, list, b, e);
+    ctx->launches += 1;
+  }
+}
+
 // The batch scheduler: counting sort by size, then one launch per size class.
 template <typename T>
 int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
@@ -241,8 +287,22 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
       case 4: launch_group<T, 4>(ctx, a, sorted, b, e, head, st); break;
       case 8: launch_group<T, 8>(ctx, a, sorted, b, e, head, st); break;
       case 16: launch_group<T, 16>(ctx, a, sorted, b, e, head, st); break;
-      default: launch_group<T, 32>(ctx, a, sorted, b, e, head, st); break;
+      case 32: launch_group<T, 32>(ctx, a, sorted, b, e, head, st); break;
+      case 200: launch_persist<T, 0>(ctx, a, sorted, b, e, head, st); break;
+      case 201: launch_persist<T, 1>(ctx, a, sorted, b, e, head, st); break;
+      case 202: launch_persist<T, 2>(ctx, a, sorted, b, e, head, st); break;
+      case 204: launch_persist<T, 4>(ctx, a, sorted, b, e, head, st); break;
+      case 208: launch_persist<T, 8>(ctx, a, sorted, b, e, head, st); break;
+      case 216: launch_persist<T, 16>(ctx, a, sorted, b, e, head, st); break;
+      case 232: launch_persist<T, 32>(ctx, a, sorted, b, e, head, st); break;
+      case 101: rc = launch_staged<T, 1>(ctx, a, sorted, b, e, head, hi, st); break;
+      case 102: rc = launch_staged<T, 2>(ctx, a, sorted, b, e, head, hi, st); break;
+      case 104: rc = launch_staged<T, 4>(ctx, a, sorted, b, e, head, hi, st); break;
+      case 108: rc = launch_staged<T, 8>(ctx, a, sorted, b, e, head, hi, st); break;
+      case 116: rc = launch_staged<T, 16>(ctx, a, sorted, b, e, head, hi, st); break;
+      default: rc = launch_staged<T, 32>(ctx, a, sorted, b, e, head, hi, st); break;
     }
+    if (rc) return rc;
     mark(ctx, st, 2 + c, 1);
     ctx->launches += 1;
     lo = hi;
@@ -680,8 +740,11 @@ int ogjk_ctx_set_classes(ogjk_ctx* c, int n, const int* hi_keys, const int* lane
   int prev = 0;
   for (int i = 0; i < n; ++i) {
     const int l = lanes[i];
-    if (!(l == 0 || l == 1 || l == 2 || l == 4 || l == 8 || l == 16 || l == 32)) return fail(OGJK_ERR_ARG, "lanes must be 0 or a power of two <= 32%s");
-    if (l == 0 && hi_keys[i] > kSmallKeyMax) return fail(OGJK_ERR_ARG, "register-resident class is limited to key <= 4%s");
+    // 100 + G: shared-memory staged flavour; 200 + G: persistent-lane flavour (200 = register-resident)
+    const int gl = l >= 200 ? l - 200 : (l >= 100 ? l - 100 : l);
+    if (!((gl == 0 && (l == 0 || l == 200)) || gl == 1 || gl == 2 || gl == 4 || gl == 8 || gl == 16 || gl == 32))
+      return fail(OGJK_ERR_ARG, "lanes must be 0, a power of two <= 32, or 100/200 + that%s");
+    if (gl == 0 && hi_keys[i] > kSmallKeyMax) return fail(OGJK_ERR_ARG, "register-resident class is limited to key <= 4%s");
     if (hi_keys[i] <= prev) return fail(OGJK_ERR_ARG, "class keys must increase%s");
     prev = hi_keys[i];
   }

@@ -82,39 +82,59 @@ template <typename T> struct WarpBody {
   }
 };
 
-// ---- one GJK query (openGJK.c:941-1046) ---------------------------------------
-// Returns the distance; fills `s` (post-witness simplex) and the witnesses.
+// Both support calls of one GJK iteration (openGJK.c:992-993): body 1 along -v,
+// body 2 along +v.  (A fused single-stream scan of both bodies was measured and was
+// slower than two 2-chunk-per-trip scans: less ILP per trip.)
 template <typename T, typename Body>
-OGJK_DI T gjk_query(const Body& b1, const Body& b2, Splx<T>& s, V3<T>& wit1, V3<T>& wit2) {
-  V3<T> sa = b1.vertex(0), sb = b2.vertex(0);
-  int ia = 0, ib = 0;
-  V3<T> v = sub(sa, sb);
+OGJK_DI void support_both(const Body& b1, const Body& b2, const V3<T>& v, V3<T>& sa, int& ia, V3<T>& sb, int& ib) {
+  b1.support(-v.x, -v.y, -v.z, sa, ia);
+  b2.support(v.x, v.y, v.z, sb, ib);
+}
+
+// ---- one GJK query (openGJK.c:941-1046), split into init / step / finish --------
+template <typename T> struct GjkState {
+  V3<T> v, sa, sb;   // search direction, carried support points of body 1 / body 2
+  int ia, ib;        // their vertex indices
+  Splx<T> s;
+  T wmax2;
+  int k;
+};
+
+// :957-980
+template <typename T, typename Body>
+OGJK_DI void gjk_init(const Body& b1, const Body& b2, GjkState<T>& st) {
+  st.sa = b1.vertex(0);
+  st.sb = b2.vertex(0);
+  st.ia = 0; st.ib = 0;
+  st.v = sub(st.sa, st.sb);
   const MV<T> zero = MV<T>{(T)0, (T)0, (T)0, 0, 0};
-  s.n = 1;
-  s.q0 = MV<T>{v.x, v.y, v.z, 0, 0};
-  s.q1 = zero; s.q2 = zero; s.q3 = zero;
+  st.s.n = 1;
+  st.s.q0 = MV<T>{st.v.x, st.v.y, st.v.z, 0, 0};
+  st.s.q1 = zero; st.s.q2 = zero; st.s.q3 = zero;
+  st.wmax2 = (T)0;
+  st.k = 0;
+}
 
+// One pass of the do-while at :983-1036.  Returns true when the query is finished.
+template <typename T, typename Body>
+OGJK_DI bool gjk_step(const Body& b1, const Body& b2, GjkState<T>& st) {
   const T er = eps_rel<T>(), ea = eps_abs<T>();
-  const T er2 = er * er;
-  T wmax2 = (T)0;
-  int k = 0;
-  do {
-    k++;
-    b1.support(-v.x, -v.y, -v.z, sa, ia);
-    b2.support(v.x, v.y, v.z, sb, ib);
-    const V3<T> w = sub(sa, sb);
+  st.k++;
+  support_both(b1, b2, st.v, st.sa, st.ia, st.sb, st.ib);
+  const V3<T> w = sub(st.sa, st.sb);
+  const T vv = nrm2(st.v.x, st.v.y, st.v.z);
+  const T gap = vv - dot3(st.v, w);
+  if (gap <= (er * vv) || gap < ea) return true;   // :1002-1006
+  if (vv < er * er) return true;                     // :1008-1010
+  push_and_solve(st.s, MV<T>{w.x, w.y, w.z, st.ia, st.ib}, st.v);
+  st.wmax2 = update_wmax(st.s, st.wmax2);
+  if (nrm2(st.v.x, st.v.y, st.v.z) <= (ea * ea * st.wmax2)) return true;  // :1032
+  return st.s.n == 4 || st.k == kMaxIter;
+}
 
-    const T vv = nrm2(v.x, v.y, v.z);
-    const T gap = vv - dot3(v, w);
-    if (gap <= (er * vv) || gap < ea) break;   // :1002-1006
-    if (vv < er2) break;                         // :1008-1010
-
-    push_and_solve(s, MV<T>{w.x, w.y, w.z, ia, ib}, v);
-
-    wmax2 = update_wmax(s, wmax2);
-    if (nrm2(v.x, v.y, v.z) <= (ea * ea * wmax2)) break;  // :1032
-  } while (s.n != 4 && k != kMaxIter);
-
+// compute_witnesses (:921-939): may reduce `s`; blends the source vertices.
+template <typename T, typename Body>
+OGJK_DI void gjk_witnesses(const Body& b1, const Body& b2, Splx<T>& s, V3<T>& wit1, V3<T>& wit2) {
   const Wts<T> a = witness_weights(s);
   const V3<T> p0 = b1.vertex(s.q0.ia), r0 = b2.vertex(s.q0.ib);
   if (a.terms == 1) {
@@ -142,7 +162,17 @@ OGJK_DI T gjk_query(const Body& b1, const Body& b2, Splx<T>& s, V3<T>& wit1, V3<
       }
     }
   }
-  return sqrt(nrm2(v.x, v.y, v.z));  // :1045 (IEEE sqrt; double rounding via double is innocuous)
+}
+
+// Returns the distance; fills `s` (post-witness simplex) and the witnesses.
+template <typename T, typename Body>
+OGJK_DI T gjk_query(const Body& b1, const Body& b2, Splx<T>& s, V3<T>& wit1, V3<T>& wit2) {
+  GjkState<T> st;
+  gjk_init(b1, b2, st);
+  while (!gjk_step(b1, b2, st)) {}
+  s = st.s;
+  gjk_witnesses(b1, b2, s, wit1, wit2);
+  return sqrt(nrm2(st.v.x, st.v.y, st.v.z));  // :1045 (IEEE sqrt; double rounding via double is innocuous)
 }
 
 template <typename T>
@@ -261,12 +291,38 @@ template <typename T, int G> struct GroupBody {
     T best = dot3(cur.x, cur.y, cur.z, dx, dy, dz);
     int better = 0x7fffffff;
     const int nchunks = np / CV;
-#pragma unroll 2
-    for (int c = g; c < nchunks; c += G) {
+    const T* xp = blk;
+    const T* yp = blk + np;
+    const T* zp = blk + 2 * np;
+    // Two chunks per trip.  The common case -- nothing in the chunk pair beats the
+    // running best -- costs one max-tree and one compare; the exact "strictly
+    // greater, ascending index" update runs only when the max says it must.
+    int c = g;
+    for (; c + G < nchunks; c += 2 * G) {
+      Chunk<T> X0, Y0, Z0, X1, Y1, Z1;
+      X0.load(xp + CV * c); Y0.load(yp + CV * c); Z0.load(zp + CV * c);
+      X1.load(xp + CV * (c + G)); Y1.load(yp + CV * (c + G)); Z1.load(zp + CV * (c + G));
+      T s0[CV], s1[CV];
+#pragma unroll
+      for (int t = 0; t < CV; ++t) {
+        s0[t] = dot3(X0.v[t], Y0.v[t], Z0.v[t], dx, dy, dz);
+        s1[t] = dot3(X1.v[t], Y1.v[t], Z1.v[t], dx, dy, dz);
+      }
+      T m = fmax(s0[0], s1[0]);
+#pragma unroll
+      for (int t = 1; t < CV; ++t) m = fmax(m, fmax(s0[t], s1[t]));
+      if (m > best) {
+#pragma unroll
+        for (int t = 0; t < CV; ++t)
+          if (s0[t] > best) { best = s0[t]; better = CV * c + t; }
+#pragma unroll
+        for (int t = 0; t < CV; ++t)
+          if (s1[t] > best) { best = s1[t]; better = CV * (c + G) + t; }
+      }
+    }
+    if (c < nchunks) {
       Chunk<T> X, Y, Z;
-      X.load(blk + CV * c);
-      Y.load(blk + np + CV * c);
-      Z.load(blk + 2 * np + CV * c);
+      X.load(xp + CV * c); Y.load(yp + CV * c); Z.load(zp + CV * c);
 #pragma unroll
       for (int t = 0; t < CV; ++t) {
         const T sc = dot3(X.v[t], Y.v[t], Z.v[t], dx, dy, dz);
@@ -287,7 +343,7 @@ template <typename T, int G> struct GroupBody {
 // list when `list` is null) is consumed through a device-side work queue, 32/G
 // pairs per grab.
 template <typename T, int G>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 gjk_group_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* __restrict__ seg_begin,
                  const unsigned* __restrict__ seg_end, unsigned long long* __restrict__ head) {
   constexpr int PER_WARP = 32 / G;
@@ -317,6 +373,68 @@ gjk_group_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* _
         a.distances[p] = d;
         if (a.simplices) store_simplex(a.simplices + p, s, w1, w2);
       }
+    }
+  }
+}
+
+// Shared-memory staged flavour of the group kernel (north_star item 1: "staged into
+// shared memory").  GJK re-reads both polytopes once per iteration (3..8 times per
+// query); with tens of thousands of pairs in flight those re-reads overflow L1 and
+// L2 and the first-generation kernels stalled on `long_scoreboard`.  Here every
+// G-lane group owns a shared-memory slot: the pair's two store blocks (each one
+// contiguous, 16-byte aligned range) are copied in once with 128-bit loads, and
+// every support scan and witness lookup then reads shared memory.  Slots are
+// `slot_bytes` apart with slot_bytes = 16*G (mod 128), which keeps the 128-bit
+// shared loads of neighbouring groups on disjoint banks.  The host routes a size class
+// here only when every pair of the class fits a slot.
+template <typename T, int G>
+__global__ void __launch_bounds__(128)
+gjk_staged_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* __restrict__ seg_begin,
+                  const unsigned* __restrict__ seg_end, unsigned long long* __restrict__ head, int slot_bytes) {
+  extern __shared__ uint4 ogjk_stage[];
+  constexpr int PER_WARP = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int g = lane % G;
+  const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - g));
+  uint4* slot = ogjk_stage + (size_t)(threadIdx.x / G) * (slot_bytes / 16);
+  const long long begin = seg_begin ? (long long)*seg_begin : 0;
+  const long long end = seg_end ? (long long)*seg_end : a.npairs;
+  for (;;) {
+    unsigned long long got = 0;
+    if (lane == 0) got = atomicAdd(head, (unsigned long long)PER_WARP);
+    got = __shfl_sync(0xffffffffu, got, 0);
+    const long long base = begin + (long long)got;
+    if (base >= end) break;
+    const long long idx = base + lane / G;
+    if (idx < end) {
+      const long long p = list ? (long long)list[idx] : idx;
+      const long long h1 = a.idx1 ? (long long)a.idx1[p] : p;
+      const long long h2 = a.idx2 ? (long long)a.idx2[p] : p;
+      const int n1 = a.s1.cnt[h1], n2 = a.s2.cnt[h2];
+      const int np1 = pad4(n1), np2 = pad4(n2);
+      const T* src1 = a.s1.data + a.s1.boff[h1];
+      const T* src2 = a.s2.data + a.s2.boff[h2];
+      const int c1 = 3 * np1 * (int)sizeof(T) / 16, c2 = 3 * np2 * (int)sizeof(T) / 16;
+      // the host only routes a class here when every pair of the class fits its slot
+      const uint4* s1v = reinterpret_cast<const uint4*>(src1);
+      const uint4* s2v = reinterpret_cast<const uint4*>(src2);
+#pragma unroll 4
+      for (int c = g; c < c1; c += G) slot[c] = s1v[c];
+#pragma unroll 4
+      for (int c = g; c < c2; c += G) slot[c1 + c] = s2v[c];
+      const T* blk1 = reinterpret_cast<const T*>(slot);
+      const T* blk2 = reinterpret_cast<const T*>(slot + c1);
+      __syncwarp(mask);
+      GroupBody<T, G> b1{blk1, n1, np1, g, mask};
+      GroupBody<T, G> b2{blk2, n2, np2, g, mask};
+      Splx<T> s;
+      V3<T> w1, w2;
+      const T d = gjk_query<T>(b1, b2, s, w1, w2);
+      if (g == 0) {
+        a.distances[p] = d;
+        if (a.simplices) store_simplex(a.simplices + p, s, w1, w2);
+      }
+      __syncwarp(mask);  // everyone is done reading the slot before it is refilled
     }
   }
 }
@@ -381,6 +499,146 @@ gjk_small_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* _
       a.distances[p] = d;
       if (a.simplices) store_simplex(a.simplices + p, s, w1, w2);
     }
+  }
+}
+
+// =============================================================================
+// Persistent-lane kernels: refill on termination, witnesses in a second pass
+// =============================================================================
+// GJK needs 1..25 iterations per pair (mean ~5).  With one batch of pairs per warp,
+// every lane waits for the slowest pair of its warp (ncu: 10-12 of 32 lanes active).
+// Here a lane (or G-lane group) that finishes its pair writes the raw result -- the
+// distance and the pre-witness simplex, straight into the output gkSimplex -- and
+// takes the next pair from the queue at the top of the next round, so every round
+// runs one GJK iteration for (almost) every lane.  The witness reconstruction,
+// which is short and divergent, is left to gjk_witness_kernel over all pairs.
+
+template <typename T>
+OGJK_DI void store_raw(const StoreArgs<T>& a, long long p, const GjkState<T>& st) {
+  a.distances[p] = sqrt(nrm2(st.v.x, st.v.y, st.v.z));
+  if (a.simplices) {
+    const V3<T> z{(T)0, (T)0, (T)0};
+    store_simplex(a.simplices + p, st.s, z, z);
+  }
+}
+
+// Warp-aggregated queue grab for the group leaders in `need` (a ballot of leader
+// lanes).  Returns this group's queue position or -1.
+OGJK_DI long long grab_slots(unsigned need, int leader_lane, int lane, long long begin, long long end,
+                             unsigned long long* head) {
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(head, (unsigned long long)__popc(need));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (!((need >> leader_lane) & 1u)) return -1;
+  const long long slot = begin + (long long)base + __popc(need & ((1u << leader_lane) - 1u));
+  return slot < end ? slot : -1;
+}
+
+template <typename T, int G>
+__global__ void __launch_bounds__(128, 4)
+gjk_persist_group_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* __restrict__ seg_begin,
+                         const unsigned* __restrict__ seg_end, unsigned long long* __restrict__ head) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane % G;
+  const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - g));
+  const long long begin = seg_begin ? (long long)*seg_begin : 0;
+  const long long end = seg_end ? (long long)*seg_end : a.npairs;
+  GroupBody<T, G> b1{nullptr, 0, 0, g, mask}, b2{nullptr, 0, 0, g, mask};
+  GjkState<T> st;
+  long long p = -1;
+  bool active = false, dry = false;
+  for (;;) {
+    __syncwarp();
+    const unsigned need = __ballot_sync(0xffffffffu, !active && !dry && g == 0);
+    if (need) {
+      const long long slot = grab_slots(need, lane - g, lane, begin, end, head);
+      if (!active && !dry) {
+        if (slot >= 0) {
+          p = list ? (long long)list[slot] : slot;
+          const long long h1 = a.idx1 ? (long long)a.idx1[p] : p;
+          const long long h2 = a.idx2 ? (long long)a.idx2[p] : p;
+          const int n1 = a.s1.cnt[h1], n2 = a.s2.cnt[h2];
+          b1.blk = a.s1.data + a.s1.boff[h1]; b1.n = n1; b1.np = pad4(n1);
+          b2.blk = a.s2.data + a.s2.boff[h2]; b2.n = n2; b2.np = pad4(n2);
+          gjk_init(b1, b2, st);
+          active = true;
+        } else {
+          dry = true;
+        }
+      }
+    }
+    if (!__ballot_sync(0xffffffffu, active)) break;
+    if (active && gjk_step(b1, b2, st)) {
+      if (g == 0) store_raw(a, p, st);
+      active = false;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128, (sizeof(T) == 8 ? 2 : 4))
+gjk_persist_small_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* __restrict__ seg_begin,
+                         const unsigned* __restrict__ seg_end, unsigned long long* __restrict__ head) {
+  const int lane = threadIdx.x & 31;
+  const long long begin = seg_begin ? (long long)*seg_begin : 0;
+  const long long end = seg_end ? (long long)*seg_end : a.npairs;
+  RegBody<T> b1, b2;
+  GjkState<T> st;
+  long long p = -1;
+  bool active = false, dry = false;
+  for (;;) {
+    __syncwarp();
+    const unsigned need = __ballot_sync(0xffffffffu, !active && !dry);
+    if (need) {
+      const long long slot = grab_slots(need, lane, lane, begin, end, head);
+      if (!active && !dry) {
+        if (slot >= 0) {
+          p = list ? (long long)list[slot] : slot;
+          const long long h1 = a.idx1 ? (long long)a.idx1[p] : p;
+          const long long h2 = a.idx2 ? (long long)a.idx2[p] : p;
+          b1.load(a.s1.data + a.s1.boff[h1], pad4(a.s1.cnt[h1]));
+          b2.load(a.s2.data + a.s2.boff[h2], pad4(a.s2.cnt[h2]));
+          gjk_init(b1, b2, st);
+          active = true;
+        } else {
+          dry = true;
+        }
+      }
+    }
+    if (!__ballot_sync(0xffffffffu, active)) break;
+    if (active && gjk_step(b1, b2, st)) {
+      store_raw(a, p, st);
+      active = false;
+    }
+  }
+}
+
+// Second pass: witness reconstruction for every pair, thread per pair, in place on
+// the raw simplices written by the persistent kernels.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gjk_witness_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* __restrict__ seg_begin,
+                   const unsigned* __restrict__ seg_end) {
+  const long long begin = seg_begin ? (long long)*seg_begin : 0;
+  const long long end = seg_end ? (long long)*seg_end : a.npairs;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
+    const long long p = list ? (long long)list[i] : i;
+    GkSimplex<T>* o = a.simplices + p;
+    Splx<T> s;
+    s.n = o->nvrtx;
+    s.q0 = MV<T>{o->vrtx[0][0], o->vrtx[0][1], o->vrtx[0][2], o->vrtx_idx[0][0], o->vrtx_idx[0][1]};
+    s.q1 = MV<T>{o->vrtx[1][0], o->vrtx[1][1], o->vrtx[1][2], o->vrtx_idx[1][0], o->vrtx_idx[1][1]};
+    s.q2 = MV<T>{o->vrtx[2][0], o->vrtx[2][1], o->vrtx[2][2], o->vrtx_idx[2][0], o->vrtx_idx[2][1]};
+    s.q3 = MV<T>{o->vrtx[3][0], o->vrtx[3][1], o->vrtx[3][2], o->vrtx_idx[3][0], o->vrtx_idx[3][1]};
+    const long long h1 = a.idx1 ? (long long)a.idx1[p] : p;
+    const long long h2 = a.idx2 ? (long long)a.idx2[p] : p;
+    const int n1 = a.s1.cnt[h1], n2 = a.s2.cnt[h2];
+    const GroupBody<T, 1> b1{a.s1.data + a.s1.boff[h1], n1, pad4(n1), 0, 0u};
+    const GroupBody<T, 1> b2{a.s2.data + a.s2.boff[h2], n2, pad4(n2), 0, 0u};
+    V3<T> w1, w2;
+    gjk_witnesses(b1, b2, s, w1, w2);
+    store_simplex(o, s, w1, w2);
   }
 }
 

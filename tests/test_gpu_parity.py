@@ -106,7 +106,7 @@ def test_random_batches_vs_oracle(eng, prec, dt, maker):
     _assert_same(w.name, d, s, dref, sref, prec)
 
 
-DEFAULT_CLASSES = [(4, 0), (24, 4), (64, 8), (192, 16), (2048, 32)]
+DEFAULT_CLASSES = [(4, 0), (32, 2), (128, 8), (2048, 32)]
 
 
 @pytest.mark.parametrize("prec,dt", PRECS)
@@ -116,6 +116,12 @@ def test_scheduler_classes_do_not_change_results(eng, prec, dt):
     base = _gpu(eng, w, api.MODE_THREAD)
     tables = [[(2048, g)] for g in (1, 2, 4, 8, 16, 32)] + [
         [(4, 0), (2048, 1)], [(4, 0), (8, 2), (16, 4), (32, 8), (64, 16), (2048, 32)], [(3, 1), (5, 32), (2048, 2)]]
+    # shared-memory staged flavours (100 + lanes), one and several slot sizes
+    tables += [[(80, 100 + g), (2048, g)] for g in (1, 2, 4, 8, 16, 32)]
+    tables += [[(4, 0), (12, 102), (24, 104), (48, 108), (80, 132), (2048, 16)]]
+    # persistent-lane flavours (200 + lanes; 200 = register-resident)
+    tables += [[(2048, 200 + g)] for g in (1, 2, 4, 8, 16, 32)]
+    tables += [[(4, 200), (24, 202), (64, 204), (2048, 232)]]
     try:
         for t in tables:
             eng.set_classes(t)

@@ -11,9 +11,12 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from bench import WORKLOADS  # noqa: E402
-from opengjk_b200 import api  # noqa: E402
+from opengjk_b200 import api, workloads as W  # noqa: E402
 
 names = sys.argv[1:] or ["hulls64_f64", "hulls64_f32", "boxes_f32", "hulls1k_f32"]
+WORKLOADS["hulls256_f32"] = ("64-256 vertices fp32", np.float32, lambda n, seed: W.random_hulls(n, 64, 256, seed, 4.0, np.float32), 300_000)
+WORKLOADS["hulls256_f64"] = ("64-256 vertices fp64", np.float64, lambda n, seed: W.random_hulls(n, 64, 256, seed, 4.0, np.float64), 300_000)
+WORKLOADS["hulls600_f32"] = ("256-600 vertices fp32", np.float32, lambda n, seed: W.random_hulls(n, 256, 600, seed, 4.0, np.float32), 100_000)
 eng = api.Engine(0)
 dev = torch.device("cuda:0")
 for name in names:
@@ -30,8 +33,26 @@ for name in names:
     store = eng.store_create(coords, off, cnt, st)
     tables = {"small+g": None}
     small_ok = int(w.cnt.max()) <= 8
-    for g in ([0] if small_ok else []) + [1, 2, 4, 8, 16, 32]:
-        eng.set_classes([(4, 0), (2048, 1)] if g == 0 else [(2048, g)])
+    kmax = int((((w.cnt[w.pa] + 3) // 4 * 4 + (w.cnt[w.pb] + 3) // 4 * 4) // 4).max())
+    variants = ([0, 200] if small_ok else []) + [1, 2, 4, 8, 16, 32]
+    if os.environ.get("TUNE_PERSIST"):
+        variants += [201, 202, 204, 208, 232]
+    if os.environ.get("TUNE_STAGED"):
+        variants += [101, 102, 104, 108, 116, 132]
+    for g in variants:
+        if g == 0:
+            table = [(4, 0), (2048, 1)]
+        elif g == 200:
+            table = [(4, 200), (2048, 201)]
+        elif g > 200:
+            table = [(2048, g)]
+        elif g >= 100:
+            table = [(kmax, g), (2048, g - 100)]
+        else:
+            table = [(2048, g)]
+        if kmax >= 2048 and g >= 100:
+            continue
+        eng.set_classes(table)
         for _ in range(3):
             eng.store_gjk(store, pa, store, pb, w.npairs, simp, dist, st)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -42,5 +63,5 @@ for name in names:
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
-        print(f"{name:14s} lanes={g:2d}  {ms:8.3f} ms  {w.npairs / ms / 1e3:10.1f} Mpairs/s", flush=True)
+        print(f"{name:14s} lanes={g:3d}  {ms:8.3f} ms  {w.npairs / ms / 1e3:10.1f} Mpairs/s", flush=True)
     store.close()
