@@ -39,7 +39,7 @@ L2_BYTES = 126e6
 CLASS_TABLE = [(4, 0), (32, 2), (128, 8), (2048, 32)]
 
 WORKLOADS = {
-    # name: (description, dtype, maker(npairs, seed), default pairs per GPU)
+    # name: (description, dtype, maker(npairs, seed), default pairs per GPU[, epa])
     "hulls64_f64": ("config2: random convex-hull pairs, 8-64 vertices, fp64", np.float64,
                     lambda n, seed: W.mixed_hulls(n, 8, 64, seed, np.float64), 1_000_000),
     "hulls64_f32": ("config2 in fp32: random convex-hull pairs, 8-64 vertices", np.float32,
@@ -52,7 +52,18 @@ WORKLOADS = {
                     lambda n, seed: W.large_hull_pool(n, 32768, 1000, 1000, seed, dtype=np.float32), 200_000),
     "hulls1k10k_f32": ("config4: indexed pairs of 1k-10k-vertex hulls, fp32", np.float32,
                        lambda n, seed: W.large_hull_pool(n, 2048, 1000, 10000, seed, dtype=np.float32), 50_000),
+    "epa_f32": ("config5: intersecting 8-64-vertex hull pairs, GJK + EPA, fp32", np.float32,
+                lambda n, seed: W.random_hulls(n, 8, 64, seed, 1.0, np.float32, 0.5), 1_000_000, True),
 }
+
+
+def traffic_for(name):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(p)).get(name)
+    except Exception:
+        return None
 
 
 def peaks():
@@ -66,21 +77,43 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the measured region (NVML every 20 ms;
+    falls back to polling nvidia-smi)."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.sm, self.bits, self.max_mhz, self._stop = index, [], 0, None, threading.Event()
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self._stop.is_set():
+                self.sm.append(int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                try:
+                    self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self._stop.wait(0.02)
+            return
+        except Exception:
+            pass
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
                                       str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                r = [x.strip() for x in out.split(",")]
+                self.sm.append(int(r[0]))
+                self.max_mhz = int(r[1])
+                for i, n in enumerate(names):
+                    if r[2 + i].lower().startswith("active"):
+                        self.bits |= self.REASONS[n]
             except Exception:
                 pass
             self._stop.wait(0.1)
@@ -94,13 +127,11 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"], "samples": 0}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz,
+                "reasons": [n for n, b in self.REASONS.items() if self.bits & b], "samples": len(sm)}
 
 
 def cpu_baseline(w, prec, budget_s=12.0):
@@ -132,7 +163,7 @@ def run_reference_arm(args, rank, world):
     """--impl reference: the reference's own CPU implementation, rank 0 only."""
     if rank != 0:
         return
-    desc, dt, maker, default_pairs = WORKLOADS[args.workload]
+    desc, dt, maker, default_pairs = WORKLOADS[args.workload][:4]
     prec = "f64" if dt == np.float64 else "f32"
     from oracle.pyoracle import Oracle, Reference
     cores = os.cpu_count() or 1
@@ -212,7 +243,8 @@ def main():
     hbm_peak, peak_src = peaks()
 
     def measure(name, pairs, steps, warmup, with_cpu):
-        desc, dt, maker, default_pairs = WORKLOADS[name]
+        desc, dt, maker, default_pairs = WORKLOADS[name][:4]
+        epa = len(WORKLOADS[name]) > 4 and WORKLOADS[name][4]
         prec = "f64" if dt == np.float64 else "f32"
         n = pairs or default_pairs
         w = maker(n, args.seed + rank)  # each rank owns its own slice of the job
@@ -238,8 +270,14 @@ def main():
         torch.cuda.synchronize()
         store_build_ms = 1e3 * (time.perf_counter() - t0)
 
+        if epa:
+            d_w1, d_w2, d_nr = (torch.empty(n * 3, dtype=h_coords.dtype, device=dev) for _ in range(3))
+
         def step():
-            eng.store_gjk(store, d_pa, store, d_pb, n, d_simp, d_dist, stream)
+            if epa:
+                eng.store_gjk_epa(store, d_pa, store, d_pb, n, d_simp, d_dist, d_w1, d_w2, d_nr, stream)
+            else:
+                eng.store_gjk(store, d_pa, store, d_pb, n, d_simp, d_dist, stream)
 
         def step_from_raw():
             eng.gjk_device(prec, n, d_coords, d_off, d_cnt, d_pa, d_coords, d_off, d_cnt, d_pb, d_simp, d_dist,
@@ -258,6 +296,12 @@ def main():
                 step()
             e1.record()
             barrier()
+            # keep the same load on the GPU for >= 0.3 s so the clock record has samples
+            # taken under load even when K steps last only a few milliseconds (untimed)
+            t_load = time.perf_counter()
+            while time.perf_counter() - t_load < 0.3:
+                step()
+                torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         launches = eng.launch_count - launches0
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -267,15 +311,17 @@ def main():
         value = n * world * steps / (ms_max * 1e-3)
 
         # same job starting from the raw xyz-interleaved arrays (repack inside the step)
-        for _ in range(2):
-            step_from_raw()
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(max(2, steps // 2)):
-            step_from_raw()
-        e1.record()
-        torch.cuda.synchronize()
-        raw_ms = e0.elapsed_time(e1) / max(2, steps // 2)
+        raw_ms = float("nan")
+        if not epa:
+            for _ in range(2):
+                step_from_raw()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(max(2, steps // 2)):
+                step_from_raw()
+            e1.record()
+            torch.cuda.synchronize()
+            raw_ms = e0.elapsed_time(e1) / max(2, steps // 2)
 
         # ---- per-phase durations (events around each launch, same stream) -----------
         eng.set_timing(True)
@@ -285,7 +331,7 @@ def main():
             torch.cuda.synchronize()
             lt = eng.last_timing()
             sort_ms.append(lt["sort"])
-            class_ms.append(lt["classes"])
+            class_ms.append(lt["classes"])  # last slot = EPA when it ran
         eng.set_timing(False)
         class_avg = [float(x) for x in np.mean(np.array(class_ms), axis=0)]
         dom = int(np.argmax(class_avg))
@@ -294,10 +340,13 @@ def main():
         # other size classes, if any, moved some of them)
         achieved = alg_bytes / (class_avg[dom] * 1e-3) / 1e9
         tname = "double" if prec == "f64" else "float"
-        lanes = CLASS_TABLE[dom][1]
-        kname = f"gjk_small_kernel<{tname}>" if lanes == 0 else f"gjk_group_kernel<{tname},{lanes}>"
+        if epa and dom == 5:
+            kname = f"epa_warp_kernel<{tname}>"
+        else:
+            lanes = CLASS_TABLE[dom][1]
+            kname = f"gjk_small_kernel<{tname}>" if lanes == 0 else f"gjk_group_kernel<{tname},{lanes}>"
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "kernel": kname, "kernel_ms": class_avg[dom],
+                    "traffic": traffic_for(name), "kernel": kname, "kernel_ms": class_avg[dom],
                     "step_phases_ms": {"sort": float(np.mean(sort_ms)), "classes": class_avg},
                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
 
@@ -305,27 +354,42 @@ def main():
         o = (h_dist.numpy(), h_simp.numpy().view(sdt))
         hc, ho, hk, ha, hb = (t.numpy() for t in (h_coords, h_off, h_cnt, h_pa, h_pb))
         e2e_steps = max(2, min(steps, 5))
-        eng.gjk_host(hc, ho, hk, ha, hb, True, o)  # warm (allocates staging)
+        e2e_call = (lambda: eng.gjk_epa_host(hc, ho, hk, ha, hb)) if epa else (lambda: eng.gjk_host(hc, ho, hk, ha, hb, True, o))
+        e2e_call()  # warm (allocates staging)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            eng.gjk_host(hc, ho, hk, ha, hb, True, o)
+            e2e_call()
         barrier()
         e2e_s = time.perf_counter() - t0
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": n * world * e2e_steps / float(t.item()), "unit": "pairs/s", "h2d_bytes_per_step": in_bytes,
-               "d2h_bytes_per_step": out_bytes, "steps": e2e_steps,
-               "api": f"ogjk_gjk_host_{prec} (pinned host buffers in, distances + gkSimplex out)"}
+               "d2h_bytes_per_step": out_bytes + (n * 9 * h_dist.element_size() if epa else 0), "steps": e2e_steps,
+               "api": (f"ogjk_gjk_epa_host_{prec}" if epa else f"ogjk_gjk_host_{prec}")
+               + " (pinned host buffers in, distances + gkSimplex" + (" + witnesses + normals" if epa else "") + " out)"}
 
         # quick self-check on a sample against the oracle (checker only, outside any timed region)
-        res = {"workload": desc, "value": value, "from_raw_arrays": {"value": n * world / (raw_ms * 1e-3), "ms_per_step": raw_ms,
-                                                                     "note": "repack into the store inside the step"},
+        res = {"workload": desc, "value": value, "from_raw_arrays": (None if epa else {"value": n * world / (raw_ms * 1e-3), "ms_per_step": raw_ms,
+                                                                                   "note": "repack into the store inside the step"}),
                "store_build_ms": store_build_ms, "store_bytes": store.nbytes, "ms_per_step": ms_max / steps, "launches": launches, "roofline": roofline,
                "e2e": e2e, "clocks": clk.summary(), "prec": prec, "pairs_per_gpu": n,
                "input_bytes_per_gpu": in_bytes}
-        if with_cpu and rank == 0:
+        if with_cpu and rank == 0 and epa:
+            from oracle.pyoracle import Oracle
+            o_ = Oracle(prec)
+            m = min(n, 20000)
+            cores = os.cpu_count() or 1
+            t0 = time.perf_counter()
+            ref = o_.gjk_epa_batch(w.coords, w.off, w.cnt, w.pa[:m], w.pb[:m], nthreads=cores)
+            dt_s = time.perf_counter() - t0
+            res["cpu_baseline"] = {"value": m / dt_s, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                   "sample": f"first {m} pairs, GJK + EPA restatement (the reference has no CPU EPA)"}
+            res["sample_parity"] = {"pairs": m, "distance_bits_equal": bool(
+                d_dist[:m].cpu().numpy().tobytes() == ref["distances"].tobytes()),
+                "witness_bits_equal": bool(d_w1[:3 * m].cpu().numpy().tobytes() == ref["witness1"].tobytes())}
+        elif with_cpu and rank == 0:
             res["cpu_baseline"] = cpu_baseline(w, prec)
             from oracle.pyoracle import Oracle
             m = min(n, 20000)
