@@ -295,6 +295,7 @@ def main():
             for _ in range(steps):
                 step()
             e1.record()
+            launches = eng.launch_count - launches0  # kernels launched inside the timed region
             barrier()
             # keep the same load on the GPU for >= 0.3 s so the clock record has samples
             # taken under load even when K steps last only a few milliseconds (untimed)
@@ -303,7 +304,6 @@ def main():
                 step()
                 torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        launches = eng.launch_count - launches0
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
