@@ -206,6 +206,12 @@ OGJK_API int ogjk_compute_epa_f64(ogjk_ctx* ctx, int n, const ogjk_polytope_f64*
                                   ogjk_simplex_f64* simplices, double* distances, double* witness1, double* witness2,
                                   double* contact_normals);
 
+/* ---- sub-solver test hook, replacing opengjk_test_S1D/S2D/S3D (scalar/include/openGJK/openGJK.h:120-122,
+ * scalar/openGJK.c:1232-1248): runs the device Signed-Volumes sub-solver once on `simplex`
+ * (nvrtx 2..4, newest vertex in the highest slot), in place; v[3] receives the closest point. */
+OGJK_API int ogjk_test_subalgorithm_f32(ogjk_ctx* ctx, ogjk_simplex_f32* simplex, float* v);
+OGJK_API int ogjk_test_subalgorithm_f64(ogjk_ctx* ctx, ogjk_simplex_f64* simplex, double* v);
+
 #ifdef __cplusplus
 }
 #endif

@@ -380,6 +380,22 @@ def compute_minimum_distance_indexed_structs(bodies, pairs, dtype=np.float32, en
     return dist, simp
 
 
+def subalgorithm(vrtx, idx=None, dtype=np.float64, engine=None):
+    """Device sub-solver on one simplex given as (nvrtx,3), newest vertex last
+    (reference test hooks opengjk_test_S{1,2,3}D).  Returns (v, simplex)."""
+    eng = engine or default_engine()
+    prec, sdt = _PREC[np.dtype(dtype)]
+    vrtx = np.asarray(vrtx, dtype=dtype).reshape(-1, 3)
+    s = np.zeros(1, dtype=sdt)
+    s["nvrtx"] = vrtx.shape[0]
+    s["vrtx"][0, : vrtx.shape[0]] = vrtx
+    if idx is not None:
+        s["vrtx_idx"][0, : vrtx.shape[0]] = idx
+    v = np.ones(3, dtype=dtype)
+    check(getattr(_lib.lib(), f"ogjk_test_subalgorithm_{prec}")(eng._h, _p(s), _p(v)))
+    return v, s[0]
+
+
 def single_query(vertices0, vertices1, dtype=np.float64, engine=None):
     """One pair through the scalar library's row-pointer layout
     (scalar/examples/python_ctypes/src/pyopengjk/opengjk.py:60-91)."""

@@ -639,6 +639,26 @@ int store_gjk(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_s
 }
 
 template <typename T, typename S>
+int test_subalgorithm(ogjk_ctx* ctx, S* simplex, T* v) {
+  if (!ctx || !simplex || !v) return fail(OGJK_ERR_ARG, "NULL argument%s");
+  if (simplex->nvrtx < 2 || simplex->nvrtx > 4) return fail(OGJK_ERR_ARG, "sub-solver needs 2..4 vertices%s");
+  CU(cudaSetDevice(ctx->device));
+  int rc = ctx->d_simp.reserve(sizeof(S));
+  if (rc) return rc;
+  if ((rc = ctx->d_dist.reserve(3 * sizeof(T)))) return rc;
+  cudaStream_t st = ctx->own_stream;
+  CU(cudaMemcpyAsync(ctx->d_simp.p, simplex, sizeof(S), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_dist.p, v, 3 * sizeof(T), cudaMemcpyHostToDevice, st));
+  subsolver_kernel<T><<<1, 1, 0, st>>>(static_cast<GkSimplex<T>*>(ctx->d_simp.p), static_cast<T*>(ctx->d_dist.p));
+  ctx->launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(simplex, ctx->d_simp.p, sizeof(S), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(v, ctx->d_dist.p, 3 * sizeof(T), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return OGJK_OK;
+}
+
+template <typename T, typename S>
 int store_epa(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_store* s2, const int* idx2, int64_t npairs,
               const S* simplices, T* distances, T* w1, T* w2, T* normals, void* stream) {
   if (!ctx || !s1 || !s2 || !simplices || !distances || !w1 || !w2) return fail(OGJK_ERR_ARG, "NULL argument%s");
@@ -876,5 +896,12 @@ int ogjk_single_rows_f64(ogjk_ctx* ctx, int n1, double* const* rows1, int n2, do
   }
 OGJK_EPA_IMPL(f32, float, ogjk_polytope_f32, ogjk_simplex_f32)
 OGJK_EPA_IMPL(f64, double, ogjk_polytope_f64, ogjk_simplex_f64)
+
+int ogjk_test_subalgorithm_f32(ogjk_ctx* ctx, ogjk_simplex_f32* simplex, float* v) {
+  return test_subalgorithm<float, ogjk_simplex_f32>(ctx, simplex, v);
+}
+int ogjk_test_subalgorithm_f64(ogjk_ctx* ctx, ogjk_simplex_f64* simplex, double* v) {
+  return test_subalgorithm<double, ogjk_simplex_f64>(ctx, simplex, v);
+}
 
 }  // extern "C"

@@ -1,0 +1,45 @@
+/* compat_scalar.c -- reference-named scalar flavour (include/openGJK/openGJK.h).
+ * Plain C host code over the C ABI; one lazily created context guarded by a mutex
+ * (the reference function is re-entrant, so concurrent callers are serialised here). */
+#include <math.h>
+#include <pthread.h>
+
+#include "openGJK/openGJK.h"
+#include "opengjk_b200.h"
+
+#ifdef USE_32BITS
+#define SINGLE ogjk_single_rows_f32
+#define SUBALG ogjk_test_subalgorithm_f32
+typedef ogjk_simplex_f32 simplex_t;
+#else
+#define SINGLE ogjk_single_rows_f64
+#define SUBALG ogjk_test_subalgorithm_f64
+typedef ogjk_simplex_f64 simplex_t;
+#endif
+
+static ogjk_ctx* g_ctx;
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static ogjk_ctx* context(void) {
+  if (!g_ctx && ogjk_ctx_create(0, &g_ctx) != OGJK_OK) g_ctx = 0;
+  return g_ctx;
+}
+
+gkFloat compute_minimum_distance(gkPolytope bd1, gkPolytope bd2, gkSimplex* s) {
+  gkFloat d = (gkFloat)NAN;
+  pthread_mutex_lock(&g_lock);
+  ogjk_ctx* c = context();
+  if (c && s) SINGLE(c, bd1.numpoints, bd1.coord, bd2.numpoints, bd2.coord, (simplex_t*)s, &d);
+  pthread_mutex_unlock(&g_lock);
+  return d;
+}
+
+static void sub(gkSimplex* s, gkFloat* v) {
+  pthread_mutex_lock(&g_lock);
+  ogjk_ctx* c = context();
+  if (c && s && v) SUBALG(c, (simplex_t*)s, v);
+  pthread_mutex_unlock(&g_lock);
+}
+void opengjk_test_S1D(gkSimplex* s, gkFloat* v) { sub(s, v); }
+void opengjk_test_S2D(gkSimplex* s, gkFloat* v) { sub(s, v); }
+void opengjk_test_S3D(gkSimplex* s, gkFloat* v) { sub(s, v); }

@@ -642,6 +642,26 @@ gjk_witness_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned*
   }
 }
 
+// Sub-solver test hook (reference: opengjk_test_S{1,2,3}D, scalar/openGJK.c:1232-1248):
+// one thread runs S1D/S2D/S3D on a caller-supplied simplex, in place.
+template <typename T>
+__global__ void subsolver_kernel(GkSimplex<T>* io, T* v_out) {
+  Splx<T> s;
+  s.n = io->nvrtx;
+  s.q0 = MV<T>{io->vrtx[0][0], io->vrtx[0][1], io->vrtx[0][2], io->vrtx_idx[0][0], io->vrtx_idx[0][1]};
+  s.q1 = MV<T>{io->vrtx[1][0], io->vrtx[1][1], io->vrtx[1][2], io->vrtx_idx[1][0], io->vrtx_idx[1][1]};
+  s.q2 = MV<T>{io->vrtx[2][0], io->vrtx[2][1], io->vrtx[2][2], io->vrtx_idx[2][0], io->vrtx_idx[2][1]};
+  s.q3 = MV<T>{io->vrtx[3][0], io->vrtx[3][1], io->vrtx[3][2], io->vrtx_idx[3][0], io->vrtx_idx[3][1]};
+  V3<T> v{v_out[0], v_out[1], v_out[2]};
+  if (s.n == 4) { if (sub_3d(s, v)) sub_2d(s, v); }
+  else if (s.n == 3) sub_2d(s, v);
+  else if (s.n == 2) sub_1d(s, v);
+  const V3<T> keep1{io->witnesses[0][0], io->witnesses[0][1], io->witnesses[0][2]};
+  const V3<T> keep2{io->witnesses[1][0], io->witnesses[1][1], io->witnesses[1][2]};
+  store_simplex(io, s, keep1, keep2);
+  v_out[0] = v.x; v_out[1] = v.y; v_out[2] = v.z;
+}
+
 // Batch scheduler, stage 1: split the pair list by total vertex count so that
 // thread-per-pair warps do not wait on one large hull (north_star item 5).
 // Warp-aggregated appends keep the in-warp pair order.
