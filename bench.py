@@ -354,7 +354,17 @@ def main():
         o = (h_dist.numpy(), h_simp.numpy().view(sdt))
         hc, ho, hk, ha, hb = (t.numpy() for t in (h_coords, h_off, h_cnt, h_pa, h_pb))
         e2e_steps = max(2, min(steps, 5))
-        e2e_call = (lambda: eng.gjk_epa_host(hc, ho, hk, ha, hb)) if epa else (lambda: eng.gjk_host(hc, ho, hk, ha, hb, True, o))
+        pair_owned = bool(np.array_equal(w.pa, np.arange(0, 2 * n, 2)) and np.array_equal(w.pb, w.pa + 1))
+        if pair_owned and not epa:
+            # the reference's bd1[] / bd2[] call shape: two pinned pools, pair p = polytope p of each
+            # (chunk-pipelined H2D / kernels / D2H inside the library)
+            pools = [pin(x).numpy() for x in w.two_pools()]
+            e2e_call = lambda: eng.gjk_host_pools(*pools, out=o)
+            in_bytes = sum(x.nbytes for x in pools)
+        elif epa:
+            e2e_call = lambda: eng.gjk_epa_host(hc, ho, hk, ha, hb)
+        else:
+            e2e_call = lambda: eng.gjk_host(hc, ho, hk, ha, hb, True, o)
         e2e_call()  # warm (allocates staging)
         barrier()
         t0 = time.perf_counter()

@@ -127,6 +127,10 @@ OGJK_API int ogjk_store_gjk_f32(ogjk_ctx* ctx, const ogjk_store* s1, const int* 
 OGJK_API int ogjk_store_gjk_f64(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_store* s2, const int* idx2,
                                 int64_t npairs, ogjk_simplex_f64* simplices, double* distances, void* stream);
 
+/* Number of chunks (0..16, default 8) the un-indexed host-buffer entry points cut a
+ * batch into so that H2D, kernels and D2H overlap; 0 or 1 = one shot. */
+OGJK_API int ogjk_ctx_set_pipeline_chunks(ogjk_ctx* ctx, int chunks);
+
 /* ---- host-buffer batch over flat pools (what a zero-copy binding calls; the
  * e2e number in bench.py goes through this).  All pointers are HOST pointers.
  * Copies inputs to the device, runs, copies results back, synchronises.

@@ -159,6 +159,29 @@ class Engine:
                  _p(cnt), cnt.shape[0], coords.shape[0], _p(pb), _p(simp), _p(dist), _p(w1), _p(w2), _p(nr)))
         return {"distances": dist, "simplices": simp, "witness1": w1, "witness2": w2, "normals": nr}
 
+    def set_pipeline_chunks(self, chunks):
+        check(_lib.lib().ogjk_ctx_set_pipeline_chunks(self._h, int(chunks)))
+
+    def gjk_host_pools(self, c1, o1, k1, c2, o2, k2, out=None, epa=False):
+        """Un-indexed form over two pools (pair p = polytope p of each pool), the shape of
+        the reference's bd1[] / bd2[] arrays; large batches are chunk-pipelined over PCIe."""
+        c1 = np.ascontiguousarray(c1); c2 = np.ascontiguousarray(c2)
+        prec, sdt = _PREC[c1.dtype]
+        n = int(k1.shape[0])
+        if out is None:
+            dist = np.zeros(n, dtype=c1.dtype)
+            simp = np.zeros(n, dtype=sdt)
+        else:
+            dist, simp = out
+        args = [self._h, n, _p(c1), _p(o1), _p(k1), n, c1.size // 3, None, _p(c2), _p(o2), _p(k2), n, c2.size // 3, None,
+                _p(simp), _p(dist)]
+        if epa:
+            w1 = np.zeros((n, 3), dtype=c1.dtype); w2 = np.zeros((n, 3), dtype=c1.dtype); nr = np.zeros((n, 3), dtype=c1.dtype)
+            check(getattr(_lib.lib(), f"ogjk_gjk_epa_host_{prec}")(*args, _p(w1), _p(w2), _p(nr)))
+            return {"distances": dist, "simplices": simp, "witness1": w1, "witness2": w2, "normals": nr}
+        check(getattr(_lib.lib(), f"ogjk_gjk_host_{prec}")(*args))
+        return dist, simp
+
     def run_workload(self, w, want_simplices=True):
         return self.gjk_host(w.coords, w.off, w.cnt, w.pa, w.pb, want_simplices)
 

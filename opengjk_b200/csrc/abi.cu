@@ -93,6 +93,9 @@ struct ogjk_ctx_ {
   cudaEvent_t ev[2 * kPhases] = {};
   int timed_mask = 0;
   cudaStream_t own_stream = nullptr;  // used by the host-buffer entry points
+  cudaStream_t in_stream = nullptr, out_stream = nullptr;  // H2D / D2H legs of the chunked host pipeline
+  cudaEvent_t chunk_in[16] = {}, chunk_done[16] = {};
+  int pipeline_chunks = 8;            // 0/1 disables chunking
   DevBuf counters;                    // 16 x u64 work-queue heads
   DevBuf sort_tmp;                    // hist | start | cursor (u32 each, kMaxKey+2)
   DevBuf sorted_list;                 // pair ids, size-sorted
@@ -152,7 +155,7 @@ int launch_raw(ogjk_ctx* ctx, const BatchArgs<T>& a, int mode, cudaStream_t st) 
 // (every polytope padded by 3 vertices) keeps the call asynchronous.
 template <typename T>
 int store_build(ogjk_ctx* ctx, ogjk_store_* s, long long npoly, long long nverts, const T* coords, const int64_t* off,
-                const int* cnt, bool exact, cudaStream_t st) {
+                const int* cnt, bool exact, cudaStream_t st, bool pack_now = true) {
   s->device = ctx->device;
   s->prec = (int)sizeof(T);
   s->npoly = npoly;
@@ -177,10 +180,28 @@ int store_build(ogjk_ctx* ctx, ogjk_store_* s, long long npoly, long long nverts
   }
   if ((rc = s->data.reserve((size_t)(elems > 0 ? elems : 4) * sizeof(T)))) return rc;
   s->capacity = elems;
-  long long pblocks = (npoly * 8 + 255) / 256, cap = (long long)ctx->sm_count * 32;
+  ctx->launches += 3;
+  if (pack_now) {
+    long long pblocks = (npoly * 8 + 255) / 256, cap = (long long)ctx->sm_count * 32;
+    pack_kernel<T><<<(unsigned)(pblocks < cap ? pblocks : cap), 256, 0, st>>>(
+        coords, reinterpret_cast<const long long*>(off), cnt, npoly, boff, static_cast<T*>(s->data.p));
+    ctx->launches += 1;
+  }
+  CU(cudaGetLastError());
+  return OGJK_OK;
+}
+
+// Repack polytopes [lo, hi) of a prepared store (offsets already scanned).
+template <typename T>
+int store_pack_range(ogjk_ctx* ctx, ogjk_store_* s, long long lo, long long hi, const T* coords, const int64_t* off,
+                     const int* cnt, cudaStream_t st) {
+  const long long n = hi - lo;
+  if (n <= 0) return OGJK_OK;
+  long long pblocks = (n * 8 + 255) / 256, cap = (long long)ctx->sm_count * 32;
   pack_kernel<T><<<(unsigned)(pblocks < cap ? pblocks : cap), 256, 0, st>>>(
-      coords, reinterpret_cast<const long long*>(off), cnt, npoly, boff, static_cast<T*>(s->data.p));
-  ctx->launches += 4;
+      coords, reinterpret_cast<const long long*>(off) + lo, cnt + lo, n, static_cast<const long long*>(s->boff.p) + lo,
+      static_cast<T*>(s->data.p));
+  ctx->launches += 1;
   CU(cudaGetLastError());
   return OGJK_OK;
 }
@@ -383,6 +404,112 @@ int upload(ogjk_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
   return OGJK_OK;
 }
 
+// Chunked variant of the host pipeline for the un-indexed form (pair p uses polytope p
+// of each pool -- the reference's bd1[] / bd2[] arrays): the pair range is cut into
+// chunks whose coordinate ranges are contiguous, and H2D of chunk c+1, the kernels
+// of chunk c and D2H of chunk c-1 overlap on three streams (PCIe is full duplex and
+// the transfer is ~10x longer than the kernels, so e2e approaches the H2D time).
+// Returns 1 when the layout is not chunkable (caller falls back), 0 on success.
+template <typename T, typename S>
+int host_pipeline_chunked(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t* off1, const int* cnt1,
+                          int64_t nverts1, const T* coords2, const int64_t* off2, const int* cnt2, int64_t nverts2,
+                          S* simplices, T* distances, T* w1, T* w2, T* normals, bool run_epa) {
+  const int K = ctx->pipeline_chunks > 16 ? 16 : ctx->pipeline_chunks;
+  if (K < 2 || npairs < 4096 * (int64_t)K) return 1;
+  // chunk coordinate ranges; require monotone, gap-free-ish layouts
+  struct Range { int64_t lo, hi, a1, b1, a2, b2; };
+  Range r[16];
+  int64_t covered1 = 0, covered2 = 0;
+  for (int c = 0; c < K; ++c) {
+    r[c].lo = npairs * c / K;
+    r[c].hi = npairs * (c + 1) / K;
+    const int64_t last = r[c].hi - 1;
+    r[c].a1 = off1[r[c].lo]; r[c].b1 = off1[last] + cnt1[last];
+    r[c].a2 = off2[r[c].lo]; r[c].b2 = off2[last] + cnt2[last];
+    if (r[c].b1 < r[c].a1 || r[c].b2 < r[c].a2 || r[c].b1 > nverts1 || r[c].b2 > nverts2) return 1;
+    if (c && (r[c].a1 < r[c - 1].b1 || r[c].a2 < r[c - 1].b2)) return 1;  // not sorted by pair
+    covered1 += r[c].b1 - r[c].a1;
+    covered2 += r[c].b2 - r[c].a2;
+  }
+  // every polytope of a chunk must lie inside the chunk's range (cheap monotonicity check)
+  for (int64_t p = 1; p < npairs; ++p)
+    if (off1[p] < off1[p - 1] + cnt1[p - 1] || off2[p] < off2[p - 1] + cnt2[p - 1]) return 1;
+  (void)covered1; (void)covered2;
+
+  cudaStream_t sc = ctx->own_stream, si = ctx->in_stream, so = ctx->out_stream;
+  int rc;
+  // small metadata first, then offsets scan for both pools (no coordinates needed)
+  if ((rc = ctx->d_coords1.reserve((size_t)nverts1 * 3 * sizeof(T)))) return rc;
+  if ((rc = ctx->d_coords2.reserve((size_t)nverts2 * 3 * sizeof(T)))) return rc;
+  if ((rc = upload(ctx, ctx->d_off1, off1, (size_t)npairs * sizeof(int64_t)))) return rc;
+  if ((rc = upload(ctx, ctx->d_cnt1, cnt1, (size_t)npairs * sizeof(int)))) return rc;
+  if ((rc = upload(ctx, ctx->d_off2, off2, (size_t)npairs * sizeof(int64_t)))) return rc;
+  if ((rc = upload(ctx, ctx->d_cnt2, cnt2, (size_t)npairs * sizeof(int)))) return rc;
+  if ((rc = ctx->d_dist.reserve((size_t)npairs * sizeof(T)))) return rc;
+  if ((rc = ctx->d_simp.reserve((size_t)npairs * sizeof(S)))) return rc;
+  if (run_epa) {
+    if ((rc = ctx->d_w1.reserve((size_t)npairs * 3 * sizeof(T)))) return rc;
+    if ((rc = ctx->d_w2.reserve((size_t)npairs * 3 * sizeof(T)))) return rc;
+    if (normals && (rc = ctx->d_nrm.reserve((size_t)npairs * 3 * sizeof(T)))) return rc;
+  }
+  const T* dc1 = static_cast<const T*>(ctx->d_coords1.p);
+  const T* dc2 = static_cast<const T*>(ctx->d_coords2.p);
+  const int64_t* do1 = static_cast<const int64_t*>(ctx->d_off1.p);
+  const int64_t* do2 = static_cast<const int64_t*>(ctx->d_off2.p);
+  const int* dk1 = static_cast<const int*>(ctx->d_cnt1.p);
+  const int* dk2 = static_cast<const int*>(ctx->d_cnt2.p);
+  ctx->timed_mask = 0;
+  if ((rc = store_build<T>(ctx, &ctx->scratch1, npairs, nverts1, dc1, do1, dk1, false, sc, false))) return rc;
+  if ((rc = store_build<T>(ctx, &ctx->scratch2, npairs, nverts2, dc2, do2, dk2, false, sc, false))) return rc;
+
+  for (int c = 0; c < K; ++c) {
+    CU(cudaMemcpyAsync(static_cast<T*>(ctx->d_coords1.p) + 3 * r[c].a1, coords1 + 3 * r[c].a1,
+                       (size_t)(r[c].b1 - r[c].a1) * 3 * sizeof(T), cudaMemcpyHostToDevice, si));
+    CU(cudaMemcpyAsync(static_cast<T*>(ctx->d_coords2.p) + 3 * r[c].a2, coords2 + 3 * r[c].a2,
+                       (size_t)(r[c].b2 - r[c].a2) * 3 * sizeof(T), cudaMemcpyHostToDevice, si));
+    CU(cudaEventRecord(ctx->chunk_in[c], si));
+  }
+  for (int c = 0; c < K; ++c) {
+    const int64_t lo = r[c].lo, n = r[c].hi - r[c].lo;
+    CU(cudaStreamWaitEvent(sc, ctx->chunk_in[c], 0));
+    if ((rc = store_pack_range<T>(ctx, &ctx->scratch1, lo, r[c].hi, dc1, do1, dk1, sc))) return rc;
+    if ((rc = store_pack_range<T>(ctx, &ctx->scratch2, lo, r[c].hi, dc2, do2, dk2, sc))) return rc;
+    StoreArgs<T> sa;
+    sa.s1 = view_of<T>(&ctx->scratch1); sa.s1.boff += lo; sa.s1.cnt += lo;
+    sa.s2 = view_of<T>(&ctx->scratch2); sa.s2.boff += lo; sa.s2.cnt += lo;
+    sa.idx1 = nullptr; sa.idx2 = nullptr;
+    sa.simplices = static_cast<GkSimplex<T>*>(ctx->d_simp.p) + lo;
+    sa.distances = static_cast<T*>(ctx->d_dist.p) + lo;
+    sa.npairs = n;
+    if ((rc = run_store_batch<T>(ctx, sa, sc))) return rc;
+    if (run_epa) {
+      EpaArgs<T> ea;
+      ea.s1 = sa.s1; ea.s2 = sa.s2; ea.idx1 = nullptr; ea.idx2 = nullptr;
+      ea.simplices = sa.simplices; ea.distances = sa.distances;
+      ea.witness1 = static_cast<T*>(ctx->d_w1.p) + 3 * lo;
+      ea.witness2 = static_cast<T*>(ctx->d_w2.p) + 3 * lo;
+      ea.normals = normals ? static_cast<T*>(ctx->d_nrm.p) + 3 * lo : nullptr;
+      ea.npairs = n;
+      if ((rc = run_store_epa<T>(ctx, ea, sc))) return rc;
+    }
+    CU(cudaEventRecord(ctx->chunk_done[c], sc));
+    CU(cudaStreamWaitEvent(so, ctx->chunk_done[c], 0));
+    CU(cudaMemcpyAsync(distances + lo, static_cast<T*>(ctx->d_dist.p) + lo, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, so));
+    if (simplices)
+      CU(cudaMemcpyAsync(simplices + lo, static_cast<S*>(ctx->d_simp.p) + lo, (size_t)n * sizeof(S), cudaMemcpyDeviceToHost, so));
+    if (run_epa) {
+      CU(cudaMemcpyAsync(w1 + 3 * lo, static_cast<T*>(ctx->d_w1.p) + 3 * lo, (size_t)n * 3 * sizeof(T), cudaMemcpyDeviceToHost, so));
+      CU(cudaMemcpyAsync(w2 + 3 * lo, static_cast<T*>(ctx->d_w2.p) + 3 * lo, (size_t)n * 3 * sizeof(T), cudaMemcpyDeviceToHost, so));
+      if (normals)
+        CU(cudaMemcpyAsync(normals + 3 * lo, static_cast<T*>(ctx->d_nrm.p) + 3 * lo, (size_t)n * 3 * sizeof(T), cudaMemcpyDeviceToHost, so));
+    }
+  }
+  CU(cudaStreamSynchronize(so));
+  CU(cudaStreamSynchronize(sc));
+  CU(cudaStreamSynchronize(si));
+  return OGJK_OK;
+}
+
 // Host-buffer pipeline shared by every host entry point: upload the pools, repack
 // them into the scratch stores, run GJK and/or EPA, download.  With run_gjk ==
 // false the caller's simplices/distances are inputs (the reference's compute_epa).
@@ -402,6 +529,11 @@ int host_pipeline(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t
   cudaStream_t st = ctx->own_stream;
   const bool shared_pool = (coords1 == coords2 && off1 == off2 && cnt1 == cnt2);
   const bool need_simp = simplices != nullptr || run_epa;
+  if (run_gjk && !idx1 && !idx2 && !shared_pool && npoly1 >= npairs && npoly2 >= npairs) {
+    const int rcc = host_pipeline_chunked<T, S>(ctx, npairs, coords1, off1, cnt1, nverts1, coords2, off2, cnt2, nverts2,
+                                                simplices, distances, w1, w2, normals, run_epa);
+    if (rcc <= 0) return rcc;  // done (0) or error (<0); 1 = layout not chunkable, use the one-shot path
+  }
   int rc;
   if ((rc = upload(ctx, ctx->d_coords1, coords1, (size_t)nverts1 * 3 * sizeof(T)))) return rc;
   if ((rc = upload(ctx, ctx->d_off1, off1, (size_t)npoly1 * sizeof(int64_t)))) return rc;
@@ -706,6 +838,12 @@ int ogjk_ctx_create(int device, ogjk_ctx** out) {
   e = cudaGetDeviceProperties(&prop, device);
   if (e == cudaSuccess) c->sm_count = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->in_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 16 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&c->chunk_in[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->chunk_done[i], cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) {
     delete c;
     snprintf(g_err, sizeof(g_err), "cudaStreamCreate failed: %s", cudaGetErrorString(e));
@@ -728,6 +866,12 @@ void ogjk_ctx_destroy(ogjk_ctx* c) {
   for (DevBuf* b : bufs) b->release();
   c->h_stage.release();
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->in_stream) cudaStreamDestroy(c->in_stream);
+  if (c->out_stream) cudaStreamDestroy(c->out_stream);
+  for (int i = 0; i < 16; ++i) {
+    if (c->chunk_in[i]) cudaEventDestroy(c->chunk_in[i]);
+    if (c->chunk_done[i]) cudaEventDestroy(c->chunk_done[i]);
+  }
   for (int i = 0; i < 2 * kPhases; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   delete c;
 }
@@ -896,6 +1040,12 @@ int ogjk_single_rows_f64(ogjk_ctx* ctx, int n1, double* const* rows1, int n2, do
   }
 OGJK_EPA_IMPL(f32, float, ogjk_polytope_f32, ogjk_simplex_f32)
 OGJK_EPA_IMPL(f64, double, ogjk_polytope_f64, ogjk_simplex_f64)
+
+int ogjk_ctx_set_pipeline_chunks(ogjk_ctx* c, int chunks) {
+  if (!c || chunks < 0 || chunks > 16) return fail(OGJK_ERR_ARG, "chunks must be 0..16%s");
+  c->pipeline_chunks = chunks;
+  return OGJK_OK;
+}
 
 int ogjk_test_subalgorithm_f32(ogjk_ctx* ctx, ogjk_simplex_f32* simplex, float* v) {
   return test_subalgorithm<float, ogjk_simplex_f32>(ctx, simplex, v);

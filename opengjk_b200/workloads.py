@@ -49,6 +49,18 @@ class Workload:
         o = int(self.off[h])
         return self.coords[o:o + int(self.cnt[h])]
 
+    def two_pools(self):
+        """(coords1, off1, cnt1, coords2, off2, cnt2) with pair p = polytope p of each pool:
+        the un-indexed bd1[] / bd2[] form of the reference's batched API."""
+        out = []
+        for idx in (self.pa, self.pb):
+            cnt = np.ascontiguousarray(self.cnt[idx])
+            off = _offsets(cnt)
+            start = self.off[idx]
+            src = np.repeat(start - off, cnt) + np.arange(int(cnt.sum()), dtype=np.int64)
+            out += [np.ascontiguousarray(self.coords[src]), off, cnt]
+        return tuple(out)
+
     def slice_pairs(self, lo, hi):
         return Workload(self.name, self.coords, self.off, self.cnt, self.pa[lo:hi], self.pb[lo:hi])
 

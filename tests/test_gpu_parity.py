@@ -242,3 +242,25 @@ def test_full_size_config2_properties(eng):
     o = Oracle("f64")
     dref, sref = o.batch(w.coords, w.off, w.cnt, w.pa[sel], w.pb[sel], nthreads=os.cpu_count() or 1)
     _assert_same("config2_sample", d[sel], s[sel], dref, sref, "f64")
+
+
+@pytest.mark.parametrize("prec,dt", PRECS)
+def test_chunk_pipelined_host_path(eng, prec, dt):
+    """Un-indexed two-pool form (the reference's bd1[] / bd2[] arrays): large batches are cut into
+    chunks whose H2D / kernels / D2H overlap; results must not depend on the chunking."""
+    w = W.mixed_hulls(100_000, seed=61, dtype=dt)
+    dref, sref = Oracle(prec).batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1)
+    pools = w.two_pools()
+    try:
+        for chunks in (8, 3, 16, 0):
+            eng.set_pipeline_chunks(chunks)
+            d, s = eng.gjk_host_pools(*pools)
+            _assert_same(f"chunks{chunks}", d, s, dref, sref, prec)
+    finally:
+        eng.set_pipeline_chunks(8)
+    # GJK + EPA through the same pipeline
+    w = W.random_hulls(60_000, 8, 64, 62, 1.5, dt, 0.5)
+    ref = Oracle(prec).gjk_epa_batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1)
+    got = eng.gjk_host_pools(*w.two_pools(), epa=True)
+    for k in ("distances", "witness1", "witness2", "normals"):
+        assert np.ascontiguousarray(got[k]).tobytes() == np.ascontiguousarray(ref[k]).tobytes(), k
