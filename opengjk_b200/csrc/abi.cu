@@ -431,9 +431,6 @@ int host_pipeline_chunked(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const
     covered1 += r[c].b1 - r[c].a1;
     covered2 += r[c].b2 - r[c].a2;
   }
-  // every polytope of a chunk must lie inside the chunk's range (cheap monotonicity check)
-  for (int64_t p = 1; p < npairs; ++p)
-    if (off1[p] < off1[p - 1] + cnt1[p - 1] || off2[p] < off2[p - 1] + cnt2[p - 1]) return 1;
   (void)covered1; (void)covered2;
 
   cudaStream_t sc = ctx->own_stream, si = ctx->in_stream, so = ctx->out_stream;
@@ -461,6 +458,18 @@ int host_pipeline_chunked(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const
   ctx->timed_mask = 0;
   if ((rc = store_build<T>(ctx, &ctx->scratch1, npairs, nverts1, dc1, do1, dk1, false, sc, false))) return rc;
   if ((rc = store_build<T>(ctx, &ctx->scratch2, npairs, nverts2, dc2, do2, dk2, false, sc, false))) return rc;
+  // Every polytope of a chunk must lie inside the chunk's coordinate range: checked on
+  // the device (optimistically -- the verdict is read after the pipeline has drained).
+  if ((rc = ctx->counters.reserve(16 * sizeof(unsigned long long)))) return rc;
+  int* bad_layout = reinterpret_cast<int*>(static_cast<unsigned long long*>(ctx->counters.p) + 12);
+  CU(cudaMemsetAsync(bad_layout, 0, sizeof(int), sc));
+  {
+    long long cb = (npairs + 255) / 256, ccap = (long long)ctx->sm_count * 8;
+    const unsigned grid = (unsigned)(cb < ccap ? cb : ccap);
+    check_monotone_kernel<<<grid, 256, 0, sc>>>(reinterpret_cast<const long long*>(do1), dk1, npairs, bad_layout);
+    check_monotone_kernel<<<grid, 256, 0, sc>>>(reinterpret_cast<const long long*>(do2), dk2, npairs, bad_layout);
+    ctx->launches += 2;
+  }
 
   for (int c = 0; c < K; ++c) {
     CU(cudaMemcpyAsync(static_cast<T*>(ctx->d_coords1.p) + 3 * r[c].a1, coords1 + 3 * r[c].a1,
@@ -504,10 +513,12 @@ int host_pipeline_chunked(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const
         CU(cudaMemcpyAsync(normals + 3 * lo, static_cast<T*>(ctx->d_nrm.p) + 3 * lo, (size_t)n * 3 * sizeof(T), cudaMemcpyDeviceToHost, so));
     }
   }
+  int bad = 0;
+  CU(cudaMemcpyAsync(&bad, bad_layout, sizeof(int), cudaMemcpyDeviceToHost, sc));
   CU(cudaStreamSynchronize(so));
   CU(cudaStreamSynchronize(sc));
   CU(cudaStreamSynchronize(si));
-  return OGJK_OK;
+  return bad ? 1 : OGJK_OK;  // 1: polytopes not in pair order -> caller reruns the one-shot path
 }
 
 // Host-buffer pipeline shared by every host entry point: upload the pools, repack

@@ -116,6 +116,15 @@ scan_finish_kernel(const int* __restrict__ cnt, long long n, const long long* __
   if (i < n) boff[i] = block_sums[blockIdx.x] + wprefix + v - x;
 }
 
+// Layout check for the chunked host pipeline: polytopes must be stored in pair order
+// without overlap (off[p] >= off[p-1] + cnt[p-1]).  Sets *flag when violated.
+__global__ void __launch_bounds__(256)
+check_monotone_kernel(const long long* __restrict__ off, const int* __restrict__ cnt, long long n, int* __restrict__ flag) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x + 1; p < n; p += stride)
+    if (off[p] < off[p - 1] + cnt[p - 1]) *flag = 1;
+}
+
 // ---- repack: xyz-interleaved blocks -> padded SoA blocks ------------------------
 // Eight lanes per polytope, four polytopes per warp, warp-strided over polytopes.
 template <typename T>
