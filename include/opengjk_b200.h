@@ -210,6 +210,22 @@ OGJK_API int ogjk_compute_epa_f64(ogjk_ctx* ctx, int n, const ogjk_polytope_f64*
                                   ogjk_simplex_f64* simplices, double* distances, double* witness1, double* witness2,
                                   double* contact_normals);
 
+/* ---- device arrays of gkPolytope structs whose `coord` members are DEVICE pointers:
+ * the data shape of the reference's mid-level API.  Replaces
+ *   compute_minimum_distance_device  gpu/include/openGJK_GPU.h:236-242, gpu/opengjk_gpu.cu:3186-3202
+ *   compute_epa_device               openGJK_GPU.h:255-264,             opengjk_gpu.cu:3204-3224
+ * The polytopes are repacked into the context's scratch stores on every call. */
+OGJK_API int ogjk_gjk_device_structs_f32(ogjk_ctx* ctx, int64_t n, const ogjk_polytope_f32* d_bd1, const ogjk_polytope_f32* d_bd2,
+                                         ogjk_simplex_f32* d_simplices, float* d_distances, void* stream);
+OGJK_API int ogjk_gjk_device_structs_f64(ogjk_ctx* ctx, int64_t n, const ogjk_polytope_f64* d_bd1, const ogjk_polytope_f64* d_bd2,
+                                         ogjk_simplex_f64* d_simplices, double* d_distances, void* stream);
+OGJK_API int ogjk_epa_device_structs_f32(ogjk_ctx* ctx, int64_t n, const ogjk_polytope_f32* d_bd1, const ogjk_polytope_f32* d_bd2,
+                                         ogjk_simplex_f32* d_simplices, float* d_distances, float* d_witness1,
+                                         float* d_witness2, float* d_normals, void* stream);
+OGJK_API int ogjk_epa_device_structs_f64(ogjk_ctx* ctx, int64_t n, const ogjk_polytope_f64* d_bd1, const ogjk_polytope_f64* d_bd2,
+                                         ogjk_simplex_f64* d_simplices, double* d_distances, double* d_witness1,
+                                         double* d_witness2, double* d_normals, void* stream);
+
 /* ---- sub-solver test hook, replacing opengjk_test_S1D/S2D/S3D (scalar/include/openGJK/openGJK.h:120-122,
  * scalar/openGJK.c:1232-1248): runs the device Signed-Volumes sub-solver once on `simplex`
  * (nvrtx 2..4, newest vertex in the highest slot), in place; v[3] receives the closest point. */

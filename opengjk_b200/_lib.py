@@ -38,6 +38,8 @@ EXPORTS = [
     "ogjk_store_epa_f32", "ogjk_store_epa_f64", "ogjk_store_gjk_epa_f32", "ogjk_store_gjk_epa_f64",
     "ogjk_gjk_epa_host_f32", "ogjk_gjk_epa_host_f64", "ogjk_compute_gjk_epa_f32", "ogjk_compute_gjk_epa_f64",
     "ogjk_compute_epa_f32", "ogjk_compute_epa_f64", "ogjk_test_subalgorithm_f32", "ogjk_test_subalgorithm_f64",
+    "ogjk_gjk_device_structs_f32", "ogjk_gjk_device_structs_f64", "ogjk_epa_device_structs_f32",
+    "ogjk_epa_device_structs_f64",
     "ogjk_gjk_device_f32", "ogjk_gjk_device_f64", "ogjk_gjk_host_f32", "ogjk_gjk_host_f64",
     "ogjk_compute_minimum_distance_f32", "ogjk_compute_minimum_distance_f64",
     "ogjk_compute_minimum_distance_indexed_f32", "ogjk_compute_minimum_distance_indexed_f64",
@@ -86,6 +88,8 @@ def lib():
         getattr(L, f"ogjk_compute_gjk_epa_{sfx}").argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
         getattr(L, f"ogjk_compute_epa_{sfx}").argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
         getattr(L, f"ogjk_test_subalgorithm_{sfx}").argtypes = [vp, vp, vp]
+        getattr(L, f"ogjk_gjk_device_structs_{sfx}").argtypes = [vp, i64, vp, vp, vp, vp, vp]
+        getattr(L, f"ogjk_epa_device_structs_{sfx}").argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
         getattr(L, f"ogjk_gjk_host_{sfx}").argtypes = [vp, i64, vp, vp, vp, i64, i64, vp, vp, vp, vp, i64, i64, vp,
                                                        vp, vp]
         getattr(L, f"ogjk_compute_minimum_distance_{sfx}").argtypes = [vp, i32, vp, vp, vp, vp]

@@ -781,6 +781,77 @@ int store_gjk(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_s
   return run_store_batch<T>(ctx, sa, static_cast<cudaStream_t>(stream));
 }
 
+// Build a scratch store from a DEVICE array of gkPolytope structs.  The vertex total is
+// not known on the host, so the data buffer is sized from the scanned total (one sync).
+template <typename T>
+int store_build_structs(ogjk_ctx* ctx, ogjk_store_* s, long long npoly, const void* d_bd, cudaStream_t st) {
+  const auto* bd = static_cast<const DevPolytope<T>*>(d_bd);
+  s->device = ctx->device;
+  s->prec = (int)sizeof(T);
+  s->npoly = npoly;
+  int rc;
+  if ((rc = s->boff.reserve((size_t)npoly * sizeof(long long)))) return rc;
+  if ((rc = s->cnt.reserve((size_t)npoly * sizeof(int)))) return rc;
+  const long long nblocks = (npoly + kScanBlock - 1) / kScanBlock;
+  if ((rc = s->scan_tmp.reserve((size_t)(nblocks + 1) * sizeof(long long)))) return rc;
+  int* cnt = static_cast<int*>(s->cnt.p);
+  auto* sums = static_cast<long long*>(s->scan_tmp.p);
+  auto* boff = static_cast<long long*>(s->boff.p);
+  long long eb = (npoly + 255) / 256, cap = (long long)ctx->sm_count * 32;
+  extract_counts_kernel<T><<<(unsigned)(eb < cap ? eb : cap), 256, 0, st>>>(bd, npoly, cnt);
+  scan_block_sums_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(cnt, npoly, sums);
+  scan_spine_kernel<<<1, 1024, 0, st>>>(sums, nblocks, sums + nblocks);
+  scan_finish_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(cnt, npoly, sums, boff);
+  long long total = 0;
+  CU(cudaMemcpyAsync(&total, sums + nblocks, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if ((rc = s->data.reserve((size_t)(total > 0 ? total : 4) * sizeof(T)))) return rc;
+  s->capacity = total;
+  s->nverts = total / 3;
+  long long pblocks = (npoly * 8 + 255) / 256;
+  pack_ptr_kernel<T><<<(unsigned)(pblocks < cap ? pblocks : cap), 256, 0, st>>>(bd, npoly, boff, static_cast<T*>(s->data.p));
+  ctx->launches += 5;
+  CU(cudaGetLastError());
+  return OGJK_OK;
+}
+
+// compute_minimum_distance_device / compute_epa_device over device gkPolytope arrays.
+template <typename T, typename S>
+int device_structs(ogjk_ctx* ctx, int64_t n, const void* d_bd1, const void* d_bd2, S* d_simplices, T* d_distances,
+                   T* d_w1, T* d_w2, T* d_normals, bool run_gjk, bool run_epa, void* stream) {
+  if (n <= 0) return OGJK_OK;
+  if (!ctx || !d_bd1 || !d_bd2 || !d_simplices || !d_distances) return fail(OGJK_ERR_ARG, "NULL device pointer%s");
+  if (run_epa && (!d_w1 || !d_w2)) return fail(OGJK_ERR_ARG, "EPA needs witness arrays%s");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ctx->timed_mask = 0;
+  int rc;
+  if ((rc = store_build_structs<T>(ctx, &ctx->scratch1, n, d_bd1, st))) return rc;
+  if ((rc = store_build_structs<T>(ctx, &ctx->scratch2, n, d_bd2, st))) return rc;
+  if (run_gjk) {
+    StoreArgs<T> sa;
+    sa.s1 = view_of<T>(&ctx->scratch1);
+    sa.s2 = view_of<T>(&ctx->scratch2);
+    sa.idx1 = nullptr; sa.idx2 = nullptr;
+    sa.simplices = reinterpret_cast<GkSimplex<T>*>(d_simplices);
+    sa.distances = d_distances;
+    sa.npairs = n;
+    if ((rc = run_store_batch<T>(ctx, sa, st))) return rc;
+  }
+  if (run_epa) {
+    EpaArgs<T> ea;
+    ea.s1 = view_of<T>(&ctx->scratch1);
+    ea.s2 = view_of<T>(&ctx->scratch2);
+    ea.idx1 = nullptr; ea.idx2 = nullptr;
+    ea.simplices = reinterpret_cast<const GkSimplex<T>*>(d_simplices);
+    ea.distances = d_distances;
+    ea.witness1 = d_w1; ea.witness2 = d_w2; ea.normals = d_normals;
+    ea.npairs = n;
+    if ((rc = run_store_epa<T>(ctx, ea, st))) return rc;
+  }
+  return OGJK_OK;
+}
+
 template <typename T, typename S>
 int test_subalgorithm(ogjk_ctx* ctx, S* simplex, T* v) {
   if (!ctx || !simplex || !v) return fail(OGJK_ERR_ARG, "NULL argument%s");
@@ -1051,6 +1122,29 @@ int ogjk_single_rows_f64(ogjk_ctx* ctx, int n1, double* const* rows1, int n2, do
   }
 OGJK_EPA_IMPL(f32, float, ogjk_polytope_f32, ogjk_simplex_f32)
 OGJK_EPA_IMPL(f64, double, ogjk_polytope_f64, ogjk_simplex_f64)
+
+int ogjk_gjk_device_structs_f32(ogjk_ctx* ctx, int64_t n, const ogjk_polytope_f32* d_bd1, const ogjk_polytope_f32* d_bd2,
+                                ogjk_simplex_f32* d_simplices, float* d_distances, void* stream) {
+  return device_structs<float, ogjk_simplex_f32>(ctx, n, d_bd1, d_bd2, d_simplices, d_distances, nullptr, nullptr, nullptr,
+                                                 true, false, stream);
+}
+int ogjk_gjk_device_structs_f64(ogjk_ctx* ctx, int64_t n, const ogjk_polytope_f64* d_bd1, const ogjk_polytope_f64* d_bd2,
+                                ogjk_simplex_f64* d_simplices, double* d_distances, void* stream) {
+  return device_structs<double, ogjk_simplex_f64>(ctx, n, d_bd1, d_bd2, d_simplices, d_distances, nullptr, nullptr, nullptr,
+                                                  true, false, stream);
+}
+int ogjk_epa_device_structs_f32(ogjk_ctx* ctx, int64_t n, const ogjk_polytope_f32* d_bd1, const ogjk_polytope_f32* d_bd2,
+                                ogjk_simplex_f32* d_simplices, float* d_distances, float* d_w1, float* d_w2,
+                                float* d_normals, void* stream) {
+  return device_structs<float, ogjk_simplex_f32>(ctx, n, d_bd1, d_bd2, d_simplices, d_distances, d_w1, d_w2, d_normals, false,
+                                                 true, stream);
+}
+int ogjk_epa_device_structs_f64(ogjk_ctx* ctx, int64_t n, const ogjk_polytope_f64* d_bd1, const ogjk_polytope_f64* d_bd2,
+                                ogjk_simplex_f64* d_simplices, double* d_distances, double* d_w1, double* d_w2,
+                                double* d_normals, void* stream) {
+  return device_structs<double, ogjk_simplex_f64>(ctx, n, d_bd1, d_bd2, d_simplices, d_distances, d_w1, d_w2, d_normals,
+                                                  false, true, stream);
+}
 
 int ogjk_ctx_set_pipeline_chunks(ogjk_ctx* c, int chunks) {
   if (!c || chunks < 0 || chunks > 16) return fail(OGJK_ERR_ARG, "chunks must be 0..16%s");

@@ -148,6 +148,41 @@ pack_kernel(const T* __restrict__ coords, const long long* __restrict__ off, con
   }
 }
 
+// ---- device arrays of reference-shaped gkPolytope structs ------------------------
+// (what the reference's mid-level API hands around: gpu/include/openGJK_GPU.h:71-76,
+// built by allocate_and_copy_device_arrays).  Same memory layout for both precisions'
+// struct; only numpoints and the device `coord` pointer are read.
+template <typename T> struct DevPolytope { int numpoints; T s[3]; int s_idx; const T* coord; };
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+extract_counts_kernel(const DevPolytope<T>* __restrict__ bd, long long n, int* __restrict__ cnt) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) cnt[i] = bd[i].numpoints;
+}
+
+// Repack from per-polytope device pointers (eight lanes per polytope, as pack_kernel).
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_ptr_kernel(const DevPolytope<T>* __restrict__ bd, long long npoly, const long long* __restrict__ boff,
+                T* __restrict__ out) {
+  const int sub = threadIdx.x & 7;
+  const long long first = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const long long stride = ((long long)gridDim.x * blockDim.x) >> 3;
+  for (long long h = first; h < npoly; h += stride) {
+    const int n = bd[h].numpoints;
+    const int np = pad4(n);
+    const T* src = bd[h].coord;
+    T* dst = out + boff[h];
+    for (int i = sub; i < np; i += 8) {
+      const int j = i < n ? i : 0;
+      dst[i] = src[3 * j];
+      dst[np + i] = src[3 * j + 1];
+      dst[2 * np + i] = src[3 * j + 2];
+    }
+  }
+}
+
 // ---- counting sort of pairs by padded vertex total ------------------------------
 // key = (pad4(n1) + pad4(n2)) / 4, clamped to kMaxKey.  Output order is
 // DESCENDING key (largest pairs first: better tail behaviour of the work queue).
