@@ -271,7 +271,7 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
   unsigned long long* counters = nullptr;
   int rc = reset_counters(ctx, st, &counters);
   if (rc) return rc;
-  const size_t nkeys = kMaxKey + 2;
+  const size_t nkeys = kNumBins + 1;
   if ((rc = ctx->sort_tmp.reserve(3 * nkeys * sizeof(unsigned)))) return rc;
   if ((rc = ctx->sorted_list.reserve((size_t)a.npairs * sizeof(int)))) return rc;
   unsigned* hist = static_cast<unsigned*>(ctx->sort_tmp.p);
@@ -289,13 +289,14 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
   mark(ctx, st, 1, 1);
   ctx->launches += 3;
 
-  // start[k] = number of pairs with key > k  =>  class (lo, hi] occupies [start[hi], start[lo])
+  // start[b] = number of pairs with bin > b  =>  the class of size keys (lo, hi] occupies
+  // [start[bin_upper(hi)], start[bin_upper(lo)]) of the sorted list
   int lo = 0;
   for (int c = 0; c < ctx->nclasses; ++c) {
     const int hi = ctx->class_hi[c] > kMaxKey ? kMaxKey : ctx->class_hi[c];
     if (hi <= lo) continue;
-    const unsigned* b = start + hi;
-    const unsigned* e = start + lo;
+    const unsigned* b = start + bin_upper(hi);
+    const unsigned* e = start + bin_upper(lo);
     unsigned long long* head = counters + c;
     mark(ctx, st, 2 + c, 0);
     switch (ctx->class_lanes[c]) {

@@ -184,10 +184,28 @@ pack_ptr_kernel(const DevPolytope<T>* __restrict__ bd, long long npoly, const lo
 }
 
 // ---- counting sort of pairs by padded vertex total ------------------------------
-// key = (pad4(n1) + pad4(n2)) / 4, clamped to kMaxKey.  Output order is
-// DESCENDING key (largest pairs first: better tail behaviour of the work queue).
+// size key tk = (pad4(n1) + pad4(n2)) / 4, clamped to kMaxKey: what the scheduler's class
+// table is expressed in.  The sort itself uses a finer bin: for tk <= kFineKeys the
+// bin also encodes pad4(n1)/4, so that the pairs of a warp agree not only on the
+// total but on the split -- both support scans of every lane then have the same
+// trip count (ncu: the scans ran at 12/32 lanes when only the total was sorted).
+// Output order is DESCENDING bin (largest pairs first: better queue tail).
 constexpr int kMaxKey = 2048;
 constexpr int kSmallKeyMax = 4;
+constexpr int kFineKeys = 64;   // totals up to 256 padded vertices get the (total, split) bin
+constexpr int kFineSub = 32;    // sub-bins per total
+constexpr int kNumBins = kFineKeys * kFineSub + kFineSub + (kMaxKey - kFineKeys);  // 4064
+__host__ __device__ __forceinline__ int bin_of(int tk, int np1) {
+  if (tk <= kFineKeys) {
+    const int sub = (np1 >> 2) < kFineSub ? (np1 >> 2) : kFineSub - 1;
+    return tk * kFineSub + sub;
+  }
+  return kFineKeys * kFineSub + kFineSub - 1 + (tk - kFineKeys);
+}
+// Largest bin that belongs to size key <= tk (class boundaries).
+__host__ __device__ __forceinline__ int bin_upper(int tk) {
+  return tk <= kFineKeys ? tk * kFineSub + kFineSub - 1 : kFineKeys * kFineSub + kFineSub - 1 + (tk - kFineKeys);
+}
 constexpr int kSortBlock = 256;
 constexpr int kSortItems = 8;  // pairs per thread
 
@@ -200,15 +218,16 @@ __device__ __forceinline__ int pair_key(const StoreView<T>& s1, const StoreView<
   int k = (np1 + np2) >> 2;
   // keys 2..4 are reserved for pairs whose two polytopes both fit 8 register slots
   if ((np1 > 8 || np2 > 8) && k < kSmallKeyMax + 1) k = kSmallKeyMax + 1;
-  return k > kMaxKey ? kMaxKey : k;
+  if (k > kMaxKey) k = kMaxKey;
+  return bin_of(k, np1);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kSortBlock)
 sort_hist_kernel(StoreView<T> s1, StoreView<T> s2, const int* __restrict__ idx1, const int* __restrict__ idx2,
                  long long npairs, unsigned* __restrict__ hist) {
-  __shared__ unsigned sh[kMaxKey + 1];
-  for (int i = threadIdx.x; i <= kMaxKey; i += kSortBlock) sh[i] = 0;
+  __shared__ unsigned sh[kNumBins];
+  for (int i = threadIdx.x; i < kNumBins; i += kSortBlock) sh[i] = 0;
   __syncthreads();
   const long long base = (long long)blockIdx.x * kSortBlock * kSortItems;
 #pragma unroll
@@ -217,27 +236,44 @@ sort_hist_kernel(StoreView<T> s1, StoreView<T> s2, const int* __restrict__ idx1,
     if (p < npairs) atomicAdd(&sh[pair_key(s1, s2, idx1, idx2, p)], 1u);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i <= kMaxKey; i += kSortBlock)
+  for (int i = threadIdx.x; i < kNumBins; i += kSortBlock)
     if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
-// Single block.  start[k] = number of pairs with key > k (descending layout);
-// start[kMaxKey+1 .. ] unused.  Also resets the scatter cursors.
+// Single block.  start[b] = number of pairs with bin > b (descending layout).  Also
+// resets the scatter cursors.  Warp 0 does a chunked suffix scan over the bins.
 __global__ void __launch_bounds__(1024)
 sort_scan_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ start, unsigned* __restrict__ cursor) {
-  __shared__ unsigned sh[kMaxKey + 2];
-  for (int i = threadIdx.x; i <= kMaxKey; i += 1024) sh[i] = hist[i];
+  __shared__ unsigned sh[kNumBins];
+  for (int i = threadIdx.x; i < kNumBins; i += 1024) sh[i] = hist[i];
   __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned acc = 0;
-    for (int k = kMaxKey; k >= 0; --k) {
-      const unsigned c = sh[k];
-      sh[k] = acc;
-      acc += c;
+  if (threadIdx.x < 32) {
+    // lane l owns the contiguous bins [l*per, (l+1)*per) counted from the TOP
+    constexpr int per = (kNumBins + 31) / 32;
+    const int lane = threadIdx.x;
+    unsigned local = 0;
+    for (int j = 0; j < per; ++j) {
+      const int b = kNumBins - 1 - (lane * per + j);
+      if (b >= 0) local += sh[b];
+    }
+    unsigned incl = local;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, m);
+      if (lane >= m) incl += t;
+    }
+    unsigned acc = incl - local;  // pairs in bins above this lane's range
+    for (int j = 0; j < per; ++j) {
+      const int b = kNumBins - 1 - (lane * per + j);
+      if (b >= 0) {
+        const unsigned c = sh[b];
+        sh[b] = acc;
+        acc += c;
+      }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i <= kMaxKey; i += 1024) {
+  for (int i = threadIdx.x; i < kNumBins; i += 1024) {
     start[i] = sh[i];
     cursor[i] = 0;
   }
@@ -248,8 +284,8 @@ __global__ void __launch_bounds__(kSortBlock)
 sort_scatter_kernel(StoreView<T> s1, StoreView<T> s2, const int* __restrict__ idx1, const int* __restrict__ idx2,
                     long long npairs, const unsigned* __restrict__ start, unsigned* __restrict__ cursor,
                     int* __restrict__ sorted) {
-  __shared__ unsigned sh[kMaxKey + 1];
-  for (int i = threadIdx.x; i <= kMaxKey; i += kSortBlock) sh[i] = 0;
+  __shared__ unsigned sh[kNumBins];
+  for (int i = threadIdx.x; i < kNumBins; i += kSortBlock) sh[i] = 0;
   __syncthreads();
   const long long base = (long long)blockIdx.x * kSortBlock * kSortItems;
   int key[kSortItems];
@@ -265,7 +301,7 @@ sort_scatter_kernel(StoreView<T> s1, StoreView<T> s2, const int* __restrict__ id
   }
   __syncthreads();
   // reserve a contiguous range per key for this block
-  for (int i = threadIdx.x; i <= kMaxKey; i += kSortBlock) {
+  for (int i = threadIdx.x; i < kNumBins; i += kSortBlock) {
     const unsigned c = sh[i];
     if (c) sh[i] = start[i] + atomicAdd(&cursor[i], c);
   }
