@@ -52,6 +52,8 @@ WORKLOADS = {
                     lambda n, seed: W.large_hull_pool(n, 32768, 1000, 1000, seed, dtype=np.float32), 200_000),
     "hulls1k10k_f32": ("config4: indexed pairs of 1k-10k-vertex hulls, fp32", np.float32,
                        lambda n, seed: W.large_hull_pool(n, 2048, 1000, 10000, seed, dtype=np.float32), 50_000),
+    "boxes100m_f32": ("config3 at full size: 100 M oriented box-box pairs generated on the device, fp32", np.float32,
+                      None, 100_000_000),
     "epa_f32": ("config5: intersecting 8-64-vertex hull pairs, GJK + EPA, fp32", np.float32,
                 lambda n, seed: W.random_hulls(n, 8, 64, seed, 1.0, np.float32, 0.5), 1_000_000, True),
 }
@@ -168,6 +170,7 @@ def run_reference_arm(args, rank, world):
     from oracle.pyoracle import Oracle, Reference
     cores = os.cpu_count() or 1
     n = min(args.pairs or default_pairs, args.ref_sample)
+    maker = maker or (lambda n_, seed_: W.boxes(n_, True, seed_, dtype=np.float32))  # device-generated workloads
     w = maker(n, args.seed)
     if Reference.available(prec):
         kind, ref = "reference", Reference(prec)
@@ -413,6 +416,142 @@ def main():
         del d_coords, d_simp, d_dist
         torch.cuda.empty_cache()
         return res
+
+    def device_boxes(n, seed):
+        """Config #3 inputs generated on the GPU in 10 M-pair slabs (same construction as
+        workloads.boxes: half-extents U[0.5,1.5], uniform random rotation, body 2 offset 6(u-0.5))."""
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+        coords = torch.empty(2 * n * 8 * 3, dtype=torch.float32, device=dev)
+        box = torch.tensor(W._BOX, dtype=torch.float32, device=dev)
+        slab = 10_000_000
+        for lo in range(0, n, slab):
+            m = min(slab, n - lo)
+            nb = 2 * m
+            half = 0.5 + torch.rand((nb, 1, 3), generator=g, device=dev)
+            q = torch.randn((nb, 4), generator=g, device=dev)
+            q = q / q.norm(dim=1, keepdim=True)
+            qw, qx, qy, qz = q.unbind(1)
+            rot = torch.stack([1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw),
+                               2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw),
+                               2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)], 1).view(nb, 3, 3)
+            pts = torch.einsum("bij,bvj->bvi", rot, box[None] * half)
+            shift = torch.zeros((nb, 1, 3), device=dev)
+            shift[1::2, 0] = 6.0 * (torch.rand((m, 3), generator=g, device=dev) - 0.5)
+            coords[2 * lo * 24:2 * (lo + m) * 24] = (pts + shift).reshape(-1)
+            del half, q, rot, pts, shift
+        cnt = torch.full((2 * n,), 8, dtype=torch.int32, device=dev)
+        off = torch.arange(2 * n, dtype=torch.int64, device=dev) * 8
+        pa = torch.arange(0, 2 * n, 2, dtype=torch.int32, device=dev)
+        return coords, off, cnt, pa, pa + 1
+
+    def measure_device_boxes(name, pairs, steps, warmup, with_cpu):
+        """100 M-pair box batch: inputs never exist on the host; parity is checked on samples
+        copied back (first 20 k pairs and a strided 20 k), e2e on an 8 M-pair sub-batch."""
+        desc = WORKLOADS[name][0]
+        n = pairs or WORKLOADS[name][3]
+        prec, sdt = "f32", api.SIMPLEX_F32
+        d_coords, d_off, d_cnt, d_pa, d_pb = device_boxes(n, args.seed + rank)
+        d_dist = torch.empty(n, dtype=torch.float32, device=dev)
+        d_simp = torch.empty(n * sdt.itemsize, dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        t0 = time.perf_counter()
+        store = eng.store_create(d_coords, d_off, d_cnt, stream)
+        torch.cuda.synchronize()
+        store_build_ms = 1e3 * (time.perf_counter() - t0)
+        step = lambda: eng.store_gjk(store, d_pa, store, d_pb, n, d_simp, d_dist, stream)
+        eng.set_timing(False)
+        for _ in range(warmup):
+            step()
+        barrier()
+        launches0 = eng.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clk:
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            launches = eng.launch_count - launches0
+            barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_max = float(t.item())
+        eng.set_timing(True)
+        cls = []
+        for _ in range(3):
+            step()
+            torch.cuda.synchronize()
+            lt = eng.last_timing()
+            cls.append([lt["sort"]] + lt["classes"])
+        eng.set_timing(False)
+        avg = [float(x) for x in np.mean(np.array(cls), axis=0)]
+        alg_bytes = n * (16 * 12 + 108 + 4)
+        kms = avg[1]  # class 0 = register-resident kernel
+        roofline = {"bound": "hbm", "achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "kernel": "gjk_small_kernel<float>",
+                    "kernel_ms": kms, "step_phases_ms": {"sort": avg[0], "classes": avg[1:]},
+                    "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
+        # samples back to the host: parity vs the oracle, CPU baseline, e2e sub-batch
+        def host_sample(idx):
+            idx = np.asarray(idx)
+            c = torch.cat([d_coords.view(-1, 48)[idx], ]).cpu().numpy().reshape(-1, 3)  # both boxes of a pair are adjacent
+            m = len(idx)
+            cnt = np.full(2 * m, 8, dtype=np.int32)
+            off = np.arange(2 * m, dtype=np.int64) * 8
+            pa = np.arange(0, 2 * m, 2, dtype=np.int32)
+            return W.Workload("boxes_sample", c, off, cnt, pa, pa + 1)
+        res = {"workload": desc, "value": n * world * steps / (ms_max * 1e-3), "ms_per_step": ms_max / steps,
+               "launches": launches, "roofline": roofline, "clocks": clk.summary(), "prec": prec, "pairs_per_gpu": n,
+               "input_bytes_per_gpu": int(d_coords.numel() * 4 + d_off.numel() * 8 + d_cnt.numel() * 4 + 2 * d_pa.numel() * 4),
+               "from_raw_arrays": None, "store_build_ms": store_build_ms, "store_bytes": store.nbytes}
+        if rank == 0:
+            from oracle.pyoracle import Oracle
+            checks = {}
+            for label, idx in (("first", np.arange(20000)), ("strided", np.arange(0, n, max(1, n // 20000))[:20000])):
+                ws = host_sample(idx)
+                dref, sref = Oracle(prec).batch(ws.coords, ws.off, ws.cnt, ws.pa, ws.pb, nthreads=os.cpu_count() or 1)
+                ti = torch.from_numpy(idx).to(dev)
+                got_d = d_dist[ti].cpu().numpy()
+                got_s = d_simp.view(-1, sdt.itemsize)[ti].cpu().numpy().reshape(-1).view(sdt)
+                checks[label] = {"pairs": len(idx), "distance_bits_equal": bool(got_d.tobytes() == dref.tobytes()),
+                                 "simplex_bytes_equal": bool(got_s.tobytes() == sref.tobytes())}
+            res["sample_parity"] = checks
+            if with_cpu:
+                res["cpu_baseline"] = cpu_baseline(host_sample(np.arange(100000)), prec)
+        # e2e on an 8 M-pair sub-batch through the host-buffer API (two pinned pools)
+        m = min(n, 8_000_000)
+        sub = d_coords[: m * 48].view(m, 2, 24)
+        pin = lambda a: a.contiguous().cpu().pin_memory().numpy()
+        c1, c2 = pin(sub[:, 0].reshape(-1)), pin(sub[:, 1].reshape(-1))
+        k = torch.full((m,), 8, dtype=torch.int32).pin_memory().numpy()
+        o = (torch.arange(m, dtype=torch.int64) * 8).pin_memory().numpy()
+        out = (torch.empty(m, dtype=torch.float32).pin_memory().numpy(),
+               torch.empty(m * sdt.itemsize, dtype=torch.uint8).pin_memory().numpy().view(sdt))
+        eng.gjk_host_pools(c1, o, k, c2, o, k, out=out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            eng.gjk_host_pools(c1, o, k, c2, o, k, out=out)
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res["e2e"] = {"value": m * world * 3 / float(t.item()), "unit": "pairs/s",
+                      "h2d_bytes_per_step": int(c1.nbytes + c2.nbytes + 2 * (k.nbytes + o.nbytes)),
+                      "d2h_bytes_per_step": int(out[0].nbytes + out[1].nbytes), "steps": 3,
+                      "api": "ogjk_gjk_host_f32 on an 8 M-pair sub-batch (two pinned pools, chunk-pipelined)"}
+        store.close()
+        del d_coords, d_simp, d_dist
+        torch.cuda.empty_cache()
+        return res
+
+    _measure = measure
+
+    def measure(name, pairs, steps, warmup, with_cpu):
+        if WORKLOADS[name][2] is None:
+            return measure_device_boxes(name, pairs, steps, warmup, with_cpu)
+        return _measure(name, pairs, steps, warmup, with_cpu)
 
     main_res = measure(args.workload, args.pairs, args.steps, args.warmup, not args.no_cpu_baseline)
     others = {}
