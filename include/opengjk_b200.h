@@ -84,7 +84,9 @@ OGJK_API int ogjk_ctx_last_timing(ogjk_ctx* ctx, float* ms8);
  * key = (pad4(n1) + pad4(n2)) / 4; class i takes keys in (hi_keys[i-1], hi_keys[i]]
  * and runs with lanes[i] cooperating lanes per pair (1, 2, 4, 8, 16 or 32; add 100
  * for the flavour that stages both polytopes in shared memory first, 200 for the
- * persistent-lane flavour that refills a lane as soon as its pair terminates), or
+ * persistent-lane flavour that refills a lane as soon as its pair terminates, 300 for the
+ * scan-assist flavour: 32/lanes pairs per warp share the sub-solver pass while every
+ * support scan uses all 32 lanes), or
  * lanes[i] = 0 for the register-resident thread-per-pair kernel (keys <= 4 only:
  * both polytopes have at most 8 vertices).  At most 6 classes; the last one
  * always extends to the largest key. */

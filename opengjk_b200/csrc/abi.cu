@@ -247,6 +247,13 @@ int launch_staged(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const u
   return OGJK_OK;
 }
 
+template <typename T, int G>
+void launch_assist(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const unsigned* b, const unsigned* e,
+                   unsigned long long* head, cudaStream_t st) {
+  long long blocks = (a.npairs * G + 127) / 128, cap = (long long)ctx->sm_count * 16;
+  gjk_assist_kernel<T, G><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, list, b, e, head);
+}
+
 // Persistent-lane flavour: iterate kernel, then (when simplices are wanted) the witness pass
 // over the same list segment.
 template <typename T, int G>
@@ -310,6 +317,10 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
       case 8: launch_group<T, 8>(ctx, a, sorted, b, e, head, st); break;
       case 16: launch_group<T, 16>(ctx, a, sorted, b, e, head, st); break;
       case 32: launch_group<T, 32>(ctx, a, sorted, b, e, head, st); break;
+      case 302: launch_assist<T, 2>(ctx, a, sorted, b, e, head, st); break;
+      case 304: launch_assist<T, 4>(ctx, a, sorted, b, e, head, st); break;
+      case 308: launch_assist<T, 8>(ctx, a, sorted, b, e, head, st); break;
+      case 316: launch_assist<T, 16>(ctx, a, sorted, b, e, head, st); break;
       case 200: launch_persist<T, 0>(ctx, a, sorted, b, e, head, st); break;
       case 201: launch_persist<T, 1>(ctx, a, sorted, b, e, head, st); break;
       case 202: launch_persist<T, 2>(ctx, a, sorted, b, e, head, st); break;
@@ -987,10 +998,12 @@ int ogjk_ctx_set_classes(ogjk_ctx* c, int n, const int* hi_keys, const int* lane
   int prev = 0;
   for (int i = 0; i < n; ++i) {
     const int l = lanes[i];
-    // 100 + G: shared-memory staged flavour; 200 + G: persistent-lane flavour (200 = register-resident)
-    const int gl = l >= 200 ? l - 200 : (l >= 100 ? l - 100 : l);
+    // 100 + G: shared-memory staged flavour; 200 + G: persistent-lane flavour (200 = register-resident);
+    // 300 + G: scan-assist flavour (G = 2, 4, 8, 16 lanes of state per pair, 32-lane scans)
+    const int gl = l >= 300 ? l - 300 : (l >= 200 ? l - 200 : (l >= 100 ? l - 100 : l));
+    if (l >= 300 && !(gl == 2 || gl == 4 || gl == 8 || gl == 16)) return fail(OGJK_ERR_ARG, "scan-assist needs 302/304/308/316%s");
     if (!((gl == 0 && (l == 0 || l == 200)) || gl == 1 || gl == 2 || gl == 4 || gl == 8 || gl == 16 || gl == 32))
-      return fail(OGJK_ERR_ARG, "lanes must be 0, a power of two <= 32, or 100/200 + that%s");
+      return fail(OGJK_ERR_ARG, "lanes must be 0, a power of two <= 32, or 100/200/300 + that%s");
     if (gl == 0 && hi_keys[i] > kSmallKeyMax) return fail(OGJK_ERR_ARG, "register-resident class is limited to key <= 4%s");
     if (hi_keys[i] <= prev) return fail(OGJK_ERR_ARG, "class keys must increase%s");
     prev = hi_keys[i];

@@ -115,6 +115,22 @@ OGJK_DI void gjk_init(const Body& b1, const Body& b2, GjkState<T>& st) {
   st.k = 0;
 }
 
+// The part of one do-while pass (:983-1036) that follows the two support calls.
+// Returns true when the query is finished.
+template <typename T>
+OGJK_DI bool gjk_step_tail(GjkState<T>& st) {
+  const T er = eps_rel<T>(), ea = eps_abs<T>();
+  const V3<T> w = sub(st.sa, st.sb);
+  const T vv = nrm2(st.v.x, st.v.y, st.v.z);
+  const T gap = vv - dot3(st.v, w);
+  if (gap <= (er * vv) || gap < ea) return true;   // :1002-1006
+  if (vv < er * er) return true;                     // :1008-1010
+  push_and_solve(st.s, MV<T>{w.x, w.y, w.z, st.ia, st.ib}, st.v);
+  st.wmax2 = update_wmax(st.s, st.wmax2);
+  if (nrm2(st.v.x, st.v.y, st.v.z) <= (ea * ea * st.wmax2)) return true;  // :1032
+  return st.s.n == 4 || st.k == kMaxIter;
+}
+
 // One pass of the do-while at :983-1036.  Returns true when the query is finished.
 template <typename T, typename Body>
 OGJK_DI bool gjk_step(const Body& b1, const Body& b2, GjkState<T>& st) {
@@ -287,8 +303,14 @@ template <typename T, int G> struct GroupBody {
   const T* blk; int n; int np; int g; unsigned mask;
   OGJK_DI V3<T> vertex(int i) const { return V3<T>{blk[i], blk[np + i], blk[2 * np + i]}; }
   OGJK_DI void support(T dx, T dy, T dz, V3<T>& cur, int& cur_i) const {
+    const int better = scan(dx, dy, dz, dot3(cur.x, cur.y, cur.z, dx, dy, dz));
+    if (better != 0x7fffffff) { cur = vertex(better); cur_i = better; }
+  }
+  // Lowest index of the vertex with the largest dot product, provided it strictly exceeds
+  // `best` (the carried support point's dot); 0x7fffffff when nothing does.  Same value in
+  // every lane of the group.
+  OGJK_DI int scan(T dx, T dy, T dz, T best) const {
     constexpr int CV = Chunk<T>::kVerts;
-    T best = dot3(cur.x, cur.y, cur.z, dx, dy, dz);
     int better = 0x7fffffff;
     const int nchunks = np / CV;
     const T* xp = blk;
@@ -335,7 +357,7 @@ template <typename T, int G> struct GroupBody {
       const int oi = __shfl_xor_sync(mask, better, m);
       if (ob > best || (ob == best && oi < better)) { best = ob; better = oi; }
     }
-    if (better != 0x7fffffff) { cur = vertex(better); cur_i = better; }
+    return better;
   }
 };
 
@@ -435,6 +457,89 @@ gjk_staged_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* 
         if (a.simplices) store_simplex(a.simplices + p, s, w1, w2);
       }
       __syncwarp(mask);  // everyone is done reading the slot before it is refilled
+    }
+  }
+}
+
+// Scan-assist kernel for large hulls.  A warp owns P = 32/G pairs: the G lanes of a group
+// carry one pair's GJK state and run its sub-solver (redundantly and convergently, as in
+// gjk_group_kernel), but every support scan is done by ALL 32 lanes for one pair at a
+// time (the group leader broadcasts the block pointers, direction and carried dot; the
+// 32-lane butterfly result goes back to the group).  The warp-per-pair kernel spent ~40 %
+// of its instructions in the per-iteration fixed part (sub-solver, termination tests,
+// reductions); here that part is shared by P pairs while the scans keep all lanes busy
+// with coalesced 512-byte reads.  Scan order and tie rule are those of GroupBody<T,32>,
+// so results are unchanged.
+template <typename T, int G>
+__global__ void __launch_bounds__(128, (sizeof(T) == 8 ? 2 : 4))
+gjk_assist_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* __restrict__ seg_begin,
+                  const unsigned* __restrict__ seg_end, unsigned long long* __restrict__ head) {
+  constexpr int P = 32 / G;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / G;
+  const long long begin = seg_begin ? (long long)*seg_begin : 0;
+  const long long end = seg_end ? (long long)*seg_end : a.npairs;
+  for (;;) {
+    unsigned long long got = 0;
+    if (lane == 0) got = atomicAdd(head, (unsigned long long)P);
+    got = __shfl_sync(FULL, got, 0);
+    const long long base = begin + (long long)got;
+    if (base >= end) break;
+    const long long slot = base + grp;
+    bool active = slot < end;
+    long long p = 0;
+    const T* blk1 = nullptr; const T* blk2 = nullptr;
+    int n1 = 0, n2 = 0;
+    GjkState<T> st;
+    if (active) {
+      p = list ? (long long)list[slot] : slot;
+      const long long h1 = a.idx1 ? (long long)a.idx1[p] : p;
+      const long long h2 = a.idx2 ? (long long)a.idx2[p] : p;
+      n1 = a.s1.cnt[h1]; n2 = a.s2.cnt[h2];
+      blk1 = a.s1.data + a.s1.boff[h1];
+      blk2 = a.s2.data + a.s2.boff[h2];
+    }
+    const GroupBody<T, 32> own1{blk1, n1, pad4(n1), lane, FULL}, own2{blk2, n2, pad4(n2), lane, FULL};
+    if (active) gjk_init(own1, own2, st);
+    for (;;) {
+      const unsigned live = __ballot_sync(FULL, active);
+      if (!live) break;
+      int win1 = 0x7fffffff, win2 = 0x7fffffff;
+#pragma unroll 1
+      for (int j = 0; j < P; ++j) {
+        const int leader = j * G;
+        if (!((live >> leader) & 1u)) continue;  // uniform
+        // the leader of group j hands its pair to the whole warp
+        const unsigned long long q1 = __shfl_sync(FULL, (unsigned long long)blk1, leader);
+        const unsigned long long q2 = __shfl_sync(FULL, (unsigned long long)blk2, leader);
+        const int m1 = __shfl_sync(FULL, n1, leader), m2 = __shfl_sync(FULL, n2, leader);
+        const T vx = __shfl_sync(FULL, st.v.x, leader), vy = __shfl_sync(FULL, st.v.y, leader),
+                vz = __shfl_sync(FULL, st.v.z, leader);
+        const T c1 = __shfl_sync(FULL, dot3(st.sa.x, st.sa.y, st.sa.z, -st.v.x, -st.v.y, -st.v.z), leader);
+        const T c2 = __shfl_sync(FULL, dot3(st.sb.x, st.sb.y, st.sb.z, st.v.x, st.v.y, st.v.z), leader);
+        const GroupBody<T, 32> w1{reinterpret_cast<const T*>(q1), m1, pad4(m1), lane, FULL};
+        const GroupBody<T, 32> w2{reinterpret_cast<const T*>(q2), m2, pad4(m2), lane, FULL};
+        const int r1 = w1.scan(-vx, -vy, -vz, c1);
+        const int r2 = w2.scan(vx, vy, vz, c2);
+        if (grp == j) { win1 = r1; win2 = r2; }
+      }
+      if (active) {
+        st.k++;
+        if (win1 != 0x7fffffff) { st.sa = own1.vertex(win1); st.ia = win1; }
+        if (win2 != 0x7fffffff) { st.sb = own2.vertex(win2); st.ib = win2; }
+        if (gjk_step_tail(st)) {
+          V3<T> w1, w2;
+          Splx<T> s = st.s;
+          gjk_witnesses(own1, own2, s, w1, w2);
+          if (lane % G == 0) {
+            a.distances[p] = sqrt(nrm2(st.v.x, st.v.y, st.v.z));
+            if (a.simplices) store_simplex(a.simplices + p, s, w1, w2);
+          }
+          active = false;
+        }
+      }
+      __syncwarp();
     }
   }
 }

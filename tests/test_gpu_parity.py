@@ -122,6 +122,8 @@ def test_scheduler_classes_do_not_change_results(eng, prec, dt):
     # persistent-lane flavours (200 + lanes; 200 = register-resident)
     tables += [[(2048, 200 + g)] for g in (1, 2, 4, 8, 16, 32)]
     tables += [[(4, 200), (24, 202), (64, 204), (2048, 232)]]
+    # scan-assist flavours (300 + lanes of state per pair; scans use the whole warp)
+    tables += [[(2048, 300 + g)] for g in (2, 4, 8, 16)]
     try:
         for t in tables:
             eng.set_classes(t)
