@@ -364,8 +364,17 @@ template <typename T, int G> struct GroupBody {
 // Segment [*seg_begin, *seg_end) of the size-sorted pair list (or the identity
 // list when `list` is null) is consumed through a device-side work queue, 32/G
 // pairs per grab.
+#ifndef OGJK_LB_GROUP_F32
+#define OGJK_LB_GROUP_F32 4
+#endif
+#ifndef OGJK_LB_GROUP_F64
+#define OGJK_LB_GROUP_F64 4
+#endif
+#ifndef OGJK_LB_SMALL_F32
+#define OGJK_LB_SMALL_F32 4
+#endif
 template <typename T, int G>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, (sizeof(T) == 8 ? OGJK_LB_GROUP_F64 : OGJK_LB_GROUP_F32))
 gjk_group_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* __restrict__ seg_begin,
                  const unsigned* __restrict__ seg_end, unsigned long long* __restrict__ head) {
   constexpr int PER_WARP = 32 / G;
@@ -578,7 +587,7 @@ template <typename T> struct RegBody {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (sizeof(T) == 8 ? 2 : OGJK_LB_SMALL_F32))
 gjk_small_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* __restrict__ seg_begin,
                  const unsigned* __restrict__ seg_end, unsigned long long* __restrict__ head) {
   const int lane = threadIdx.x & 31;
