@@ -214,7 +214,8 @@ template <typename T> StoreView<T> view_of(const ogjk_store_* s) {
 template <typename T, int G>
 void launch_group(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const unsigned* b, const unsigned* e,
                   unsigned long long* head, cudaStream_t st) {
-  long long blocks = (a.npairs * G + 127) / 128, cap = (long long)ctx->sm_count * 16;
+  static const int cap_per_sm = getenv("OGJK_GRID_CAP") ? atoi(getenv("OGJK_GRID_CAP")) : 16;  // tuning hook
+  long long blocks = (a.npairs * G + 127) / 128, cap = (long long)ctx->sm_count * cap_per_sm;
   gjk_group_kernel<T, G><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, list, b, e, head);
 }
 

@@ -266,3 +266,27 @@ def test_chunk_pipelined_host_path(eng, prec, dt):
     got = eng.gjk_host_pools(*w.two_pools(), epa=True)
     for k in ("distances", "witness1", "witness2", "normals"):
         assert np.ascontiguousarray(got[k]).tobytes() == np.ascontiguousarray(ref[k]).tobytes(), k
+
+
+@pytest.mark.parametrize("prec,dt", PRECS)
+def test_scheduler_edge_cases(eng, prec, dt):
+    """Batch sizes around warp/block boundaries, one pair, a hull beyond the largest sort key
+    (> 8192 vertices per pair), and a batch that populates every size class at once."""
+    o = Oracle(prec)
+    rng = np.random.default_rng(91)
+    for n in (1, 31, 32, 33, 127, 129, 2049):
+        w = W.random_hulls(n, 1, 40, 92 + n, 3.0, dt)
+        dref, sref = o.batch(w.coords, w.off, w.cnt, w.pa, w.pb)
+        d, s = _gpu(eng, w)
+        _assert_same(f"n{n}", d, s, dref, sref, prec)
+    bodies_a, bodies_b = [], []
+    for n1, n2 in ((20000, 3), (5, 9000), (8, 8), (4, 4), (1, 1), (70, 60), (300, 200), (1000, 1200), (3, 700)):
+        a = rng.normal(size=(n1, 3)); a /= np.linalg.norm(a, axis=1, keepdims=True)
+        b = rng.normal(size=(n2, 3)); b /= np.linalg.norm(b, axis=1, keepdims=True)
+        bodies_a.append(a); bodies_b.append(b + rng.uniform(-2.5, 2.5, size=3))
+    w = W.from_bodies(bodies_a * 40, bodies_b * 40, dt, "all_classes")
+    dref, sref = o.batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1)
+    d, s = _gpu(eng, w)
+    _assert_same("all_classes", d, s, dref, sref, prec)
+    d, s = eng.run_workload(w)
+    _assert_same("all_classes_host", d, s, dref, sref, prec)
