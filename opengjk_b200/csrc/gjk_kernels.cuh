@@ -447,12 +447,18 @@ gjk_staged_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* 
       const T* src2 = a.s2.data + a.s2.boff[h2];
       const int c1 = 3 * np1 * (int)sizeof(T) / 16, c2 = 3 * np2 * (int)sizeof(T) / 16;
       // the host only routes a class here when every pair of the class fits its slot
+      // cp.async (LDGSTS): every 16-byte chunk of both blocks is put in flight at once, no
+      // register staging; one wait covers the whole pair (the first version copied through
+      // registers four chunks at a time and paid the L2 latency on every trip).
       const uint4* s1v = reinterpret_cast<const uint4*>(src1);
       const uint4* s2v = reinterpret_cast<const uint4*>(src2);
-#pragma unroll 4
-      for (int c = g; c < c1; c += G) slot[c] = s1v[c];
-#pragma unroll 4
-      for (int c = g; c < c2; c += G) slot[c1 + c] = s2v[c];
+      const unsigned sbase = (unsigned)__cvta_generic_to_shared(slot);
+      for (int c = g; c < c1; c += G)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * c), "l"(s1v + c) : "memory");
+      for (int c = g; c < c2; c += G)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * (c1 + c)), "l"(s2v + c) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       const T* blk1 = reinterpret_cast<const T*>(slot);
       const T* blk2 = reinterpret_cast<const T*>(slot + c1);
       __syncwarp(mask);

@@ -40,10 +40,15 @@ for name in names:
     if os.environ.get("TUNE_PERSIST"):
         variants += [201, 202, 204, 208, 232]
     if os.environ.get("TUNE_STAGED"):
-        variants += [101, 102, 104, 108, 116, 132]
+        variants += [102, 104, 108, 132]
+        if 12 < kmax <= 40:
+            variants += [1102, 1104, 1108]  # three slot sizes
     for g in variants:
         if g == 0:
             table = [(4, 0), (2048, 1)]
+        elif g > 1000:
+            gg = g - 1000
+            table = [(12, gg), (20, gg), (kmax, gg), (2048, gg - 100)]
         elif g == 200:
             table = [(4, 200), (2048, 201)]
         elif g > 200:
@@ -65,5 +70,5 @@ for name in names:
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
-        print(f"{name:14s} lanes={g:3d}  {ms:8.3f} ms  {w.npairs / ms / 1e3:10.1f} Mpairs/s", flush=True)
+        print(f"{name:14s} lanes={g:4d}  {ms:8.3f} ms  {w.npairs / ms / 1e3:10.1f} Mpairs/s", flush=True)
     store.close()
