@@ -248,6 +248,28 @@ int launch_staged(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const u
   return OGJK_OK;
 }
 
+// CTA-per-pair flavour: dynamic shared memory = the class's largest pair.
+template <typename T, int WARPS>
+int launch_cta(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const unsigned* b, const unsigned* e,
+               unsigned long long* head, int hi_key, cudaStream_t st) {
+  const long long bytes = (4ll * hi_key * 3 * (long long)sizeof(T) + 127) & ~127ll;
+  if (bytes > 200 * 1024 || hi_key >= kMaxKey) {  // does not fit shared memory: warp-per-pair over global memory
+    launch_group<T, 32>(ctx, a, list, b, e, head, st);
+    return OGJK_OK;
+  }
+  static long long configured = 0;  // per instantiation
+  if (bytes > configured) {
+    CU(cudaFuncSetAttribute(gjk_cta_kernel<T, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    configured = bytes;
+  }
+  long long per_sm = (220ll * 1024) / (bytes + 1024);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 2048 / (32 * WARPS)) per_sm = 2048 / (32 * WARPS);
+  long long blocks = a.npairs, cap = (long long)ctx->sm_count * per_sm;
+  gjk_cta_kernel<T, WARPS><<<(unsigned)(blocks < cap ? blocks : cap), 32 * WARPS, (size_t)bytes, st>>>(a, list, b, e, head);
+  return OGJK_OK;
+}
+
 template <typename T, int G>
 void launch_assist(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const unsigned* b, const unsigned* e,
                    unsigned long long* head, cudaStream_t st) {
@@ -318,6 +340,10 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
       case 8: launch_group<T, 8>(ctx, a, sorted, b, e, head, st); break;
       case 16: launch_group<T, 16>(ctx, a, sorted, b, e, head, st); break;
       case 32: launch_group<T, 32>(ctx, a, sorted, b, e, head, st); break;
+      case 502: rc = launch_cta<T, 2>(ctx, a, sorted, b, e, head, hi, st); break;
+      case 504: rc = launch_cta<T, 4>(ctx, a, sorted, b, e, head, hi, st); break;
+      case 508: rc = launch_cta<T, 8>(ctx, a, sorted, b, e, head, hi, st); break;
+      case 516: rc = launch_cta<T, 16>(ctx, a, sorted, b, e, head, hi, st); break;
       case 302: launch_assist<T, 2>(ctx, a, sorted, b, e, head, st); break;
       case 304: launch_assist<T, 4>(ctx, a, sorted, b, e, head, st); break;
       case 308: launch_assist<T, 8>(ctx, a, sorted, b, e, head, st); break;
@@ -999,12 +1025,16 @@ int ogjk_ctx_set_classes(ogjk_ctx* c, int n, const int* hi_keys, const int* lane
   int prev = 0;
   for (int i = 0; i < n; ++i) {
     const int l = lanes[i];
-    // 100 + G: shared-memory staged flavour; 200 + G: persistent-lane flavour (200 = register-resident);
-    // 300 + G: scan-assist flavour (G = 2, 4, 8, 16 lanes of state per pair, 32-lane scans)
-    const int gl = l >= 300 ? l - 300 : (l >= 200 ? l - 200 : (l >= 100 ? l - 100 : l));
-    if (l >= 300 && !(gl == 2 || gl == 4 || gl == 8 || gl == 16)) return fail(OGJK_ERR_ARG, "scan-assist needs 302/304/308/316%s");
-    if (!((gl == 0 && (l == 0 || l == 200)) || gl == 1 || gl == 2 || gl == 4 || gl == 8 || gl == 16 || gl == 32))
-      return fail(OGJK_ERR_ARG, "lanes must be 0, a power of two <= 32, or 100/200/300 + that%s");
+    // plain G or 0; 100 + G: shared-memory staged; 200 + G: persistent lanes (200 = register-resident);
+    // 300 + G: scan-assist (G = 2, 4, 8, 16); 500 + W: CTA-per-pair with W = 2, 4, 8, 16 warps
+    const int fam = l / 100, gl = l % 100;
+    const bool pow2 = gl == 1 || gl == 2 || gl == 4 || gl == 8 || gl == 16 || gl == 32;
+    bool ok = false;
+    if (fam == 0) ok = gl == 0 || pow2;
+    else if (fam == 1) ok = pow2;
+    else if (fam == 2) ok = gl == 0 || pow2;
+    else if (fam == 3 || fam == 5) ok = gl == 2 || gl == 4 || gl == 8 || gl == 16;
+    if (l < 0 || !ok) return fail(OGJK_ERR_ARG, "unknown kernel flavour in class table%s");
     if (gl == 0 && hi_keys[i] > kSmallKeyMax) return fail(OGJK_ERR_ARG, "register-resident class is limited to key <= 4%s");
     if (hi_keys[i] <= prev) return fail(OGJK_ERR_ARG, "class keys must increase%s");
     prev = hi_keys[i];

@@ -559,6 +559,140 @@ gjk_assist_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* 
   }
 }
 
+// CTA-per-pair kernel for large hulls (hundreds to thousands of vertices per pair).
+// ncu on the warp-per-pair kernel (1000-vertex hulls): L1 hit 13 %, ~10 TB/s of L2->SM
+// traffic -- every GJK iteration re-reads both hulls from L2, and that re-read, not HBM,
+// bounds the kernel.  Here a CTA of WARPS warps owns one pair at a time:
+//   * both store blocks are copied ONCE into shared memory with cp.async (all 16-byte
+//     chunks in flight together), so HBM/L2 see each hull once per query;
+//   * every support scan reads shared memory, thread t taking chunks t, t+NT, ...; a
+//     warp butterfly and a WARPS-entry shared-memory pass produce the (value, lowest
+//     index) winner -- the same rule as everywhere else, so results are unchanged;
+//   * warp 0 alone runs the termination tests, the sub-solver and the witnesses while
+//     the other warps wait at the barrier (no issue slots spent on redundant copies),
+//     then publishes the next search direction.
+// Shared memory per CTA is the class's largest pair, so 227 KB / slot pairs are resident
+// per SM with WARPS warps each.
+template <typename T, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS)
+gjk_cta_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* __restrict__ seg_begin,
+               const unsigned* __restrict__ seg_end, unsigned long long* __restrict__ head) {
+  extern __shared__ uint4 ogjk_stage[];
+  constexpr int NT = 32 * WARPS;
+  constexpr int CV = Chunk<T>::kVerts;
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ long long s_slot;
+  __shared__ T s_dir[3], s_carry[2];
+  __shared__ int s_done;
+  __shared__ T s_val[2][WARPS];
+  __shared__ int s_idx[2][WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long begin = seg_begin ? (long long)*seg_begin : 0;
+  const long long end = seg_end ? (long long)*seg_end : a.npairs;
+  for (;;) {
+    if (tid == 0) s_slot = begin + (long long)atomicAdd(head, 1ull);
+    __syncthreads();
+    const long long slot = s_slot;
+    if (slot >= end) break;
+    const long long p = list ? (long long)list[slot] : slot;
+    const long long h1 = a.idx1 ? (long long)a.idx1[p] : p;
+    const long long h2 = a.idx2 ? (long long)a.idx2[p] : p;
+    const int n1 = a.s1.cnt[h1], n2 = a.s2.cnt[h2];
+    const int np1 = pad4(n1), np2 = pad4(n2);
+    const uint4* s1v = reinterpret_cast<const uint4*>(a.s1.data + a.s1.boff[h1]);
+    const uint4* s2v = reinterpret_cast<const uint4*>(a.s2.data + a.s2.boff[h2]);
+    const int c1 = 3 * np1 * (int)sizeof(T) / 16, c2 = 3 * np2 * (int)sizeof(T) / 16;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(ogjk_stage);
+    for (int c = tid; c < c1; c += NT)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * c), "l"(s1v + c) : "memory");
+    for (int c = tid; c < c2; c += NT)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * (c1 + c)), "l"(s2v + c) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const T* blk1 = reinterpret_cast<const T*>(ogjk_stage);
+    const T* blk2 = reinterpret_cast<const T*>(ogjk_stage + c1);
+    const GroupBody<T, 32> own1{blk1, n1, np1, lane, FULL}, own2{blk2, n2, np2, lane, FULL};
+    GjkState<T> st;
+    if (warp == 0) {
+      gjk_init(own1, own2, st);
+      if (lane == 0) {
+        s_dir[0] = st.v.x; s_dir[1] = st.v.y; s_dir[2] = st.v.z;
+        s_carry[0] = dot3(st.sa.x, st.sa.y, st.sa.z, -st.v.x, -st.v.y, -st.v.z);
+        s_carry[1] = dot3(st.sb.x, st.sb.y, st.sb.z, st.v.x, st.v.y, st.v.z);
+        s_done = 0;
+      }
+    }
+    for (;;) {
+      __syncthreads();  // direction / carried dots / done flag of this round are visible
+      if (s_done) break;
+      const T vx = s_dir[0], vy = s_dir[1], vz = s_dir[2];
+      T best1 = s_carry[0], best2 = s_carry[1];
+      int bt1 = 0x7fffffff, bt2 = 0x7fffffff;
+      // thread-strided scans of both blocks out of shared memory
+      for (int c = tid; c < np1 / CV; c += NT) {
+        Chunk<T> X, Y, Z;
+        X.load(blk1 + CV * c); Y.load(blk1 + np1 + CV * c); Z.load(blk1 + 2 * np1 + CV * c);
+#pragma unroll
+        for (int t = 0; t < CV; ++t) {
+          const T sc = dot3(X.v[t], Y.v[t], Z.v[t], -vx, -vy, -vz);
+          if (sc > best1) { best1 = sc; bt1 = CV * c + t; }
+        }
+      }
+      for (int c = tid; c < np2 / CV; c += NT) {
+        Chunk<T> X, Y, Z;
+        X.load(blk2 + CV * c); Y.load(blk2 + np2 + CV * c); Z.load(blk2 + 2 * np2 + CV * c);
+#pragma unroll
+        for (int t = 0; t < CV; ++t) {
+          const T sc = dot3(X.v[t], Y.v[t], Z.v[t], vx, vy, vz);
+          if (sc > best2) { best2 = sc; bt2 = CV * c + t; }
+        }
+      }
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) {
+        const T o1 = __shfl_xor_sync(FULL, best1, m);
+        const int i1 = __shfl_xor_sync(FULL, bt1, m);
+        const T o2 = __shfl_xor_sync(FULL, best2, m);
+        const int i2 = __shfl_xor_sync(FULL, bt2, m);
+        if (o1 > best1 || (o1 == best1 && i1 < bt1)) { best1 = o1; bt1 = i1; }
+        if (o2 > best2 || (o2 == best2 && i2 < bt2)) { best2 = o2; bt2 = i2; }
+      }
+      if (lane == 0) { s_val[0][warp] = best1; s_idx[0][warp] = bt1; s_val[1][warp] = best2; s_idx[1][warp] = bt2; }
+      __syncthreads();
+      if (warp == 0) {
+        T b1 = s_carry[0], b2 = s_carry[1];
+        int i1 = 0x7fffffff, i2 = 0x7fffffff;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+          const T v1 = s_val[0][w]; const int k1 = s_idx[0][w];
+          const T v2 = s_val[1][w]; const int k2 = s_idx[1][w];
+          if (v1 > b1 || (v1 == b1 && k1 < i1)) { b1 = v1; i1 = k1; }
+          if (v2 > b2 || (v2 == b2 && k2 < i2)) { b2 = v2; i2 = k2; }
+        }
+        st.k++;
+        if (i1 != 0x7fffffff) { st.sa = own1.vertex(i1); st.ia = i1; }
+        if (i2 != 0x7fffffff) { st.sb = own2.vertex(i2); st.ib = i2; }
+        const bool done = gjk_step_tail(st);
+        if (done) {
+          V3<T> w1, w2;
+          Splx<T> s = st.s;
+          gjk_witnesses(own1, own2, s, w1, w2);
+          if (lane == 0) {
+            a.distances[p] = sqrt(nrm2(st.v.x, st.v.y, st.v.z));
+            if (a.simplices) store_simplex(a.simplices + p, s, w1, w2);
+          }
+        }
+        if (lane == 0) {
+          s_dir[0] = st.v.x; s_dir[1] = st.v.y; s_dir[2] = st.v.z;
+          s_carry[0] = dot3(st.sa.x, st.sa.y, st.sa.z, -st.v.x, -st.v.y, -st.v.z);
+          s_carry[1] = dot3(st.sb.x, st.sb.y, st.sb.z, st.v.x, st.v.y, st.v.z);
+          s_done = done ? 1 : 0;
+        }
+      }
+    }
+  }
+}
+
 // Thread-per-pair kernel for pairs whose two polytopes have at most 8 vertices
 // each (boxes, tetrahedra, the reference's tiny random bodies): all 16 vertices
 // live in registers for the whole query, so global memory is touched once per

@@ -124,6 +124,8 @@ def test_scheduler_classes_do_not_change_results(eng, prec, dt):
     tables += [[(4, 200), (24, 202), (64, 204), (2048, 232)]]
     # scan-assist flavours (300 + lanes of state per pair; scans use the whole warp)
     tables += [[(2048, 300 + g)] for g in (2, 4, 8, 16)]
+    # CTA-per-pair flavours (500 + warps), shared memory sized by the class bound
+    tables += [[(80, 500 + g), (2048, 32)] for g in (2, 4, 8, 16)]
     try:
         for t in tables:
             eng.set_classes(t)

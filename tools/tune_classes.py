@@ -35,8 +35,10 @@ for name in names:
     small_ok = int(w.cnt.max()) <= 8
     kmax = int((((w.cnt[w.pa] + 3) // 4 * 4 + (w.cnt[w.pb] + 3) // 4 * 4) // 4).max())
     variants = ([0, 200] if small_ok else []) + [1, 2, 4, 8, 16, 32]
-    if kmax > 40:
+    if os.environ.get("TUNE_ASSIST") and kmax > 40:
         variants += [302, 304, 308, 316]
+    if 40 < kmax < 2048:
+        variants += [502, 504, 508, 516]
     if os.environ.get("TUNE_PERSIST"):
         variants += [201, 202, 204, 208, 232]
     if os.environ.get("TUNE_STAGED"):
@@ -51,6 +53,8 @@ for name in names:
             table = [(12, gg), (20, gg), (kmax, gg), (2048, gg - 100)]
         elif g == 200:
             table = [(4, 200), (2048, 201)]
+        elif g > 500:
+            table = [(kmax, g), (2048, 32)]  # CTA-per-pair: shared memory sized for the largest pair
         elif g > 200:
             table = [(2048, g)]  # persistent-lane (2xx) and scan-assist (3xx) flavours
         elif g >= 100:
