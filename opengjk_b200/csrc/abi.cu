@@ -214,7 +214,8 @@ template <typename T> StoreView<T> view_of(const ogjk_store_* s) {
 template <typename T, int G>
 void launch_group(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const unsigned* b, const unsigned* e,
                   unsigned long long* head, cudaStream_t st) {
-  static const int cap_per_sm = getenv("OGJK_GRID_CAP") ? atoi(getenv("OGJK_GRID_CAP")) : 16;  // tuning hook
+  const char* cap_env = getenv("OGJK_GRID_CAP");  // tuning hook (blocks per SM), read per call
+  const int cap_per_sm = cap_env ? atoi(cap_env) : 16;
   long long blocks = (a.npairs * G + 127) / 128, cap = (long long)ctx->sm_count * cap_per_sm;
   gjk_group_kernel<T, G><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, list, b, e, head);
 }
@@ -1203,5 +1204,16 @@ int ogjk_test_subalgorithm_f32(ogjk_ctx* ctx, ogjk_simplex_f32* simplex, float* 
 int ogjk_test_subalgorithm_f64(ogjk_ctx* ctx, ogjk_simplex_f64* simplex, double* v) {
   return test_subalgorithm<double, ogjk_simplex_f64>(ctx, simplex, v);
 }
+
+#ifdef OGJK_PHASE_CLOCKS
+// Debug build only: copy out and clear the phase-cycle counters (tools/phase_clocks.py).
+OGJK_API int ogjk_debug_phase_clocks(unsigned long long* out8) {
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyFromSymbol(out8, ogjk::g_phase_clk, 8 * sizeof(unsigned long long)));
+  unsigned long long zero[8] = {0};
+  CU(cudaMemcpyToSymbol(ogjk::g_phase_clk, zero, sizeof(zero)));
+  return OGJK_OK;
+}
+#endif
 
 }  // extern "C"

@@ -91,6 +91,19 @@ OGJK_DI void support_both(const Body& b1, const Body& b2, const V3<T>& v, V3<T>&
   b2.support(v.x, v.y, v.z, sb, ib);
 }
 
+#ifdef OGJK_PHASE_CLOCKS
+// Debug build only (tools/phase_clocks.py): SM cycles summed over lane 0 of every
+// group.  [0] support scans, [1] rest of the step, [2] witness phase, [3] steps, [4] pairs.
+__device__ unsigned long long g_phase_clk[8];
+#define OGJK_CLK_BEGIN() const long long _clk0 = clock64()
+#define OGJK_CLK_MARK(name) const long long name = clock64()
+#define OGJK_CLK_ADD(slot, cyc) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase_clk[slot], (unsigned long long)(cyc)); } while (0)
+#else
+#define OGJK_CLK_BEGIN()
+#define OGJK_CLK_MARK(name)
+#define OGJK_CLK_ADD(slot, cyc)
+#endif
+
 // ---- one GJK query (openGJK.c:941-1046), split into init / step / finish --------
 template <typename T> struct GjkState {
   V3<T> v, sa, sb;   // search direction, carried support points of body 1 / body 2
@@ -136,7 +149,16 @@ template <typename T, typename Body>
 OGJK_DI bool gjk_step(const Body& b1, const Body& b2, GjkState<T>& st) {
   const T er = eps_rel<T>(), ea = eps_abs<T>();
   st.k++;
+  OGJK_CLK_BEGIN();
   support_both(b1, b2, st.v, st.sa, st.ia, st.sb, st.ib);
+  OGJK_CLK_MARK(_clk1);
+  OGJK_CLK_ADD(0, _clk1 - _clk0);
+  OGJK_CLK_ADD(3, 1);
+#ifdef OGJK_PHASE_CLOCKS
+  const bool done = gjk_step_tail(st);
+  OGJK_CLK_ADD(1, clock64() - _clk1);
+  return done;
+#else
   const V3<T> w = sub(st.sa, st.sb);
   const T vv = nrm2(st.v.x, st.v.y, st.v.z);
   const T gap = vv - dot3(st.v, w);
@@ -146,6 +168,7 @@ OGJK_DI bool gjk_step(const Body& b1, const Body& b2, GjkState<T>& st) {
   st.wmax2 = update_wmax(st.s, st.wmax2);
   if (nrm2(st.v.x, st.v.y, st.v.z) <= (ea * ea * st.wmax2)) return true;  // :1032
   return st.s.n == 4 || st.k == kMaxIter;
+#endif
 }
 
 // compute_witnesses (:921-939): may reduce `s`; blends the source vertices.
@@ -187,7 +210,10 @@ OGJK_DI T gjk_query(const Body& b1, const Body& b2, Splx<T>& s, V3<T>& wit1, V3<
   gjk_init(b1, b2, st);
   while (!gjk_step(b1, b2, st)) {}
   s = st.s;
+  OGJK_CLK_BEGIN();
   gjk_witnesses(b1, b2, s, wit1, wit2);
+  OGJK_CLK_ADD(2, clock64() - _clk0);
+  OGJK_CLK_ADD(4, 1);
   return sqrt(nrm2(st.v.x, st.v.y, st.v.z));  // :1045 (IEEE sqrt; double rounding via double is innocuous)
 }
 
