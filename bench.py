@@ -243,6 +243,10 @@ def main():
     if os.environ.get("OGJK_CLASSES"):  # e.g. "4:0,24:4,64:8,192:16,2048:32"
         CLASS_TABLE[:] = [tuple(int(x) for x in c.split(":")) for c in os.environ["OGJK_CLASSES"].split(",")]
     eng.set_classes(CLASS_TABLE)
+    if os.environ.get("OGJK_ACCEL_MIN"):  # tuning hook: 0 = no cluster tables in the resident store
+        eng.set_accel_min(int(os.environ["OGJK_ACCEL_MIN"]))
+    if os.environ.get("OGJK_TABLE_LANES"):
+        eng.set_table_lanes(int(os.environ["OGJK_TABLE_LANES"]))
     hbm_peak, peak_src = peaks()
 
     def measure(name, pairs, steps, warmup, with_cpu):
@@ -348,7 +352,12 @@ def main():
             kname = f"epa_warp_kernel<{tname}>"
         else:
             lanes = CLASS_TABLE[dom][1]
-            kname = f"gjk_small_kernel<{tname}>" if lanes == 0 else f"gjk_group_kernel<{tname},{lanes}>"
+            lo_key = CLASS_TABLE[dom - 1][0] if dom else 0
+            amin = int(os.environ.get("OGJK_ACCEL_MIN", 256))
+            if store.table_bytes > 0 and 1 <= lanes <= 32 and 4 * (lo_key + 1) >= 2 * amin:  # as run_store_batch routes
+                kname = f"gjk_table_kernel<{tname},{int(os.environ.get('OGJK_TABLE_LANES', 32))}>"
+            else:
+                kname = f"gjk_small_kernel<{tname}>" if lanes == 0 else f"gjk_group_kernel<{tname},{lanes}>"
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "traffic": traffic_for(name), "kernel": kname, "kernel_ms": class_avg[dom],
                     "step_phases_ms": {"sort": float(np.mean(sort_ms)), "classes": class_avg},

@@ -121,9 +121,20 @@ OGJK_API int ogjk_store_create_f32(ogjk_ctx* ctx, int64_t npoly, int64_t nverts,
                                    const int* cnt, int on_device, void* stream, ogjk_store** out);
 OGJK_API int ogjk_store_create_f64(ogjk_ctx* ctx, int64_t npoly, int64_t nverts, const double* coords, const int64_t* off,
                                    const int* cnt, int on_device, void* stream, ogjk_store** out);
+/* Stores created AFTER this call give every polytope with at least `min_vertices`
+ * vertices (default 256; clamped to >= 64; at most 16384 vertices; 0 = off) a cluster
+ * table: a spatially clustered copy of its vertices with per-cluster bounding boxes that
+ * lets the warp-per-pair kernel skip clusters which provably cannot change the support
+ * point.  Results are bit-identical with and without the table. */
+OGJK_API int ogjk_ctx_set_accel_min(ogjk_ctx* ctx, int min_vertices);
+/* Lanes cooperating on one pair in the kernel that uses the cluster tables: 8, 16 or
+ * 32 (default).  A tuning knob; results do not depend on it. */
+OGJK_API int ogjk_ctx_set_table_lanes(ogjk_ctx* ctx, int lanes);
 OGJK_API void ogjk_store_destroy(ogjk_store* store);
 OGJK_API int64_t ogjk_store_bytes(const ogjk_store* store);
 OGJK_API int64_t ogjk_store_num_polytopes(const ogjk_store* store);
+/* Bytes of cluster tables the store carries (0: none, queries use the plain scans). */
+OGJK_API int64_t ogjk_store_table_bytes(const ogjk_store* store);
 OGJK_API int ogjk_store_gjk_f32(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_store* s2, const int* idx2,
                                 int64_t npairs, ogjk_simplex_f32* simplices, float* distances, void* stream);
 OGJK_API int ogjk_store_gjk_f64(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_store* s2, const int* idx2,

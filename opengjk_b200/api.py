@@ -159,6 +159,14 @@ class Engine:
                  _p(cnt), cnt.shape[0], coords.shape[0], _p(pb), _p(simp), _p(dist), _p(w1), _p(w2), _p(nr)))
         return {"distances": dist, "simplices": simp, "witness1": w1, "witness2": w2, "normals": nr}
 
+    def set_accel_min(self, min_vertices):
+        """Vertex count from which stores created afterwards get a cluster table (0 = off)."""
+        check(_lib.lib().ogjk_ctx_set_accel_min(self._h, int(min_vertices)))
+
+    def set_table_lanes(self, lanes):
+        """Lanes per pair (8, 16, 32) of the kernel that uses the cluster tables."""
+        check(_lib.lib().ogjk_ctx_set_table_lanes(self._h, int(lanes)))
+
     def set_pipeline_chunks(self, chunks):
         check(_lib.lib().ogjk_ctx_set_pipeline_chunks(self._h, int(chunks)))
 
@@ -195,6 +203,11 @@ class Store:
     @property
     def nbytes(self):
         return int(_lib.lib().ogjk_store_bytes(self._h))
+
+    @property
+    def table_bytes(self):
+        """Bytes of cluster tables (large polytopes' pruned-scan accelerator); 0 = none."""
+        return int(_lib.lib().ogjk_store_table_bytes(self._h))
 
     @property
     def num_polytopes(self):

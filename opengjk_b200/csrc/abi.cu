@@ -76,6 +76,12 @@ struct ogjk_store_ {
   long long nverts = 0;       // true vertices
   long long capacity = 0;     // elements allocated in `data`
   DevBuf data, boff, cnt, scan_tmp;
+  DevBuf accel, aoff;            // cluster tables of the large polytopes (store.cuh); empty when none
+  int accel_min = 0x7fffffff;    // smallest vertex count that has a table
+  long long accel_elems = 0;
+  void release_all() {
+    data.release(); boff.release(); cnt.release(); scan_tmp.release(); accel.release(); aoff.release();
+  }
 };
 
 struct ogjk_ctx_ {
@@ -89,6 +95,8 @@ struct ogjk_ctx_ {
   int nclasses = 4;
   int class_hi[kMaxClasses] = {4, 32, 128, 2048, 2048, 2048};
   int class_lanes[kMaxClasses] = {0, 2, 8, 32, 32, 32};
+  int accel_min = 256;  // persistent stores: cluster tables for polytopes with >= this many vertices (0 = none)
+  int table_lanes = 32;  // lanes per pair of the pruned-scan kernel (8, 16 or 32; B200 sweep: profiles/r1_lanes_sweep.txt)
   bool timing = false;
   cudaEvent_t ev[2 * kPhases] = {};
   int timed_mask = 0;
@@ -168,9 +176,9 @@ int store_build(ogjk_ctx* ctx, ogjk_store_* s, long long npoly, long long nverts
   CU(cudaMemcpyAsync(s->cnt.p, cnt, (size_t)npoly * sizeof(int), cudaMemcpyDeviceToDevice, st));
   auto* sums = static_cast<long long*>(s->scan_tmp.p);
   auto* boff = static_cast<long long*>(s->boff.p);
-  scan_block_sums_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(cnt, npoly, sums);
+  scan_block_sums_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(cnt, npoly, sums, BlockElems{});
   scan_spine_kernel<<<1, 1024, 0, st>>>(sums, nblocks, sums + nblocks);
-  scan_finish_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(cnt, npoly, sums, boff);
+  scan_finish_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(cnt, npoly, sums, boff, BlockElems{});
   long long elems = 3 * (nverts + 3 * npoly);
   if (exact) {
     long long total = 0;
@@ -206,9 +214,67 @@ int store_pack_range(ogjk_ctx* ctx, ogjk_store_* s, long long lo, long long hi, 
   return OGJK_OK;
 }
 
+// Cluster tables for the polytopes of a packed store with at least ctx->accel_min vertices
+// (persistent stores only: the build sorts every such polytope once, queries then prune
+// their support scans, see store.cuh).  Synchronises `st`.
+template <typename T>
+int store_build_accel(ogjk_ctx* ctx, ogjk_store_* s, cudaStream_t st) {
+  s->accel_min = 0x7fffffff;
+  s->accel_elems = 0;
+  const int amin = ctx->accel_min;
+  if (amin <= 0) return OGJK_OK;
+  const long long npoly = s->npoly;
+  const long long nblocks = (npoly + kScanBlock - 1) / kScanBlock;
+  int rc;
+  if ((rc = s->aoff.reserve((size_t)npoly * sizeof(long long)))) return rc;
+  if ((rc = s->scan_tmp.reserve((size_t)(nblocks + 2) * sizeof(long long)))) return rc;
+  const int* cnt = static_cast<const int*>(s->cnt.p);
+  auto* sums = static_cast<long long*>(s->scan_tmp.p);
+  auto* aoff = static_cast<long long*>(s->aoff.p);
+  int* d_max = reinterpret_cast<int*>(sums + nblocks + 1);
+  CU(cudaMemsetAsync(d_max, 0, sizeof(long long), st));
+  const AccelElems<T> f{amin};
+  scan_block_sums_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(cnt, npoly, sums, f);
+  scan_spine_kernel<<<1, 1024, 0, st>>>(sums, nblocks, sums + nblocks);
+  scan_finish_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(cnt, npoly, sums, aoff, f);
+  {
+    long long mb = (npoly + 255) / 256, cap = (long long)ctx->sm_count * 8;
+    max_count_kernel<<<(unsigned)(mb < cap ? mb : cap), 256, 0, st>>>(cnt, npoly, amin, d_max);
+  }
+  long long tail[2] = {0, 0};  // total elements, largest eligible vertex count
+  CU(cudaMemcpyAsync(tail, sums + nblocks, sizeof(tail), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  ctx->launches += 4;
+  const long long total = tail[0];
+  const int maxn = (int)(tail[1] & 0xffffffffll);
+  if (total <= 0 || maxn <= 0) return OGJK_OK;
+  if ((rc = s->accel.reserve((size_t)total * sizeof(T)))) return rc;
+  int pcap = 32;
+  while (pcap < maxn) pcap <<= 1;
+  const size_t smem = (size_t)pcap * sizeof(unsigned long long);
+  CU(cudaFuncSetAttribute(accel_build_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  StoreView<T> v{static_cast<const T*>(s->data.p), static_cast<const long long*>(s->boff.p), cnt};
+  v.accel = static_cast<const T*>(s->accel.p);
+  v.aoff = aoff;
+  v.accel_min = amin;
+  const long long cap = (long long)ctx->sm_count * (pcap <= 4096 ? 2 : 1);
+  accel_build_kernel<T><<<(unsigned)(npoly < cap ? npoly : cap), 1024, smem, st>>>(v, npoly, static_cast<T*>(s->accel.p), pcap);
+  ctx->launches += 1;
+  CU(cudaGetLastError());
+  s->accel_min = amin;
+  s->accel_elems = total;
+  return OGJK_OK;
+}
+
 template <typename T> StoreView<T> view_of(const ogjk_store_* s) {
-  return StoreView<T>{static_cast<const T*>(s->data.p), static_cast<const long long*>(s->boff.p),
-                      static_cast<const int*>(s->cnt.p)};
+  StoreView<T> v{static_cast<const T*>(s->data.p), static_cast<const long long*>(s->boff.p),
+                 static_cast<const int*>(s->cnt.p)};
+  if (s->accel_elems > 0) {
+    v.accel = static_cast<const T*>(s->accel.p);
+    v.aoff = static_cast<const long long*>(s->aoff.p);
+    v.accel_min = s->accel_min;
+  }
+  return v;
 }
 
 template <typename T, int G>
@@ -218,6 +284,13 @@ void launch_group(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const u
   const int cap_per_sm = cap_env ? atoi(cap_env) : 16;
   long long blocks = (a.npairs * G + 127) / 128, cap = (long long)ctx->sm_count * cap_per_sm;
   gjk_group_kernel<T, G><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, list, b, e, head);
+}
+
+template <typename T, int G>
+void launch_table(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const unsigned* b, const unsigned* e,
+                  unsigned long long* head, cudaStream_t st) {
+  long long blocks = (a.npairs * G + 127) / 128, cap = (long long)ctx->sm_count * 16;
+  gjk_table_kernel<T, G><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, list, b, e, head);
 }
 
 // Shared-memory slot size for a staged class: room for 4*hi_key vertices, rounded so
@@ -330,7 +403,16 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
     const unsigned* e = start + bin_upper(lo);
     unsigned long long* head = counters + c;
     mark(ctx, st, 2 + c, 0);
-    switch (ctx->class_lanes[c]) {
+    int lanes = ctx->class_lanes[c];
+    // A group-kernel class in which every pair is large enough for both bodies to carry a
+    // cluster table (persistent stores) runs the pruned-scan kernel instead.
+    if (a.s1.accel && a.s2.accel && lanes >= 1 && lanes <= 32 &&
+        4ll * (lo + 1) >= (long long)a.s1.accel_min + a.s2.accel_min)
+      lanes = 1000 + ctx->table_lanes;
+    switch (lanes) {
+      case 1008: launch_table<T, 8>(ctx, a, sorted, b, e, head, st); break;
+      case 1016: launch_table<T, 16>(ctx, a, sorted, b, e, head, st); break;
+      case 1032: launch_table<T, 32>(ctx, a, sorted, b, e, head, st); break;
       case 0: {
         long long blocks = (a.npairs + 127) / 128, cap = (long long)ctx->sm_count * 16;
         gjk_small_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, sorted, b, e, head);
@@ -772,6 +854,7 @@ int store_create(ogjk_ctx* ctx, int64_t npoly, int64_t nverts, const T* coords, 
   int rc = OGJK_OK;
   if (on_device) {
     rc = store_build<T>(ctx, s, npoly, nverts, coords, off, cnt, true, st);
+    if (!rc) rc = store_build_accel<T>(ctx, s, st);
   } else {
     DevBuf dc, doff, dcnt;
     if (!(rc = dc.reserve((size_t)nverts * 3 * sizeof(T))) && !(rc = doff.reserve((size_t)npoly * sizeof(int64_t))) &&
@@ -785,13 +868,14 @@ int store_create(ogjk_ctx* ctx, int64_t npoly, int64_t nverts, const T* coords, 
       } else {
         rc = store_build<T>(ctx, s, npoly, nverts, static_cast<const T*>(dc.p), static_cast<const int64_t*>(doff.p),
                             static_cast<const int*>(dcnt.p), true, st);
+        if (!rc) rc = store_build_accel<T>(ctx, s, st);
         if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(OGJK_ERR_CUDA, "store pack failed%s");
       }
     }
     dc.release(); doff.release(); dcnt.release();
   }
   if (rc) {
-    s->data.release(); s->boff.release(); s->cnt.release(); s->scan_tmp.release();
+    s->release_all();
     delete s;
     return rc;
   }
@@ -839,9 +923,9 @@ int store_build_structs(ogjk_ctx* ctx, ogjk_store_* s, long long npoly, const vo
   auto* boff = static_cast<long long*>(s->boff.p);
   long long eb = (npoly + 255) / 256, cap = (long long)ctx->sm_count * 32;
   extract_counts_kernel<T><<<(unsigned)(eb < cap ? eb : cap), 256, 0, st>>>(bd, npoly, cnt);
-  scan_block_sums_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(cnt, npoly, sums);
+  scan_block_sums_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(cnt, npoly, sums, BlockElems{});
   scan_spine_kernel<<<1, 1024, 0, st>>>(sums, nblocks, sums + nblocks);
-  scan_finish_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(cnt, npoly, sums, boff);
+  scan_finish_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(cnt, npoly, sums, boff, BlockElems{});
   long long total = 0;
   CU(cudaMemcpyAsync(&total, sums + nblocks, sizeof(long long), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
@@ -1083,13 +1167,14 @@ OGJK_STORE_IMPL(f64, double, ogjk_simplex_f64)
 void ogjk_store_destroy(ogjk_store* s) {
   if (!s) return;
   cudaSetDevice(s->device);
-  s->data.release(); s->boff.release(); s->cnt.release(); s->scan_tmp.release();
+  s->release_all();
   delete s;
 }
 int64_t ogjk_store_bytes(const ogjk_store* s) {
-  return s ? (int64_t)(s->capacity * s->prec + s->npoly * 12) : 0;
+  return s ? (int64_t)((s->capacity + s->accel_elems) * s->prec + s->npoly * (s->accel_elems ? 20 : 12)) : 0;
 }
 int64_t ogjk_store_num_polytopes(const ogjk_store* s) { return s ? s->npoly : 0; }
+int64_t ogjk_store_table_bytes(const ogjk_store* s) { return s ? (int64_t)(s->accel_elems * s->prec) : 0; }
 
 int ogjk_gjk_host_f32(ogjk_ctx* ctx, int64_t npairs, const float* coords1, const int64_t* off1, const int* cnt1,
                       int64_t npoly1, int64_t nverts1, const int* idx1, const float* coords2, const int64_t* off2,
@@ -1190,6 +1275,18 @@ int ogjk_epa_device_structs_f64(ogjk_ctx* ctx, int64_t n, const ogjk_polytope_f6
                                 double* d_normals, void* stream) {
   return device_structs<double, ogjk_simplex_f64>(ctx, n, d_bd1, d_bd2, d_simplices, d_distances, d_w1, d_w2, d_normals,
                                                   false, true, stream);
+}
+
+int ogjk_ctx_set_accel_min(ogjk_ctx* c, int min_vertices) {
+  if (!c || min_vertices < 0) return fail(OGJK_ERR_ARG, "min_vertices must be >= 0%s");
+  c->accel_min = (min_vertices > 0 && min_vertices < 64) ? 64 : min_vertices;
+  return OGJK_OK;
+}
+
+int ogjk_ctx_set_table_lanes(ogjk_ctx* c, int lanes) {
+  if (!c || (lanes != 8 && lanes != 16 && lanes != 32)) return fail(OGJK_ERR_ARG, "table lanes must be 8, 16 or 32%s");
+  c->table_lanes = lanes;
+  return OGJK_OK;
 }
 
 int ogjk_ctx_set_pipeline_chunks(ogjk_ctx* c, int chunks) {

@@ -387,6 +387,234 @@ template <typename T, int G> struct GroupBody {
   }
 };
 
+// Warp-per-pair body with the store's cluster table (store.cuh, "cluster tables").
+// Polytopes without a table have acc == null.
+// ---- pruned support scans over the store's cluster tables (store.cuh) -------------
+// Vector loads of N consecutive elements (N * sizeof <= 32 bytes, naturally aligned).
+template <int N> OGJK_DI void load_vec(const float* p, float (&v)[N]) {
+  if constexpr (N == 4) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  else if constexpr (N == 2) { const float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; }
+  else { v[0] = p[0]; }
+}
+template <int N> OGJK_DI void load_vec(const double* p, double (&v)[N]) {
+  if constexpr (N == 4) {
+    const double2 t = *reinterpret_cast<const double2*>(p), u = *reinterpret_cast<const double2*>(p + 2);
+    v[0] = t.x; v[1] = t.y; v[2] = u.x; v[3] = u.y;
+  } else if constexpr (N == 2) { const double2 t = *reinterpret_cast<const double2*>(p); v[0] = t.x; v[1] = t.y; }
+  else { v[0] = p[0]; }
+}
+template <int N> OGJK_DI void load_vec(const int* p, int (&v)[N]) {
+  if constexpr (N == 4) { const int4 t = *reinterpret_cast<const int4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  else if constexpr (N == 2) { const int2 t = *reinterpret_cast<const int2*>(p); v[0] = t.x; v[1] = t.y; }
+  else { v[0] = p[0]; }
+}
+
+// Order-preserving key of a float / double (after -0 -> +0, so that equal values have equal
+// keys); group-wide max and "lowest index among the lanes holding the max" then run on the
+// redux unit instead of shuffle butterflies.  NaN keys sort above +inf / below -inf: a NaN
+// bound only disables pruning, and a lane's best value is never NaN unless every lane's is.
+OGJK_DI unsigned okey(float f) {
+  const unsigned u = __float_as_uint(f + 0.0f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+OGJK_DI float unkey(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+OGJK_DI unsigned long long okey(double f) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(f + 0.0);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+OGJK_DI double unkey(unsigned long long k) {
+  return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+OGJK_DI unsigned group_max_key(unsigned gm, unsigned k) { return __reduce_max_sync(gm, k); }
+OGJK_DI unsigned long long group_max_key(unsigned gm, unsigned long long k) {
+  const unsigned hi = (unsigned)(k >> 32);
+  const unsigned mh = __reduce_max_sync(gm, hi);
+  const unsigned ml = __reduce_max_sync(gm, hi == mh ? (unsigned)k : 0u);
+  return ((unsigned long long)mh << 32) | ml;
+}
+
+// G-lane body (G = 8, 16, 32) with the polytope's cluster table; acc == null when it has none.
+template <typename T, int G> struct AccelBody {
+  GroupBody<T, G> base;
+  const T* acc;
+  OGJK_DI V3<T> vertex(int i) const { return base.vertex(i); }
+};
+
+// One body's half of the fused, pruned support scan below.  A lane owns VPL = 32/G
+// consecutive clusters of every 32-cluster tile and VPL consecutive vertices of every
+// cluster record, so all its loads are single 4..32-byte vectors.
+template <typename T, int G> struct ScanSide {
+  static constexpr int VPL = 32 / G;
+  const T* acc; int nc, ncs;
+  T dx, dy, dz;
+  T bl, px, py, pz;  // this lane's best value and its vertex
+  int il;            // original index of that vertex (-1: still the carried point)
+  struct Hit { T sc[VPL], x[VPL], y[VPL], z[VPL]; int o[VPL]; };
+  OGJK_DI void open(const AccelBody<T, G>& b, T ex, T ey, T ez, const V3<T>& cur) {
+    acc = b.acc;
+    nc = (b.base.n + kAccelCluster - 1) / kAccelCluster;
+    ncs = accel_table_stride(nc);
+    dx = ex; dy = ey; dz = ez;
+    bl = dot3(cur.x, cur.y, cur.z, dx, dy, dz);
+    px = cur.x; py = cur.y; pz = cur.z;
+    il = -1;
+  }
+  // Upper bounds of this lane's clusters of tile t: the box corner picked by the signs of d,
+  // multiplied and summed in the order of dot3 (rounding is monotone, so each bound holds
+  // for the rounded dots of the cluster's vertices too).
+  OGJK_DI void bounds(int t, int g, T (&ub)[VPL]) const {
+    const int c0 = t * 32 + g * VPL;
+    T cx[VPL], cy[VPL], cz[VPL];
+    load_vec<VPL>(acc + (dx >= (T)0 ? 3 : 0) * ncs + c0, cx);
+    load_vec<VPL>(acc + (dy >= (T)0 ? 4 : 1) * ncs + c0, cy);
+    load_vec<VPL>(acc + (dz >= (T)0 ? 5 : 2) * ncs + c0, cz);
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) ub[j] = dot3(cx[j], cy[j], cz[j], dx, dy, dz);
+  }
+  OGJK_DI void fetch(int c, int g, Hit& h) const {
+    const T* r = acc + 6 * ncs + (long long)c * kAccelRecord<T> + g * VPL;
+    load_vec<VPL>(r, h.x);
+    load_vec<VPL>(r + kAccelCluster, h.y);
+    load_vec<VPL>(r + 2 * kAccelCluster, h.z);
+    load_vec<VPL>(reinterpret_cast<const int*>(r - g * VPL + 3 * kAccelCluster) + g * VPL, h.o);
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) h.sc[j] = dot3(h.x[j], h.y[j], h.z[j], dx, dy, dz);
+  }
+  OGJK_DI void take(const Hit& h, bool valid) {
+#pragma unroll
+    for (int j = 0; j < VPL; ++j)
+      if (valid && (h.sc[j] > bl || (h.sc[j] == bl && h.o[j] < il))) {
+        bl = h.sc[j]; il = h.o[j]; px = h.x[j]; py = h.y[j]; pz = h.z[j];
+      }
+  }
+  OGJK_DI T group_best(unsigned gm) const { return unkey(group_max_key(gm, okey(bl))); }
+};
+
+#ifndef OGJK_ACCEL_K
+#define OGJK_ACCEL_K 0  // clusters per body per trip; 0 = by G (1 for G = 8, else 2)
+#endif
+
+// Both support calls of one iteration for a G-lane query over two bodies with cluster
+// tables, run in lockstep so that the two bodies' memory round trips overlap:
+//   1. bounds of 32 clusters per body;
+//   2. the vertices of the cluster with the largest bound (first tile only);
+//   3. the clusters whose bound is not below the running maximum, a few per trip.
+// All loads of a step are unconditional (indices clamped, results masked) so that they are
+// issued back to back.  A skipped cluster cannot hold a vertex that beats or ties the
+// maximum, so the result is the full scan's: the largest dot if it strictly exceeds the
+// carried point's, lowest original index among equals.  The winner's coordinates travel by
+// shuffle.  Without two tables both bodies take the plain scan.
+template <typename T, int G>
+OGJK_DI void support_both(const AccelBody<T, G>& b1, const AccelBody<T, G>& b2, const V3<T>& v, V3<T>& sa, int& ia,
+                          V3<T>& sb, int& ib) {
+  if (!(b1.acc && b2.acc)) {
+    b1.base.support(-v.x, -v.y, -v.z, sa, ia);
+    b2.base.support(v.x, v.y, v.z, sb, ib);
+    return;
+  }
+  constexpr int VPL = 32 / G;
+  constexpr int K = OGJK_ACCEL_K ? OGJK_ACCEL_K : (G == 8 ? 1 : 2);
+  using Side = ScanSide<T, G>;
+  using Hit = typename Side::Hit;
+  const int g = b1.base.g;
+  const unsigned gm = b1.base.mask;
+  Side s[2];
+  s[0].open(b1, -v.x, -v.y, -v.z, sa);
+  s[1].open(b2, v.x, v.y, v.z, sb);
+  const int tiles = ((s[0].nc > s[1].nc ? s[0].nc : s[1].nc) + 31) >> 5;
+  for (int t = 0; t < tiles; ++t) {
+    T ub[2][VPL];
+    unsigned has[2];  // bit j: this lane's j-th cluster of the tile exists
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int tt = t * 32 < s[k].nc ? t : 0;  // a body with fewer tiles re-reads tile 0, masked off
+      s[k].bounds(tt, g, ub[k]);
+      has[k] = 0;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j)
+        if (tt == t && t * 32 + g * VPL + j < s[k].nc) has[k] |= 1u << j;
+    }
+    int top[2] = {-1, -1};
+    if (t == 0) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        auto mk = okey((T)-INFINITY);
+#pragma unroll
+        for (int j = 0; j < VPL; ++j)
+          if (((has[k] >> j) & 1u) && okey(ub[k][j]) > mk) mk = okey(ub[k][j]);
+        const auto m = group_max_key(gm, mk);
+        unsigned mine = 0xffffffffu;
+#pragma unroll
+        for (int j = VPL - 1; j >= 0; --j)
+          if (((has[k] >> j) & 1u) && okey(ub[k][j]) == m) mine = (unsigned)(g * VPL + j);
+        const unsigned first = __reduce_min_sync(gm, mine);
+        top[k] = first == 0xffffffffu ? 0 : (int)first;
+      }
+      Hit h[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) s[k].fetch(top[k], g, h[k]);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) s[k].take(h[k], true);
+    }
+    unsigned live[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const T wb = s[k].group_best(gm);
+      unsigned bits = 0;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j)
+        if (((has[k] >> j) & 1u) && !(ub[k][j] < wb)) bits |= 1u << (g * VPL + j);
+      live[k] = __reduce_or_sync(gm, bits);
+      if (top[k] >= 0) live[k] &= ~(1u << top[k]);
+    }
+    while (live[0] | live[1]) {
+      OGJK_CLK_ADD(5, __popc(live[0]) + __popc(live[1]));  // debug build: clusters still live at trip start
+      OGJK_CLK_ADD(6, 1);                                   // trips
+      int cl[2][K];
+      Hit h[2][K];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          cl[k][j] = live[k] ? t * 32 + __ffs(live[k]) - 1 : -1;
+          live[k] &= live[k] - 1;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) s[k].fetch(cl[k][j] < 0 ? 0 : cl[k][j], g, h[k][j]);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) s[k].take(h[k][j], cl[k][j] >= 0);
+      }
+      if (live[0] | live[1]) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const T wb = s[k].group_best(gm);
+          unsigned bits = 0;
+#pragma unroll
+          for (int j = 0; j < VPL; ++j)
+            if (!(ub[k][j] < wb)) bits |= 1u << (g * VPL + j);
+          live[k] &= __reduce_or_sync(gm, bits);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const auto key = okey(s[k].bl);
+    const bool cand = key == group_max_key(gm, key);
+    const unsigned fi = __reduce_min_sync(gm, cand ? (unsigned)s[k].il : 0xffffffffu);
+    if (fi == 0xffffffffu) continue;  // nothing beats the carried point
+    const int src = __ffs(__ballot_sync(gm, cand && (unsigned)s[k].il == fi)) - 1;
+    const V3<T> w{__shfl_sync(gm, s[k].px, src), __shfl_sync(gm, s[k].py, src), __shfl_sync(gm, s[k].pz, src)};
+    if (k == 0) { sa = w; ia = (int)fi; } else { sb = w; ib = (int)fi; }
+  }
+}
+
 // Segment [*seg_begin, *seg_end) of the size-sorted pair list (or the identity
 // list when `list` is null) is consumed through a device-side work queue, 32/G
 // pairs per grab.
@@ -395,6 +623,12 @@ template <typename T, int G> struct GroupBody {
 #endif
 #ifndef OGJK_LB_GROUP_F64
 #define OGJK_LB_GROUP_F64 4
+#endif
+#ifndef OGJK_LB_TABLE_F64  // table kernels: the fused two-body pruned scan needs the registers in fp64
+#define OGJK_LB_TABLE_F64 3
+#endif
+#ifndef OGJK_LB_TABLE_F32
+#define OGJK_LB_TABLE_F32 4
 #endif
 #ifndef OGJK_LB_SMALL_F32
 #define OGJK_LB_SMALL_F32 4
@@ -410,6 +644,7 @@ gjk_group_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* _
   const long long begin = seg_begin ? (long long)*seg_begin : 0;
   const long long end = seg_end ? (long long)*seg_end : a.npairs;
   for (;;) {
+    OGJK_CLK_MARK(_grab0);
     unsigned long long got = 0;
     if (lane == 0) got = atomicAdd(head, (unsigned long long)PER_WARP);
     got = __shfl_sync(0xffffffffu, got, 0);
@@ -430,6 +665,52 @@ gjk_group_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* _
         a.distances[p] = d;
         if (a.simplices) store_simplex(a.simplices + p, s, w1, w2);
       }
+#ifdef OGJK_PHASE_CLOCKS
+      OGJK_CLK_ADD(7, clock64() - _grab0);  // whole grab: queue, pair setup, query, stores
+#endif
+    }
+  }
+}
+
+// The group kernel for classes whose pairs (mostly) have cluster tables on both bodies
+// (persistent stores, large polytopes): same queue and outputs, pruned support scans.
+template <typename T, int G>
+__global__ void __launch_bounds__(128, (sizeof(T) == 8 ? OGJK_LB_TABLE_F64 : OGJK_LB_TABLE_F32))
+gjk_table_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* __restrict__ seg_begin,
+                 const unsigned* __restrict__ seg_end, unsigned long long* __restrict__ head) {
+  constexpr int PER_WARP = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int g = lane % G;
+  const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - g));
+  const long long begin = seg_begin ? (long long)*seg_begin : 0;
+  const long long end = seg_end ? (long long)*seg_end : a.npairs;
+  for (;;) {
+    OGJK_CLK_MARK(_grab0);
+    unsigned long long got = 0;
+    if (lane == 0) got = atomicAdd(head, (unsigned long long)PER_WARP);
+    got = __shfl_sync(0xffffffffu, got, 0);
+    const long long base = begin + (long long)got;
+    if (base >= end) break;
+    const long long slot = base + lane / G;
+    if (slot < end) {
+      const long long p = list ? (long long)list[slot] : slot;
+      const long long h1 = a.idx1 ? (long long)a.idx1[p] : p;
+      const long long h2 = a.idx2 ? (long long)a.idx2[p] : p;
+      const int n1 = a.s1.cnt[h1], n2 = a.s2.cnt[h2];
+      const bool t1 = a.s1.accel && n1 >= a.s1.accel_min && n1 <= kAccelMaxVerts;
+      const bool t2 = a.s2.accel && n2 >= a.s2.accel_min && n2 <= kAccelMaxVerts;
+      AccelBody<T, G> b1{{a.s1.data + a.s1.boff[h1], n1, pad4(n1), g, mask}, t1 ? a.s1.accel + a.s1.aoff[h1] : nullptr};
+      AccelBody<T, G> b2{{a.s2.data + a.s2.boff[h2], n2, pad4(n2), g, mask}, t2 ? a.s2.accel + a.s2.aoff[h2] : nullptr};
+      Splx<T> s;
+      V3<T> w1, w2;
+      const T d = gjk_query<T>(b1, b2, s, w1, w2);
+      if (g == 0) {
+        a.distances[p] = d;
+        if (a.simplices) store_simplex(a.simplices + p, s, w1, w2);
+      }
+#ifdef OGJK_PHASE_CLOCKS
+      OGJK_CLK_ADD(7, clock64() - _grab0);  // whole grab: queue, pair setup, query, stores
+#endif
     }
   }
 }

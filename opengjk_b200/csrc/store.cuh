@@ -28,16 +28,57 @@ template <typename T> struct StoreView {
   const T* data;           // packed blocks
   const long long* boff;   // element offset of each block (multiple of 4)
   const int* cnt;          // true vertex counts
+  // support-scan accelerator (persistent stores only; null when absent), see "cluster tables" below
+  const T* accel = nullptr;
+  const long long* aoff = nullptr;  // element offset of each polytope's accelerator block
+  int accel_min = 0x7fffffff;       // polytopes with accel_min <= n <= kAccelMaxVerts have one
 };
 
-// ---- exclusive scan of 3*pad4(cnt[h]) over polytopes (three small kernels) ----
+// ---- cluster tables: exact pruning of the support scan for large polytopes --------
+//   A polytope with many vertices gets, next to its block, a
+// copy of its vertices grouped into spatially compact clusters of 32 (k-d median
+// splits), the original index of every copied vertex, and each cluster's bounding box.
+// For a search direction d the box corner picked by the signs of d gives
+//   ub = (cx*dx + cy*dy) + cz*dz  >=  (x*dx + y*dy) + z*dz   for every vertex of the cluster,
+// and the inequality holds for the ROUNDED values too (same operation order, IEEE
+// rounding is monotone), so a cluster with ub < best cannot hold a vertex that beats or
+// ties `best` and skipping it leaves the scan result bit-identical.
+// Block layout in T elements, nc = ceil(n/32), ncs = nc rounded up to 32:
+//   lox[ncs] loy[ncs] loz[ncs] hix[ncs] hiy[ncs] hiz[ncs] | nc cluster records
+//   cluster record = x[32] y[32] z[32] | int orig[32]          (kAccelRecord<T> elements)
+// (slots past n in the last cluster repeat that cluster's first vertex; table entries
+// past nc are zero and never used).
+constexpr int kAccelCluster = 32;
+constexpr int kAccelMaxVerts = 16384;
+constexpr int kAccelMaxClusters = kAccelMaxVerts / kAccelCluster;
+template <typename T> constexpr int kAccelRecord = 3 * kAccelCluster + kAccelCluster * (int)sizeof(int) / (int)sizeof(T);
+
+__host__ __device__ __forceinline__ int accel_table_stride(int nc) { return (nc + 31) & ~31; }
+template <typename T> __host__ __device__ __forceinline__ long long accel_elems(int n) {
+  const int nc = (n + kAccelCluster - 1) / kAccelCluster;
+  return 6ll * accel_table_stride(nc) + (long long)nc * kAccelRecord<T>;
+}
+
+// Per-polytope element counts the three scan kernels below accumulate.
+struct BlockElems {
+  __device__ __forceinline__ long long operator()(int n) const { return 3ll * pad4(n); }
+};
+template <typename T> struct AccelElems {
+  int amin;
+  __device__ __forceinline__ long long operator()(int n) const {
+    return (n >= amin && n <= kAccelMaxVerts) ? accel_elems<T>(n) : 0;
+  }
+};
+
+// ---- exclusive scan of F(cnt[h]) over polytopes (three small kernels) ----
 constexpr int kScanBlock = 1024;
 
+template <typename F>
 __global__ void __launch_bounds__(kScanBlock)
-scan_block_sums_kernel(const int* __restrict__ cnt, long long n, long long* __restrict__ block_sums) {
+scan_block_sums_kernel(const int* __restrict__ cnt, long long n, long long* __restrict__ block_sums, F elems) {
   __shared__ long long warp_sums[32];
   const long long i = (long long)blockIdx.x * kScanBlock + threadIdx.x;
-  long long v = i < n ? 3ll * pad4(cnt[i]) : 0;
+  long long v = i < n ? elems(cnt[i]) : 0;
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
   if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = v;
@@ -88,12 +129,13 @@ scan_spine_kernel(long long* __restrict__ block_sums, long long nblocks, long lo
   if (threadIdx.x == 0) *total = carry;
 }
 
+template <typename F>
 __global__ void __launch_bounds__(kScanBlock)
 scan_finish_kernel(const int* __restrict__ cnt, long long n, const long long* __restrict__ block_sums,
-                   long long* __restrict__ boff) {
+                   long long* __restrict__ boff, F elems) {
   __shared__ long long warp_sums[32];
   const long long i = (long long)blockIdx.x * kScanBlock + threadIdx.x;
-  const long long x = i < n ? 3ll * pad4(cnt[i]) : 0;
+  const long long x = i < n ? elems(cnt[i]) : 0;
   long long v = x;
 #pragma unroll
   for (int m = 1; m < 32; m <<= 1) {
@@ -145,6 +187,145 @@ pack_kernel(const T* __restrict__ coords, const long long* __restrict__ off, con
       dst[np + i] = src[3 * j + 1];
       dst[2 * np + i] = src[3 * j + 2];
     }
+  }
+}
+
+// ---- cluster-table build (one CTA per large polytope, off the query path) ----------
+__device__ __forceinline__ unsigned accel_ord(float f) {  // order-preserving float -> unsigned
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float accel_unord(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+// Segment of clusters [c0, c1) that position `i` belongs to after `level` median splits
+// of the cluster range [0, nc): a segment of m clusters splits into ceil(m/2) and the rest.
+__device__ __forceinline__ void accel_segment(int i, int level, int nc, int& c0, int& c1) {
+  c0 = 0; c1 = nc;
+  const int c = i / kAccelCluster;
+  for (int l = 0; l < level && c1 - c0 > 1; ++l) {
+    const int mid = c0 + (c1 - c0 + 1) / 2;
+    if (c < mid) c1 = mid; else c0 = mid;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+max_count_kernel(const int* __restrict__ cnt, long long n, int amin, int* __restrict__ out) {
+  int m = 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int c = cnt[i];
+    if (c >= amin && c <= kAccelMaxVerts && c > m) m = c;
+  }
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, k));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+// Sort keys live in dynamic shared memory: (segment's first cluster) << 46 | ordered
+// fp32 coordinate along the segment's widest axis << 14 | vertex index; one bitonic sort
+// per k-d level.  The partition is a heuristic (any partition gives exact queries), so
+// the split coordinate is compared in fp32 even for fp64 stores.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+accel_build_kernel(StoreView<T> s, long long npoly, T* __restrict__ accel, int pcap) {
+  extern __shared__ unsigned long long accel_keys[];
+  __shared__ unsigned seg_lo[3][kAccelMaxClusters], seg_hi[3][kAccelMaxClusters];
+  __shared__ unsigned char seg_axis[kAccelMaxClusters];
+  const int tid = threadIdx.x, nth = blockDim.x;
+  for (long long h = blockIdx.x; h < npoly; h += gridDim.x) {
+    const int n = s.cnt[h];
+    if (n < s.accel_min || n > kAccelMaxVerts) continue;
+    const int np = pad4(n);
+    const T* blk = s.data + s.boff[h];
+    const int nc = (n + kAccelCluster - 1) / kAccelCluster;
+    int P = 32;
+    while (P < n) P <<= 1;
+    if (P > pcap) continue;  // cannot happen: pcap is sized from the largest eligible polytope
+    for (int i = tid; i < P; i += nth) accel_keys[i] = i < n ? (unsigned long long)i : ~0ull;
+    int levels = 0;
+    while ((1 << levels) < nc) ++levels;
+    __syncthreads();
+    for (int level = 0; level < levels; ++level) {
+      for (int c = tid; c < nc; c += nth) {
+        seg_lo[0][c] = seg_lo[1][c] = seg_lo[2][c] = 0xffffffffu;
+        seg_hi[0][c] = seg_hi[1][c] = seg_hi[2][c] = 0u;
+      }
+      __syncthreads();
+      for (int i = tid; i < n; i += nth) {
+        int c0, c1;
+        accel_segment(i, level, nc, c0, c1);
+        if (c1 - c0 > 1) {
+          const int v = (int)(accel_keys[i] & 0x3fffu);
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            const unsigned f = accel_ord((float)blk[a * np + v]);
+            atomicMin(&seg_lo[a][c0], f);
+            atomicMax(&seg_hi[a][c0], f);
+          }
+        }
+      }
+      __syncthreads();
+      for (int c = tid; c < nc; c += nth) {
+        int best = 0;
+        float ext = -1.0f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float e = accel_unord(seg_hi[a][c]) - accel_unord(seg_lo[a][c]);
+          if (e > ext) { ext = e; best = a; }  // NaN/empty extents leave axis 0
+        }
+        seg_axis[c] = (unsigned char)best;
+      }
+      __syncthreads();
+      for (int i = tid; i < n; i += nth) {
+        int c0, c1;
+        accel_segment(i, level, nc, c0, c1);
+        const unsigned long long v = accel_keys[i] & 0x3fffu;
+        const unsigned f = (c1 - c0 > 1) ? accel_ord((float)blk[seg_axis[c0] * np + (int)v]) : 0u;
+        accel_keys[i] = ((unsigned long long)c0 << 46) | ((unsigned long long)f << 14) | v;
+      }
+      __syncthreads();
+      for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int t = tid; t < (P >> 1); t += nth) {
+            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+            const int l = i | j;
+            const unsigned long long a = accel_keys[i], b = accel_keys[l];
+            if ((a > b) == ((i & k) == 0)) { accel_keys[i] = b; accel_keys[l] = a; }
+          }
+          __syncthreads();
+        }
+      }
+    }
+    // cluster records + original indices; a warp per cluster reduces its bounding box
+    const int ncs = accel_table_stride(nc);
+    T* out = accel + s.aoff[h];
+    T* rec = out + 6 * ncs;
+    for (int c = tid >> 5; c < ncs; c += nth >> 5) {
+      const int lane = tid & 31;
+      if (c >= nc) {  // table padding, never used by queries
+        if (lane < 6) out[lane * ncs + c] = (T)0;
+        continue;
+      }
+      const int i = c * kAccelCluster + lane;
+      const int v = (int)(accel_keys[i < n ? i : c * kAccelCluster] & 0x3fffu);
+      const T x = blk[v], y = blk[np + v], z = blk[2 * np + v];
+      T* r = rec + (long long)c * kAccelRecord<T>;
+      r[lane] = x; r[kAccelCluster + lane] = y; r[2 * kAccelCluster + lane] = z;
+      reinterpret_cast<int*>(r + 3 * kAccelCluster)[lane] = v;
+      T lx = x, ly = y, lz = z, hx = x, hy = y, hz = z;
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) {
+        lx = fmin(lx, __shfl_xor_sync(0xffffffffu, lx, m)); hx = fmax(hx, __shfl_xor_sync(0xffffffffu, hx, m));
+        ly = fmin(ly, __shfl_xor_sync(0xffffffffu, ly, m)); hy = fmax(hy, __shfl_xor_sync(0xffffffffu, hy, m));
+        lz = fmin(lz, __shfl_xor_sync(0xffffffffu, lz, m)); hz = fmax(hz, __shfl_xor_sync(0xffffffffu, hz, m));
+      }
+      if (lane == 0) {
+        out[c] = lx; out[ncs + c] = ly; out[2 * ncs + c] = lz;
+        out[3 * ncs + c] = hx; out[4 * ncs + c] = hy; out[5 * ncs + c] = hz;
+      }
+    }
+    __syncthreads();
   }
 }
 

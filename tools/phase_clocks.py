@@ -11,14 +11,18 @@ from opengjk_b200 import api, _lib
 eng = api.Engine(0)
 L = _lib.lib()
 dev = torch.device("cuda:0")
-CASES = (("hulls1k_f32", 32, 100000), ("hulls1k_f32", 132, 100000), ("hulls64_f64", 2, 500000), ("hulls64_f64", 104, 500000),
-         ("hulls64_f32", 2, 500000))
-for name, lanes, pairs in CASES:
+CASES = (("hulls1k_f32", 32, 100000, 0), ("hulls1k_f32", 32, 100000, 256), ("hulls1k10k_f32", 32, 20000, 0),
+         ("hulls1k10k_f32", 32, 20000, 256), ("hulls1k_f32", 132, 100000, 0), ("hulls64_f64", 2, 500000, 0),
+         ("hulls64_f64", 104, 500000, 0), ("hulls64_f32", 2, 500000, 0))
+if len(sys.argv) > 1:
+    CASES = tuple(c for c in CASES if c[0] in sys.argv[1:])
+for name, lanes, pairs, amin in CASES:
     desc, dt, maker, _ = WORKLOADS[name][:4]
     w = maker(pairs, 42)
     prec = "f64" if dt == np.float64 else "f32"
     sdt = api.SIMPLEX_F64 if prec == "f64" else api.SIMPLEX_F32
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    eng.set_accel_min(amin)
     store = eng.store_create(w.coords, w.off, w.cnt)
     pa, pb = t(w.pa), t(w.pb)
     simp = torch.empty(pairs * sdt.itemsize, dtype=torch.uint8, device=dev)
@@ -31,6 +35,6 @@ for name, lanes, pairs in CASES:
         eng.store_gjk(store, pa, store, pb, pairs, simp, dist, 0)
         L.ogjk_debug_phase_clocks(out)
         steps, npairs = max(out[3], 1), max(out[4], 1)
-        print(f"{name:12s} lanes={lanes:2d} blocks/SM cap={cap:>2s}: support {out[0]/steps:7.0f} cyc/iter  rest-of-step {out[1]/steps:7.0f} cyc/iter  "
-              f"witness {out[2]/npairs:6.0f} cyc/pair  iters/pair {steps/npairs:.2f}", flush=True)
+        print(f"{name:12s} lanes={lanes:2d} tables>={amin:<3d} blocks/SM cap={cap:>2s}: support {out[0]/steps:7.0f} cyc/iter  rest-of-step {out[1]/steps:7.0f} cyc/iter  "
+              f"witness {out[2]/npairs:6.0f} cyc/pair  iters/pair {steps/npairs:.2f}  table trips/iter {out[6]/steps:.2f} live-at-trip {out[5]/max(out[6],1):.1f}  whole grab {out[7]/max(out[4]*lanes/32 if lanes<=32 else out[4],1):.0f} cyc", flush=True)
     store.close()
