@@ -491,7 +491,7 @@ template <typename T, int G> struct ScanSide {
 };
 
 #ifndef OGJK_ACCEL_K
-#define OGJK_ACCEL_K 0  // clusters per body per trip; 0 = by G (1 for G = 8, else 2)
+#define OGJK_ACCEL_K 0  // clusters per body per trip; 0 = by G (1, 2, 3 for G = 8, 16, 32: tools/accel_sweep.sh)
 #endif
 
 // Both support calls of one iteration for a G-lane query over two bodies with cluster
@@ -513,7 +513,7 @@ OGJK_DI void support_both(const AccelBody<T, G>& b1, const AccelBody<T, G>& b2, 
     return;
   }
   constexpr int VPL = 32 / G;
-  constexpr int K = OGJK_ACCEL_K ? OGJK_ACCEL_K : (G == 8 ? 1 : 2);
+  constexpr int K = OGJK_ACCEL_K ? OGJK_ACCEL_K : (G == 8 ? 1 : G == 16 ? 2 : 3);
   using Side = ScanSide<T, G>;
   using Hit = typename Side::Hit;
   const int g = b1.base.g;

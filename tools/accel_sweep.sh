@@ -10,7 +10,7 @@ j=json.loads(sys.stdin.read()); print('$1', '$w', '%.1f Mpairs/s' % (j['value']/
 }
 for cfg in "$@"; do
   set -- $cfg
-  make -B -s -C opengjk_b200/csrc EXTRA="-DOGJK_ACCEL_K=$1 -DOGJK_LB_WARP_F32=$2 $3" 2>&1 | grep -i error
-  grep -A2 "gjk_group_kernelIfLi32" opengjk_b200/csrc/ptxas.log | grep -E "registers|spill" | tr '\n' ' '; echo
+  make -B -s -C opengjk_b200/csrc EXTRA="-DOGJK_ACCEL_K=$1 -DOGJK_LB_TABLE_F32=$2 $3" 2>&1 | grep -i error
+  grep -A2 "gjk_table_kernelIfLi32" opengjk_b200/csrc/ptxas.log | grep -E "registers|spill" | tr '\n' ' '; echo
   run "K=$1 lb=$2 $3"
 done
