@@ -70,3 +70,12 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in text and "gjk_oracle" not in text and "oracle/" not in text, f
+
+
+def test_tensor_front_door_rejects_host_tensors():
+    """opengjk_b200.torch_api is device-only: host tensors are refused before any engine call."""
+    import pytest
+    import torch
+    from opengjk_b200 import torch_api
+    with pytest.raises(ValueError, match="CUDA tensors required"):
+        torch_api.compute_minimum_distance(torch.zeros(2, 4, 3), torch.zeros(2, 4, 3))
