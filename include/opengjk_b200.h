@@ -140,6 +140,32 @@ OGJK_API int ogjk_store_gjk_f32(ogjk_ctx* ctx, const ogjk_store* s1, const int* 
 OGJK_API int ogjk_store_gjk_f64(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_store* s2, const int* idx2,
                                 int64_t npairs, ogjk_simplex_f64* simplices, double* distances, void* stream);
 
+/* ---- broad-phase-adjacent pair production (device pointers, asynchronous on `stream`) ----
+ * The caller step just before the indexed entries (gkCollisionPair lists,
+ * gpu/include/openGJK_GPU.h:89-92, 331-366).  Output lists are deterministic: culling keeps
+ * the candidates' order, the all-pairs list is sorted by (i, j).
+ *
+ * ogjk_store_aabbs_*: d_boxes[6*h .. 6*h+5] = {min x, min y, min z, max x, max y, max z} of
+ *   polytope h of the store.
+ * ogjk_pairs_cull_*: of the `ncand` candidates (d_idx1[p] into boxes1, d_idx2[p] into boxes2;
+ *   indices are not range-checked) keep those not separated by more than `margin` on any axis
+ *   (loA - hiB > margin or loB - hiA > margin culls; NaN never culls).  *d_count (device) receives
+ *   the number kept; at most `capacity` of them are written to d_out1 / d_out2, which can be
+ *   passed as idx1 / idx2 to ogjk_store_gjk_*.
+ * ogjk_pairs_all_*: the same test over every i < j of one pool (warp per row, O(n^2) box tests). */
+OGJK_API int ogjk_store_aabbs_f32(ogjk_ctx* ctx, const ogjk_store* store, float* d_boxes, void* stream);
+OGJK_API int ogjk_store_aabbs_f64(ogjk_ctx* ctx, const ogjk_store* store, double* d_boxes, void* stream);
+OGJK_API int ogjk_pairs_cull_f32(ogjk_ctx* ctx, const float* d_boxes1, const float* d_boxes2, int64_t ncand,
+                                 const int* d_idx1, const int* d_idx2, float margin, int64_t capacity, int* d_out1,
+                                 int* d_out2, int64_t* d_count, void* stream);
+OGJK_API int ogjk_pairs_cull_f64(ogjk_ctx* ctx, const double* d_boxes1, const double* d_boxes2, int64_t ncand,
+                                 const int* d_idx1, const int* d_idx2, double margin, int64_t capacity, int* d_out1,
+                                 int* d_out2, int64_t* d_count, void* stream);
+OGJK_API int ogjk_pairs_all_f32(ogjk_ctx* ctx, const float* d_boxes, int64_t npoly, float margin, int64_t capacity,
+                                int* d_out1, int* d_out2, int64_t* d_count, void* stream);
+OGJK_API int ogjk_pairs_all_f64(ogjk_ctx* ctx, const double* d_boxes, int64_t npoly, double margin, int64_t capacity,
+                                int* d_out1, int* d_out2, int64_t* d_count, void* stream);
+
 /* Number of chunks (0..16, default 8) the un-indexed host-buffer entry points cut a
  * batch into so that H2D, kernels and D2H overlap; 0 or 1 = one shot. */
 OGJK_API int ogjk_ctx_set_pipeline_chunks(ogjk_ctx* ctx, int chunks);

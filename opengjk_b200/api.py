@@ -159,6 +159,20 @@ class Engine:
                  _p(cnt), cnt.shape[0], coords.shape[0], _p(pb), _p(simp), _p(dist), _p(w1), _p(w2), _p(nr)))
         return {"distances": dist, "simplices": simp, "witness1": w1, "witness2": w2, "normals": nr}
 
+    # -- broad-phase-adjacent pair production (device pointers; include/opengjk_b200.h) --------
+    def store_aabbs(self, store, boxes, stream=0):
+        """boxes: device buffer of 6*num_polytopes values, filled with {min xyz, max xyz} per polytope."""
+        check(getattr(_lib.lib(), f"ogjk_store_aabbs_{store.prec}")(self._h, store._h, _p(boxes), C.c_void_p(int(stream))))
+
+    def pairs_cull(self, prec, boxes1, boxes2, ncand, idx1, idx2, margin, capacity, out1, out2, count, stream=0):
+        check(getattr(_lib.lib(), f"ogjk_pairs_cull_{prec}")(self._h, _p(boxes1), _p(boxes2), int(ncand), _p(idx1), _p(idx2),
+                                                            float(margin), int(capacity), _p(out1), _p(out2), _p(count),
+                                                            C.c_void_p(int(stream))))
+
+    def pairs_all(self, prec, boxes, npoly, margin, capacity, out1, out2, count, stream=0):
+        check(getattr(_lib.lib(), f"ogjk_pairs_all_{prec}")(self._h, _p(boxes), int(npoly), float(margin), int(capacity),
+                                                           _p(out1), _p(out2), _p(count), C.c_void_p(int(stream))))
+
     def set_accel_min(self, min_vertices):
         """Vertex count from which stores created afterwards get a cluster table (0 = off)."""
         check(_lib.lib().ogjk_ctx_set_accel_min(self._h, int(min_vertices)))

@@ -17,6 +17,7 @@
 #include "../../include/opengjk_b200.h"
 #include "gjk_kernels.cuh"
 #include "epa_kernels.cuh"
+#include "broadphase.cuh"
 
 namespace {
 
@@ -108,6 +109,7 @@ struct ogjk_ctx_ {
   DevBuf sort_tmp;                    // hist | start | cursor (u32 each, kMaxKey+2)
   DevBuf sorted_list;                 // pair ids, size-sorted
   DevBuf epa_list;                    // pair ids that need EPA (distance <= eps)
+  DevBuf bp_tmp;                      // broad phase: block sums / row counts
   DevBuf d_w1, d_w2, d_nrm;           // EPA outputs of the host-buffer paths
   DevBuf small_list, large_list;      // raw modes
   ogjk_store_ scratch1, scratch2;     // raw device arrays are repacked into these
@@ -883,6 +885,64 @@ int store_create(ogjk_ctx* ctx, int64_t npoly, int64_t nverts, const T* coords, 
   return OGJK_OK;
 }
 
+template <typename T>
+int store_aabbs(ogjk_ctx* ctx, const ogjk_store* s, T* d_boxes, void* stream) {
+  if (!ctx || !s || !d_boxes) return fail(OGJK_ERR_ARG, "NULL argument%s");
+  if (s->prec != (int)sizeof(T)) return fail(OGJK_ERR_ARG, "store precision mismatch%s");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long blocks = (s->npoly * 8 + 255) / 256, cap = (long long)ctx->sm_count * 32;
+  aabb_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(view_of<T>(s), s->npoly, d_boxes);
+  ctx->launches += 1;
+  CU(cudaGetLastError());
+  return OGJK_OK;
+}
+
+template <typename T>
+int pairs_cull(ogjk_ctx* ctx, const T* box1, const T* box2, int64_t n, const int* idx1, const int* idx2, T margin,
+               int64_t capacity, int* out1, int* out2, int64_t* d_count, void* stream) {
+  if (!ctx || !box1 || !box2 || !d_count || n < 0 || capacity < 0) return fail(OGJK_ERR_ARG, "bad argument%s");
+  if (n && (!idx1 || !idx2)) return fail(OGJK_ERR_ARG, "NULL candidate list%s");
+  if (capacity && (!out1 || !out2)) return fail(OGJK_ERR_ARG, "NULL output list%s");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n == 0) { CU(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st)); return OGJK_OK; }
+  const long long per_block = (long long)kCullBlock * kCullItems;
+  const long long nblocks = (n + per_block - 1) / per_block;
+  int rc = ctx->bp_tmp.reserve((size_t)nblocks * sizeof(long long));
+  if (rc) return rc;
+  auto* sums = static_cast<long long*>(ctx->bp_tmp.p);
+  cull_count_kernel<T><<<(unsigned)nblocks, kCullBlock, 0, st>>>(box1, box2, idx1, idx2, n, margin, sums);
+  scan_spine_kernel<<<1, 1024, 0, st>>>(sums, nblocks, reinterpret_cast<long long*>(d_count));
+  cull_scatter_kernel<T><<<(unsigned)nblocks, kCullBlock, 0, st>>>(box1, box2, idx1, idx2, n, margin, sums, capacity, out1,
+                                                                   out2);
+  ctx->launches += 3;
+  CU(cudaGetLastError());
+  return OGJK_OK;
+}
+
+template <typename T>
+int pairs_all(ogjk_ctx* ctx, const T* box, int64_t n, T margin, int64_t capacity, int* out1, int* out2, int64_t* d_count,
+              void* stream) {
+  if (!ctx || !box || !d_count || n < 0 || capacity < 0) return fail(OGJK_ERR_ARG, "bad argument%s");
+  if (n > 0x7fffffffll) return fail(OGJK_ERR_ARG, "more than 2^31-1 polytopes%s");
+  if (capacity && (!out1 || !out2)) return fail(OGJK_ERR_ARG, "NULL output list%s");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n < 2) { CU(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st)); return OGJK_OK; }
+  int rc = ctx->bp_tmp.reserve((size_t)n * sizeof(long long));
+  if (rc) return rc;
+  auto* rows = static_cast<long long*>(ctx->bp_tmp.p);
+  long long blocks = (n * 32 + 255) / 256, cap = (long long)ctx->sm_count * 8;
+  const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+  allpairs_kernel<T, false><<<grid, 256, 0, st>>>(box, n, margin, rows, nullptr, 0, nullptr, nullptr);
+  scan_spine_kernel<<<1, 1024, 0, st>>>(rows, n, reinterpret_cast<long long*>(d_count));
+  allpairs_kernel<T, true><<<grid, 256, 0, st>>>(box, n, margin, nullptr, rows, capacity, out1, out2);
+  ctx->launches += 3;
+  CU(cudaGetLastError());
+  return OGJK_OK;
+}
+
 template <typename T, typename S>
 int store_gjk(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_store* s2, const int* idx2, int64_t npairs,
               S* simplices, T* distances, void* stream) {
@@ -1065,7 +1125,7 @@ void ogjk_ctx_destroy(ogjk_ctx* c) {
   cudaDeviceSynchronize();
   ogjk_store_* ss[] = {&c->scratch1, &c->scratch2};
   for (ogjk_store_* q : ss) { q->data.release(); q->boff.release(); q->cnt.release(); q->scan_tmp.release(); }
-  c->sort_tmp.release(); c->sorted_list.release(); c->epa_list.release();
+  c->sort_tmp.release(); c->sorted_list.release(); c->epa_list.release(); c->bp_tmp.release();
   c->d_w1.release(); c->d_w2.release(); c->d_nrm.release();
   DevBuf* bufs[] = {&c->counters, &c->small_list, &c->large_list, &c->d_coords1, &c->d_coords2, &c->d_off1, &c->d_off2,
                     &c->d_cnt1,   &c->d_cnt2,     &c->d_idx1,     &c->d_idx2,    &c->d_simp,    &c->d_dist};
@@ -1276,6 +1336,24 @@ int ogjk_epa_device_structs_f64(ogjk_ctx* ctx, int64_t n, const ogjk_polytope_f6
   return device_structs<double, ogjk_simplex_f64>(ctx, n, d_bd1, d_bd2, d_simplices, d_distances, d_w1, d_w2, d_normals,
                                                   false, true, stream);
 }
+
+// ---- broad-phase-adjacent pair production (broadphase.cuh) -------------------------------
+#define OGJK_BROADPHASE_IMPL(SFX, T)                                                                                    \
+  int ogjk_store_aabbs_##SFX(ogjk_ctx* ctx, const ogjk_store* s, T* d_boxes, void* stream) {                            \
+    return store_aabbs<T>(ctx, s, d_boxes, stream);                                                                    \
+  }                                                                                                                    \
+  int ogjk_pairs_cull_##SFX(ogjk_ctx* ctx, const T* d_boxes1, const T* d_boxes2, int64_t ncand, const int* d_idx1,      \
+                            const int* d_idx2, T margin, int64_t capacity, int* d_out1, int* d_out2, int64_t* d_count, \
+                            void* stream) {                                                                            \
+    return pairs_cull<T>(ctx, d_boxes1, d_boxes2, ncand, d_idx1, d_idx2, margin, capacity, d_out1, d_out2, d_count,    \
+                         stream);                                                                                      \
+  }                                                                                                                    \
+  int ogjk_pairs_all_##SFX(ogjk_ctx* ctx, const T* d_boxes, int64_t npoly, T margin, int64_t capacity, int* d_out1,     \
+                           int* d_out2, int64_t* d_count, void* stream) {                                              \
+    return pairs_all<T>(ctx, d_boxes, npoly, margin, capacity, d_out1, d_out2, d_count, stream);                       \
+  }
+OGJK_BROADPHASE_IMPL(f32, float)
+OGJK_BROADPHASE_IMPL(f64, double)
 
 int ogjk_ctx_set_accel_min(ogjk_ctx* c, int min_vertices) {
   if (!c || min_vertices < 0) return fail(OGJK_ERR_ARG, "min_vertices must be >= 0%s");

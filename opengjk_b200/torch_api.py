@@ -157,5 +157,45 @@ class TensorStore:
         out.update({"witnesses1": w1, "witnesses2": w2, "contact_normals": nr, "penetration_depth": -dist.clamp(max=0)})
         return out
 
+    # -- broad phase: boxes, candidate culling, all-pairs (ogjk_store_aabbs_* / ogjk_pairs_*) ----
+    def aabbs(self):
+        """(P, 6) tensor {min xyz, max xyz} of every body of the pool."""
+        torch = _torch()
+        boxes = torch.empty((self.store.num_polytopes, 6), dtype=self.dtype, device=self.device)
+        self.engine.store_aabbs(self.store, boxes, torch.cuda.current_stream(self.device).cuda_stream)
+        return boxes
+
+    def _prec(self):
+        return "f64" if self.dtype == _torch().float64 else "f32"
+
+    def cull(self, pairs, margin=0.0, boxes=None):
+        """Candidates (N, 2) -> the (M, 2) sub-list, order kept, whose boxes are within `margin` on every
+        axis (a necessary condition for distance <= margin).  Reads back one integer (M)."""
+        torch = _torch()
+        boxes = self.aabbs() if boxes is None else boxes
+        pa, pb = _pairs(pairs, self.device)
+        n = int(pa.numel())
+        out = torch.empty((2, max(n, 1)), dtype=torch.int32, device=self.device)
+        count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.engine.pairs_cull(self._prec(), boxes, boxes, n, pa, pb, margin, n, out[0], out[1], count,
+                               torch.cuda.current_stream(self.device).cuda_stream)
+        m = int(count.item())
+        return out[:, :m].t().contiguous()
+
+    def candidate_pairs(self, margin=0.0, capacity=None, boxes=None):
+        """All (i < j) whose boxes are within `margin`, sorted by (i, j), as an (M, 2) int32 tensor."""
+        torch = _torch()
+        boxes = self.aabbs() if boxes is None else boxes
+        P = self.store.num_polytopes
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        if capacity is None:  # counting pass first (the list is produced by a second call)
+            self.engine.pairs_all(self._prec(), boxes, P, margin, 0, None, None, count, st)
+            capacity = int(count.item())
+        out = torch.empty((2, max(capacity, 1)), dtype=torch.int32, device=self.device)
+        self.engine.pairs_all(self._prec(), boxes, P, margin, capacity, out[0], out[1], count, st)
+        m = min(int(count.item()), capacity)
+        return out[:, :m].t().contiguous()
+
     def close(self):
         self.store.close()
