@@ -96,41 +96,42 @@ epa_prepass_kernel(EpaArgs<T> a, int* __restrict__ list, unsigned long long* __r
   }
 }
 
-// Warp-cooperative first-index argmax from -1e10 (:1735-1825).
+// The reference reduces per-lane partial results with a __shfl_down tree (offsets 16..1,
+// strict comparisons, gpu/opengjk_gpu.cu:1780-1801 and :2582-2593).  Lanes own ascending
+// index chunks, but on an exact tie BETWEEN lanes the survivor is whatever that tree leaves
+// in lane 0 -- not always the lowest index -- and overlapping boxes tie all the time.  The
+// same partition and the same tree are used here, so ties resolve exactly as in the
+// reference (the CPU checker emulates the tree lane for lane).
 template <typename T>
-OGJK_DI int epa_support_one(const T* blk, int np, T dx, T dy, T dz, int lane) {
-  constexpr int CV = Chunk<T>::kVerts;
+OGJK_DI int epa_support_one(const T* blk, int n, int np, int ppt, T dx, T dy, T dz, int lane) {
   T best = -epa_big<T>();
-  int bi = 0x7fffffff;
-  const int nchunks = np / CV;
-  for (int c = lane; c < nchunks; c += 32) {
-    Chunk<T> X, Y, Z;
-    X.load(blk + CV * c); Y.load(blk + np + CV * c); Z.load(blk + 2 * np + CV * c);
-#pragma unroll
-    for (int t = 0; t < CV; ++t) {
-      const T sc = dot3(X.v[t], Y.v[t], Z.v[t], dx, dy, dz);
-      if (sc > best) { best = sc; bi = CV * c + t; }
-    }
+  int bi = -1;
+  const int start = lane * ppt;
+  for (int i = start; i < n && i < start + ppt; ++i) {  // :1754-1764 (lane l scans [l*ppt, (l+1)*ppt))
+    const T sc = dot3(blk[i], blk[np + i], blk[2 * np + i], dx, dy, dz);
+    if (sc > best) { best = sc; bi = i; }
   }
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) {
-    const T ob = __shfl_xor_sync(0xffffffffu, best, m);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
-    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    const T ob = __shfl_down_sync(0xffffffffu, best, m);
+    const int oi = __shfl_down_sync(0xffffffffu, bi, m);
+    if (ob > best) { best = ob; bi = oi; }
   }
-  return bi == 0x7fffffff ? 0 : bi;
+  bi = __shfl_sync(0xffffffffu, bi, 0);
+  return bi < 0 ? 0 : bi;
 }
 
 template <typename T> struct EpaBody {
-  const T* blk; int np;
+  const T* blk; int n; int np;
   OGJK_DI V3<T> vertex(int i) const { return V3<T>{blk[i], blk[np + i], blk[2 * np + i]}; }
 };
 
 // Minkowski-difference support point along dir: body1 along +dir, body2 along -dir.
 template <typename T>
 OGJK_DI MV<T> epa_support(const EpaBody<T>& b1, const EpaBody<T>& b2, const V3<T>& dir, int lane) {
-  const int i1 = epa_support_one<T>(b1.blk, b1.np, dir.x, dir.y, dir.z, lane);
-  const int i2 = epa_support_one<T>(b2.blk, b2.np, -dir.x, -dir.y, -dir.z, lane);
+  const int ppt = ((b1.n > b2.n ? b1.n : b2.n) + 31) / 32;  // :1741-1743
+  const int i1 = epa_support_one<T>(b1.blk, b1.n, b1.np, ppt, dir.x, dir.y, dir.z, lane);
+  const int i2 = epa_support_one<T>(b2.blk, b2.n, b2.np, ppt, -dir.x, -dir.y, -dir.z, lane);
   const V3<T> p1 = b1.vertex(i1), p2 = b2.vertex(i2);
   return MV<T>{p1.x - p2.x, p1.y - p2.y, p1.z - p2.z, i1, i2};
 }
@@ -242,9 +243,34 @@ OGJK_DI void epa_face_pass(EpaShared<T>& S, int max_face, const V3<T>& centroid,
   __syncwarp();
 }
 
-// First index of the smallest non-negative face distance (:2570-2595).
+// Smallest non-negative face distance (:2568-2597): lane l takes faces [l*fpt, (l+1)*fpt),
+// first index inside the lane, then the reference's __shfl_down tree (see epa_support_one).
 template <typename T>
 OGJK_DI int epa_closest_face(const EpaShared<T>& S, int max_face, int lane, T& closest_distance) {
+  T bd = epa_big<T>();
+  int bi = -1;
+  const int fpt = (max_face + 31) / 32;
+  const int start = lane * fpt;
+  const int end = start + fpt < max_face ? start + fpt : max_face;
+  for (int f = start; f < end; ++f) {
+    if (!S.fvalid[f]) continue;
+    const T d = S.fd[f];
+    if (d >= (T)0 && d < bd) { bd = d; bi = f; }
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    const T od = __shfl_down_sync(0xffffffffu, bd, m);
+    const int oi = __shfl_down_sync(0xffffffffu, bi, m);
+    if (oi >= 0 && (bi < 0 || od < bd)) { bd = od; bi = oi; }
+  }
+  closest_distance = __shfl_sync(0xffffffffu, bd, 0);
+  return __shfl_sync(0xffffffffu, bi, 0);
+}
+
+// The iteration-cap exit (:2919-2970) is a lane-0 block in the reference: plain first index
+// of the smallest non-negative distance.
+template <typename T>
+OGJK_DI int epa_closest_face_first(const EpaShared<T>& S, int max_face, int lane, T& closest_distance) {
   T bd = epa_big<T>();
   int bi = 0x7fffffff;
   for (int f = lane; f < max_face; f += 32) {
@@ -282,8 +308,8 @@ epa_warp_kernel(EpaArgs<T> a, const int* __restrict__ list, const unsigned long 
     const long long p = list[slot];
     const long long h1 = a.idx1 ? (long long)a.idx1[p] : p;
     const long long h2 = a.idx2 ? (long long)a.idx2[p] : p;
-    const EpaBody<T> b1{a.s1.data + a.s1.boff[h1], pad4(a.s1.cnt[h1])};
-    const EpaBody<T> b2{a.s2.data + a.s2.boff[h2], pad4(a.s2.cnt[h2])};
+    const EpaBody<T> b1{a.s1.data + a.s1.boff[h1], a.s1.cnt[h1], pad4(a.s1.cnt[h1])};
+    const EpaBody<T> b2{a.s2.data + a.s2.boff[h2], a.s2.cnt[h2], pad4(a.s2.cnt[h2])};
 
     // private copy of the GJK simplex (the reference grows a local copy, :2049)
     const GkSimplex<T>* gs = a.simplices + p;
@@ -470,7 +496,7 @@ epa_warp_kernel(EpaArgs<T> a, const int* __restrict__ list, const unsigned long 
     if (iteration >= kEpaMaxIter) {  // :2919-2970
       epa_face_pass(S, max_face, centroid, lane);
       T closest_distance;
-      const int closest = epa_closest_face(S, max_face, lane, closest_distance);
+      const int closest = epa_closest_face_first(S, max_face, lane, closest_distance);
       if (closest >= 0) epa_finish_on_face(a, p, S, closest, closest_distance, b1, b2, lane);
     }
     __syncwarp();

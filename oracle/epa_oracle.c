@@ -5,20 +5,22 @@
  * Algorithm) for intersecting pairs.  The reference has no CPU EPA: its only
  * implementation is the warp-per-pair CUDA kernel compute_epa_kernel
  * (/root/reference/gpu/opengjk_gpu.cu:2022-2971 with helpers :1641-2018).
- * This file states that kernel's algorithm as one thread would run it: lane
- * partitions collapse to first-index argmax / argmin loops (the reference's
- * shfl_down reductions prefer the lower lane on ties, and lanes own ascending
- * index chunks), lane-0 blocks stay as written.
+ * This file states that kernel's algorithm as one thread would run it: lane-0
+ * blocks stay as written, and the two lane-partitioned reductions (support
+ * argmax, closest-face argmin) are emulated lane for lane, because their
+ * __shfl_down tree does not resolve exact ties to the lowest index.
  *
- * Parity status: UNPINNED against the reference.  No reference test pins EPA
- * numerically (gpu/examples/python/test_examples.py only checks loose ranges),
- * the reference kernel is compiled with FMA contraction so it is not
- * bit-reproducible on a CPU, and it has undefined behaviour on degenerate
- * faces (divergent __shfl_sync under a per-lane `valid` flag, :2554-2566).
- * What this oracle pins is OUR CUDA kernel (bit-for-bit: both evaluate the same
- * un-fused expressions in the same order); tests additionally compare against
- * the reference CUDA kernel run on the same GPU within a loose tolerance and
- * against analytic penetration depths of overlapping boxes/spheres.
+ * Parity status: PINNED against outputs of the reference itself.  No reference test pins
+ * EPA numerically (gpu/examples/python/test_examples.py only checks loose ranges) and there is
+ * no CPU EPA to link against, so the pin is tests/golden/epa_ref_cuda_{f32,f64}.npz: results of
+ * the reference's own CUDA compute_gjk_epa / compute_epa (gpu/opengjk_gpu.cu compiled unmodified
+ * on a B200 by tests/golden/make_epa_golden.py) on 7 000 seeded pairs per precision.  Against the
+ * -fmad=false build this restatement reproduces distance and both witnesses bit for bit (one
+ * fp64 pair of 8 000 differs in the last bits); against the default, FMA-contracting build the
+ * depth agrees within 1e-5 / 1e-10 on every pair (tests/test_epa_golden.py).  The reference
+ * fp32 kernel faults (CUDA error 700) on axis-aligned overlapping cubes; that workload is
+ * pinned in fp64 only.  Our CUDA kernel is compared with this file bit for bit
+ * (tests/test_gpu_epa.py) and with the same golden files directly.
  *
  * Choices where the reference leaves behaviour open (all documented in DESIGN.md):
  *   - a degenerate face (|n|^2 <= eps^2) becomes invalid for everybody (:1712-1716);
@@ -124,24 +126,92 @@ static void face_normal_distance(poly_t* p, int fi, const real* centroid) {
   }
 }
 
-/* :1735-1825: first-index argmax from -1e10 on each body. */
+/* The reference reduces per-lane partial results with a __shfl_down tree (offsets 16, 8, 4,
+ * 2, 1; an out-of-range source returns the caller's own value) and strict comparisons
+ * (:1780-1801, :2582-2593).  Lanes own ascending index chunks, but on an exact tie between
+ * lanes the survivor is whatever that tree leaves in lane 0, which is NOT always the lowest
+ * index (lane 0 may already hold lane 16's candidate when it meets lane 4's).  Overlapping
+ * boxes tie all the time, so the tree is emulated literally: every lane updates from a
+ * snapshot of the previous step. */
+#define LANES 32
+static int tree_argmax(real* val, int* idx) {
+  for (int off = LANES / 2; off > 0; off >>= 1) {
+    real nv[LANES];
+    int ni[LANES];
+    for (int l = 0; l < LANES; l++) {
+      const int src = l + off < LANES ? l + off : l;
+      nv[l] = val[l]; ni[l] = idx[l];
+      if (val[src] > val[l]) { nv[l] = val[src]; ni[l] = idx[src]; }
+    }
+    memcpy(val, nv, sizeof(nv));
+    memcpy(idx, ni, sizeof(ni));
+  }
+  return idx[0];
+}
+static int tree_closest_face(real* dist, int* face) {
+  for (int off = LANES / 2; off > 0; off >>= 1) {
+    real nd[LANES];
+    int nf[LANES];
+    for (int l = 0; l < LANES; l++) {
+      const int src = l + off < LANES ? l + off : l;
+      nd[l] = dist[l]; nf[l] = face[l];
+      if (face[src] >= 0 && (face[l] < 0 || dist[src] < dist[l])) { nd[l] = dist[src]; nf[l] = face[src]; }
+    }
+    memcpy(dist, nd, sizeof(nd));
+    memcpy(face, nf, sizeof(nf));
+  }
+  return face[0];
+}
+
+/* :1735-1825: lane l scans indices [l*ppt, (l+1)*ppt) of both bodies, ppt = ceil(max(n1,n2)/32),
+ * first-index argmax from -1e10 inside the lane, then the tree above. */
 static void support_epa(int n1, const real* c1, int n2, const real* c2, const real* dir, real* out, int* out_idx) {
-  real m1 = -BIG, m2 = -BIG;
-  int b1 = -1, b2 = -1;
-  for (int i = 0; i < n1; i++) {
-    const real s = dot3(c1 + 3 * (size_t)i, dir);
-    if (s > m1) { m1 = s; b1 = i; }
-  }
+  const int max_points = n1 > n2 ? n1 : n2;
+  const int ppt = (max_points + LANES - 1) / LANES;
   const real nd[3] = {-dir[0], -dir[1], -dir[2]};
-  for (int i = 0; i < n2; i++) {
-    const real s = dot3(c2 + 3 * (size_t)i, nd);
-    if (s > m2) { m2 = s; b2 = i; }
+  real m1[LANES], m2[LANES];
+  int i1[LANES], i2[LANES];
+  for (int l = 0; l < LANES; l++) {
+    const int start = l * ppt;
+    const int end = start + ppt < max_points ? start + ppt : max_points;
+    m1[l] = m2[l] = -BIG;
+    i1[l] = i2[l] = -1;
+    for (int i = start; i < n1 && i < end; i++) {
+      const real s = dot3(c1 + 3 * (size_t)i, dir);
+      if (s > m1[l]) { m1[l] = s; i1[l] = i; }
+    }
+    for (int i = start; i < n2 && i < end; i++) {
+      const real s = dot3(c2 + 3 * (size_t)i, nd);
+      if (s > m2[l]) { m2[l] = s; i2[l] = i; }
+    }
   }
+  int b1 = tree_argmax(m1, i1), b2 = tree_argmax(m2, i2);
   if (b1 < 0) b1 = 0; /* unreachable for finite inputs below 1e10 */
   if (b2 < 0) b2 = 0;
   for (int i = 0; i < 3; i++) out[i] = c1[3 * (size_t)b1 + i] - c2[3 * (size_t)b2 + i];
   out_idx[0] = b1;
   out_idx[1] = b2;
+}
+
+/* :2568-2597: lane l takes faces [l*fpt, (l+1)*fpt), fpt = ceil(max_face_index/32), first-index
+ * argmin of the non-negative distances inside the lane, then the tree above. */
+static int closest_face(const poly_t* p, real* closest_distance) {
+  const int fpt = (p->max_face_index + LANES - 1) / LANES;
+  real d[LANES];
+  int f[LANES];
+  for (int l = 0; l < LANES; l++) {
+    const int start = l * fpt;
+    const int end = start + fpt < p->max_face_index ? start + fpt : p->max_face_index;
+    d[l] = BIG;
+    f[l] = -1;
+    for (int i = start; i < end; ++i) {
+      if (!p->faces[i].valid) continue;
+      if (p->faces[i].distance >= 0.0f && p->faces[i].distance < d[l]) { d[l] = p->faces[i].distance; f[l] = i; }
+    }
+  }
+  const int best = tree_closest_face(d, f);
+  *closest_distance = d[0];
+  return best;
 }
 
 /* contact normal from witness1 to witness2 (:2061-2080 and the copies at :2146-2164 ...) */
@@ -386,15 +456,8 @@ int SUFFIX(oracle_epa)(int n1, const real* c1, int n2, const real* c2, const osi
     for (int i = 0; i < poly.max_face_index; ++i)
       if (poly.faces[i].valid) face_normal_distance(&poly, i, centroid);
 
-    int closest = -1;
     real closest_distance = BIG;
-    for (int i = 0; i < poly.max_face_index; ++i) {
-      if (!poly.faces[i].valid) continue;
-      if (poly.faces[i].distance >= 0.0f && poly.faces[i].distance < closest_distance) {
-        closest_distance = poly.faces[i].distance;
-        closest = i;
-      }
-    }
+    const int closest = closest_face(&poly, &closest_distance);
     if (closest < 0) break; /* :2605-2607 nothing written */
 
     const real d[3] = {poly.faces[closest].normal[0], poly.faces[closest].normal[1], poly.faces[closest].normal[2]};

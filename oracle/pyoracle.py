@@ -213,13 +213,14 @@ class ReferenceGPU(_Base):
     Used as a loose cross-check (it contracts FMAs, so it is not bit-comparable) and as
     the "reference GPU kernel" baseline."""
 
-    def __init__(self, prec="f32"):
-        super().__init__(prec, os.path.join(HERE, "_ref", f"libopenGJK_GPU_ref_{prec}.so"))
+    def __init__(self, prec="f32", variant=""):
+        """variant "" = the reference's default flags; "_nofma" = the same source with -fmad=false."""
+        super().__init__(prec, os.path.join(HERE, "_ref", f"libopenGJK_GPU_ref_{prec}{variant}.so"))
         self.pdt = polytope_dtype(prec)
 
     @staticmethod
-    def available(prec="f32"):
-        return os.path.exists(os.path.join(HERE, "_ref", f"libopenGJK_GPU_ref_{prec}.so"))
+    def available(prec="f32", variant=""):
+        return os.path.exists(os.path.join(HERE, "_ref", f"libopenGJK_GPU_ref_{prec}{variant}.so"))
 
     def _bodies(self, coords, off, cnt, which):
         arr = np.zeros(which.shape[0], dtype=self.pdt)
@@ -237,6 +238,17 @@ class ReferenceGPU(_Base):
         w2 = np.zeros((n, 3), dtype=self.npf)
         self.lib.compute_gjk_epa(C.c_int(n), _ptr(b1), _ptr(b2), _ptr(simp), _ptr(dist), _ptr(w1), _ptr(w2))
         return dist, simp, w1, w2
+
+    def epa(self, coords, off, cnt, pa, pb, simplices, distances):
+        """The reference's compute_epa (gpu/include/openGJK_GPU.h:176-185): EPA only, on the GJK
+        results given.  Returns (distances, witness1, witness2, contact_normals)."""
+        coords, off, cnt, pa, pb, n, _, _ = self._prep(coords, off, cnt, pa, pb)
+        b1, b2 = self._bodies(coords, off, cnt, pa), self._bodies(coords, off, cnt, pb)
+        simp = np.ascontiguousarray(simplices, dtype=self.sdt).copy()
+        dist = np.ascontiguousarray(distances, dtype=self.npf).copy()
+        w1, w2, nr = (np.zeros((n, 3), dtype=self.npf) for _ in range(3))
+        self.lib.compute_epa(C.c_int(n), _ptr(b1), _ptr(b2), _ptr(simp), _ptr(dist), _ptr(w1), _ptr(w2), _ptr(nr))
+        return dist, w1, w2, nr
 
     def time_kernels(self, coords, off, cnt, pa, pb, reps=5, epa=False):
         """Kernel-only milliseconds through the mid-level API (device arrays built once;

@@ -122,9 +122,9 @@ def test_reference_suite_ranges(eng):
 
 def test_loose_agreement_with_reference_cuda_library(eng):
     """The reference's own CUDA kernels (compiled unmodified into oracle/_ref, FMA
-    contraction on) on the same GPU: GJK distances agree to fp32 rounding; EPA depths
-    agree for the overwhelming majority of pairs (the reference EPA is not
-    bit-reproducible: FMA, and divergent shuffles on degenerate faces)."""
+    contraction on) run live on the same GPU: GJK distances agree to fp32 rounding and EPA
+    depths for the overwhelming majority of pairs.  (The exact pin is tests/test_epa_golden.py:
+    committed outputs of the reference's -fmad=false build, matched bit for bit.)"""
     from oracle.pyoracle import ReferenceGPU
     if not ReferenceGPU.available("f32"):
         pytest.skip("oracle/_ref/libopenGJK_GPU_ref_f32.so not shipped")
