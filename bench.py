@@ -352,9 +352,10 @@ def main():
             kname = f"epa_warp_kernel<{tname}>"
         else:
             lanes = CLASS_TABLE[dom][1]
-            lo_key = CLASS_TABLE[dom - 1][0] if dom else 0
-            amin = int(os.environ.get("OGJK_ACCEL_MIN", 256))
-            if store.table_bytes > 0 and 1 <= lanes <= 32 and 4 * (lo_key + 1) >= 2 * amin:  # as run_store_batch routes
+            amin = int(os.environ.get("OGJK_ACCEL_MIN", 512))
+            # as run_store_batch routes: pairs whose two bodies both carry a table run the table kernel,
+            # timed with the last class
+            if store.table_bytes > 0 and dom == len(CLASS_TABLE) - 1 and int(w.cnt.min()) >= amin:
                 kname = f"gjk_table_kernel<{tname},{int(os.environ.get('OGJK_TABLE_LANES', 32))}>"
             else:
                 kname = f"gjk_small_kernel<{tname}>" if lanes == 0 else f"gjk_group_kernel<{tname},{lanes}>"

@@ -122,7 +122,7 @@ OGJK_API int ogjk_store_create_f32(ogjk_ctx* ctx, int64_t npoly, int64_t nverts,
 OGJK_API int ogjk_store_create_f64(ogjk_ctx* ctx, int64_t npoly, int64_t nverts, const double* coords, const int64_t* off,
                                    const int* cnt, int on_device, void* stream, ogjk_store** out);
 /* Stores created AFTER this call give every polytope with at least `min_vertices`
- * vertices (default 256; clamped to >= 64; at most 16384 vertices; 0 = off) a cluster
+ * vertices (default 512, the measured break-even on B200; clamped to >= 64; at most 16384 vertices; 0 = off) a cluster
  * table: a spatially clustered copy of its vertices with per-cluster bounding boxes that
  * lets the warp-per-pair kernel skip clusters which provably cannot change the support
  * point.  Results are bit-identical with and without the table. */

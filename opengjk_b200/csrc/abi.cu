@@ -96,7 +96,7 @@ struct ogjk_ctx_ {
   int nclasses = 4;
   int class_hi[kMaxClasses] = {4, 32, 128, 2048, 2048, 2048};
   int class_lanes[kMaxClasses] = {0, 2, 8, 32, 32, 32};
-  int accel_min = 256;  // persistent stores: cluster tables for polytopes with >= this many vertices (0 = none)
+  int accel_min = 512;  // persistent stores: cluster tables for polytopes with >= this many vertices (0 = none)
   int table_lanes = 32;  // lanes per pair of the pruned-scan kernel (8, 16 or 32; B200 sweep: profiles/r1_lanes_sweep.txt)
   bool timing = false;
   cudaEvent_t ev[2 * kPhases] = {};
@@ -377,7 +377,7 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
   unsigned long long* counters = nullptr;
   int rc = reset_counters(ctx, st, &counters);
   if (rc) return rc;
-  const size_t nkeys = kNumBins + 1;
+  const size_t nkeys = kNumBinsAll + 1;
   if ((rc = ctx->sort_tmp.reserve(3 * nkeys * sizeof(unsigned)))) return rc;
   if ((rc = ctx->sorted_list.reserve((size_t)a.npairs * sizeof(int)))) return rc;
   unsigned* hist = static_cast<unsigned*>(ctx->sort_tmp.p);
@@ -397,24 +397,34 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
 
   // start[b] = number of pairs with bin > b  =>  the class of size keys (lo, hi] occupies
   // [start[bin_upper(hi)], start[bin_upper(lo)]) of the sorted list
+  int last_run = 0;  // last class that launches (classes whose range is empty are skipped)
+  for (int c = 0, l = 0; c < ctx->nclasses; ++c) {
+    const int h = ctx->class_hi[c] > kMaxKey ? kMaxKey : ctx->class_hi[c];
+    if (h > l) { last_run = c; l = h; }
+  }
   int lo = 0;
   for (int c = 0; c < ctx->nclasses; ++c) {
     const int hi = ctx->class_hi[c] > kMaxKey ? kMaxKey : ctx->class_hi[c];
     if (hi <= lo) continue;
-    const unsigned* b = start + bin_upper(hi);
+    const unsigned* b = start + bin_upper(hi);  // class = sorted[*b, *e)
     const unsigned* e = start + bin_upper(lo);
     unsigned long long* head = counters + c;
     mark(ctx, st, 2 + c, 0);
     int lanes = ctx->class_lanes[c];
-    // A group-kernel class in which every pair is large enough for both bodies to carry a
-    // cluster table (persistent stores) runs the pruned-scan kernel instead.
-    if (a.s1.accel && a.s2.accel && lanes >= 1 && lanes <= 32 &&
-        4ll * (lo + 1) >= (long long)a.s1.accel_min + a.s2.accel_min)
-      lanes = 1000 + ctx->table_lanes;
+    // Persistent stores with cluster tables: the pairs whose two bodies both have one were
+    // sorted in front of everything else (store.cuh, kNumBinsAll) and run through the
+    // pruned-scan kernel; timed with the last class.
+    if (a.s1.accel && a.s2.accel && c == last_run) {
+      const unsigned* tb = start + (kNumBinsAll - 1);  // = 0 pairs above the top bin
+      const unsigned* te = start + (kNumBins - 1);     // = pairs in the table bins
+      switch (ctx->table_lanes) {
+        case 8: launch_table<T, 8>(ctx, a, sorted, tb, te, counters + 6, st); break;
+        case 16: launch_table<T, 16>(ctx, a, sorted, tb, te, counters + 6, st); break;
+        default: launch_table<T, 32>(ctx, a, sorted, tb, te, counters + 6, st); break;
+      }
+      ctx->launches += 1;
+    }
     switch (lanes) {
-      case 1008: launch_table<T, 8>(ctx, a, sorted, b, e, head, st); break;
-      case 1016: launch_table<T, 16>(ctx, a, sorted, b, e, head, st); break;
-      case 1032: launch_table<T, 32>(ctx, a, sorted, b, e, head, st); break;
       case 0: {
         long long blocks = (a.npairs + 127) / 128, cap = (long long)ctx->sm_count * 16;
         gjk_small_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, sorted, b, e, head);

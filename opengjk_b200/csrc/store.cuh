@@ -387,6 +387,10 @@ __host__ __device__ __forceinline__ int bin_of(int tk, int np1) {
 __host__ __device__ __forceinline__ int bin_upper(int tk) {
   return tk <= kFineKeys ? tk * kFineSub + kFineSub - 1 : kFineKeys * kFineSub + kFineSub - 1 + (tk - kFineKeys);
 }
+// Pairs whose two bodies both carry a cluster table (persistent stores) are sorted into
+// kMaxKey + 1 extra bins ABOVE the plain ones (one per size key), so they come first in the
+// sorted list and run as one segment through the pruned-scan kernel.
+constexpr int kNumBinsAll = kNumBins + kMaxKey + 1;
 constexpr int kSortBlock = 256;
 constexpr int kSortItems = 8;  // pairs per thread
 
@@ -395,8 +399,11 @@ __device__ __forceinline__ int pair_key(const StoreView<T>& s1, const StoreView<
                                         long long p) {
   const long long h1 = idx1 ? (long long)idx1[p] : p;
   const long long h2 = idx2 ? (long long)idx2[p] : p;
-  const int np1 = pad4(s1.cnt[h1]), np2 = pad4(s2.cnt[h2]);
+  const int n1 = s1.cnt[h1], n2 = s2.cnt[h2];
+  const int np1 = pad4(n1), np2 = pad4(n2);
   int k = (np1 + np2) >> 2;
+  if (s1.accel && s2.accel && n1 >= s1.accel_min && n1 <= kAccelMaxVerts && n2 >= s2.accel_min && n2 <= kAccelMaxVerts)
+    return kNumBins + (k > kMaxKey ? kMaxKey : k);
   // keys 2..4 are reserved for pairs whose two polytopes both fit 8 register slots
   if ((np1 > 8 || np2 > 8) && k < kSmallKeyMax + 1) k = kSmallKeyMax + 1;
   if (k > kMaxKey) k = kMaxKey;
@@ -407,8 +414,8 @@ template <typename T>
 __global__ void __launch_bounds__(kSortBlock)
 sort_hist_kernel(StoreView<T> s1, StoreView<T> s2, const int* __restrict__ idx1, const int* __restrict__ idx2,
                  long long npairs, unsigned* __restrict__ hist) {
-  __shared__ unsigned sh[kNumBins];
-  for (int i = threadIdx.x; i < kNumBins; i += kSortBlock) sh[i] = 0;
+  __shared__ unsigned sh[kNumBinsAll];
+  for (int i = threadIdx.x; i < kNumBinsAll; i += kSortBlock) sh[i] = 0;
   __syncthreads();
   const long long base = (long long)blockIdx.x * kSortBlock * kSortItems;
 #pragma unroll
@@ -417,7 +424,7 @@ sort_hist_kernel(StoreView<T> s1, StoreView<T> s2, const int* __restrict__ idx1,
     if (p < npairs) atomicAdd(&sh[pair_key(s1, s2, idx1, idx2, p)], 1u);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kNumBins; i += kSortBlock)
+  for (int i = threadIdx.x; i < kNumBinsAll; i += kSortBlock)
     if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
@@ -425,16 +432,16 @@ sort_hist_kernel(StoreView<T> s1, StoreView<T> s2, const int* __restrict__ idx1,
 // resets the scatter cursors.  Warp 0 does a chunked suffix scan over the bins.
 __global__ void __launch_bounds__(1024)
 sort_scan_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ start, unsigned* __restrict__ cursor) {
-  __shared__ unsigned sh[kNumBins];
-  for (int i = threadIdx.x; i < kNumBins; i += 1024) sh[i] = hist[i];
+  __shared__ unsigned sh[kNumBinsAll];
+  for (int i = threadIdx.x; i < kNumBinsAll; i += 1024) sh[i] = hist[i];
   __syncthreads();
   if (threadIdx.x < 32) {
     // lane l owns the contiguous bins [l*per, (l+1)*per) counted from the TOP
-    constexpr int per = (kNumBins + 31) / 32;
+    constexpr int per = (kNumBinsAll + 31) / 32;
     const int lane = threadIdx.x;
     unsigned local = 0;
     for (int j = 0; j < per; ++j) {
-      const int b = kNumBins - 1 - (lane * per + j);
+      const int b = kNumBinsAll - 1 - (lane * per + j);
       if (b >= 0) local += sh[b];
     }
     unsigned incl = local;
@@ -445,7 +452,7 @@ sort_scan_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ start
     }
     unsigned acc = incl - local;  // pairs in bins above this lane's range
     for (int j = 0; j < per; ++j) {
-      const int b = kNumBins - 1 - (lane * per + j);
+      const int b = kNumBinsAll - 1 - (lane * per + j);
       if (b >= 0) {
         const unsigned c = sh[b];
         sh[b] = acc;
@@ -454,7 +461,7 @@ sort_scan_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ start
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kNumBins; i += 1024) {
+  for (int i = threadIdx.x; i < kNumBinsAll; i += 1024) {
     start[i] = sh[i];
     cursor[i] = 0;
   }
@@ -465,8 +472,8 @@ __global__ void __launch_bounds__(kSortBlock)
 sort_scatter_kernel(StoreView<T> s1, StoreView<T> s2, const int* __restrict__ idx1, const int* __restrict__ idx2,
                     long long npairs, const unsigned* __restrict__ start, unsigned* __restrict__ cursor,
                     int* __restrict__ sorted) {
-  __shared__ unsigned sh[kNumBins];
-  for (int i = threadIdx.x; i < kNumBins; i += kSortBlock) sh[i] = 0;
+  __shared__ unsigned sh[kNumBinsAll];
+  for (int i = threadIdx.x; i < kNumBinsAll; i += kSortBlock) sh[i] = 0;
   __syncthreads();
   const long long base = (long long)blockIdx.x * kSortBlock * kSortItems;
   int key[kSortItems];
@@ -482,7 +489,7 @@ sort_scatter_kernel(StoreView<T> s1, StoreView<T> s2, const int* __restrict__ id
   }
   __syncthreads();
   // reserve a contiguous range per key for this block
-  for (int i = threadIdx.x; i < kNumBins; i += kSortBlock) {
+  for (int i = threadIdx.x; i < kNumBinsAll; i += kSortBlock) {
     const unsigned c = sh[i];
     if (c) sh[i] = start[i] + atomicAdd(&cursor[i], c);
   }

@@ -74,7 +74,7 @@ def test_pairwise_ragged_batch(prec, dt):
 def test_indexed_and_store(prec, dt):
     import torch
     rng = np.random.default_rng(5)
-    A, ka = _ragged(500, 300, 3, dt, scale=2.0)   # large enough for cluster tables in the store
+    A, ka = _ragged(500, 700, 3, dt, scale=2.0)   # some bodies large enough for cluster tables in the store
     pairs = rng.integers(0, 500, size=(4000, 2))
     dref, sref = _oracle(prec, A, ka, A[:0], ka[:0], pairs[:, 0], pairs[:, 1] - 500)
     dev = torch.device("cuda:0")
@@ -94,7 +94,7 @@ def test_indexed_and_store(prec, dt):
     sep = dref > np.finfo(dt).eps
     assert d[sep].tobytes() == dref[sep].tobytes()
     assert (d[~sep] <= 0).all() and np.isfinite(e["contact_normals"].cpu().numpy()).all()
-    ref = api.default_engine().gjk_epa_host(A.reshape(-1, 3), np.arange(500, dtype=np.int64) * 300, ka,
+    ref = api.default_engine().gjk_epa_host(A.reshape(-1, 3), np.arange(500, dtype=np.int64) * 700, ka,
                                             pairs[:, 0].astype(np.int32), pairs[:, 1].astype(np.int32))
     assert d.tobytes() == ref["distances"].tobytes()
     assert e["witnesses1"].cpu().numpy().tobytes() == ref["witness1"].tobytes()
