@@ -389,9 +389,11 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
   CU(cudaMemsetAsync(hist, 0, nkeys * sizeof(unsigned), st));
   const long long per_block = (long long)kSortBlock * kSortItems;
   const unsigned sblocks = (unsigned)((a.npairs + per_block - 1) / per_block);
-  sort_hist_kernel<T><<<sblocks, kSortBlock, 0, st>>>(a.s1, a.s2, a.idx1, a.idx2, a.npairs, hist);
-  sort_scan_kernel<<<1, 1024, 0, st>>>(hist, start, cursor);
-  sort_scatter_kernel<T><<<sblocks, kSortBlock, 0, st>>>(a.s1, a.s2, a.idx1, a.idx2, a.npairs, start, cursor, sorted);
+  const bool tables = a.s1.accel && a.s2.accel;
+  const int nbins = tables ? kNumBinsAll : kNumBins;
+  sort_hist_kernel<T><<<sblocks, kSortBlock, 0, st>>>(a.s1, a.s2, a.idx1, a.idx2, a.npairs, hist, nbins);
+  sort_scan_kernel<<<1, 1024, 0, st>>>(hist, start, cursor, nbins);
+  sort_scatter_kernel<T><<<sblocks, kSortBlock, 0, st>>>(a.s1, a.s2, a.idx1, a.idx2, a.npairs, start, cursor, sorted, nbins);
   mark(ctx, st, 1, 1);
   ctx->launches += 3;
 
@@ -414,7 +416,7 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
     // Persistent stores with cluster tables: the pairs whose two bodies both have one were
     // sorted in front of everything else (store.cuh, kNumBinsAll) and run through the
     // pruned-scan kernel; timed with the last class.
-    if (a.s1.accel && a.s2.accel && c == last_run) {
+    if (tables && c == last_run) {
       const unsigned* tb = start + (kNumBinsAll - 1);  // = 0 pairs above the top bin
       const unsigned* te = start + (kNumBins - 1);     // = pairs in the table bins
       switch (ctx->table_lanes) {

@@ -413,9 +413,9 @@ __device__ __forceinline__ int pair_key(const StoreView<T>& s1, const StoreView<
 template <typename T>
 __global__ void __launch_bounds__(kSortBlock)
 sort_hist_kernel(StoreView<T> s1, StoreView<T> s2, const int* __restrict__ idx1, const int* __restrict__ idx2,
-                 long long npairs, unsigned* __restrict__ hist) {
-  __shared__ unsigned sh[kNumBinsAll];
-  for (int i = threadIdx.x; i < kNumBinsAll; i += kSortBlock) sh[i] = 0;
+                 long long npairs, unsigned* __restrict__ hist, int nbins) {
+  __shared__ unsigned sh[kNumBinsAll];  // nbins = kNumBins, or kNumBinsAll when both stores carry tables
+  for (int i = threadIdx.x; i < nbins; i += kSortBlock) sh[i] = 0;
   __syncthreads();
   const long long base = (long long)blockIdx.x * kSortBlock * kSortItems;
 #pragma unroll
@@ -424,24 +424,24 @@ sort_hist_kernel(StoreView<T> s1, StoreView<T> s2, const int* __restrict__ idx1,
     if (p < npairs) atomicAdd(&sh[pair_key(s1, s2, idx1, idx2, p)], 1u);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kNumBinsAll; i += kSortBlock)
+  for (int i = threadIdx.x; i < nbins; i += kSortBlock)
     if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
 // Single block.  start[b] = number of pairs with bin > b (descending layout).  Also
 // resets the scatter cursors.  Warp 0 does a chunked suffix scan over the bins.
 __global__ void __launch_bounds__(1024)
-sort_scan_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ start, unsigned* __restrict__ cursor) {
+sort_scan_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ start, unsigned* __restrict__ cursor, int nbins) {
   __shared__ unsigned sh[kNumBinsAll];
-  for (int i = threadIdx.x; i < kNumBinsAll; i += 1024) sh[i] = hist[i];
+  for (int i = threadIdx.x; i < nbins; i += 1024) sh[i] = hist[i];
   __syncthreads();
   if (threadIdx.x < 32) {
     // lane l owns the contiguous bins [l*per, (l+1)*per) counted from the TOP
-    constexpr int per = (kNumBinsAll + 31) / 32;
+    const int per = (nbins + 31) / 32;
     const int lane = threadIdx.x;
     unsigned local = 0;
     for (int j = 0; j < per; ++j) {
-      const int b = kNumBinsAll - 1 - (lane * per + j);
+      const int b = nbins - 1 - (lane * per + j);
       if (b >= 0) local += sh[b];
     }
     unsigned incl = local;
@@ -452,7 +452,7 @@ sort_scan_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ start
     }
     unsigned acc = incl - local;  // pairs in bins above this lane's range
     for (int j = 0; j < per; ++j) {
-      const int b = kNumBinsAll - 1 - (lane * per + j);
+      const int b = nbins - 1 - (lane * per + j);
       if (b >= 0) {
         const unsigned c = sh[b];
         sh[b] = acc;
@@ -461,7 +461,7 @@ sort_scan_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ start
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kNumBinsAll; i += 1024) {
+  for (int i = threadIdx.x; i < nbins; i += 1024) {
     start[i] = sh[i];
     cursor[i] = 0;
   }
@@ -471,9 +471,9 @@ template <typename T>
 __global__ void __launch_bounds__(kSortBlock)
 sort_scatter_kernel(StoreView<T> s1, StoreView<T> s2, const int* __restrict__ idx1, const int* __restrict__ idx2,
                     long long npairs, const unsigned* __restrict__ start, unsigned* __restrict__ cursor,
-                    int* __restrict__ sorted) {
+                    int* __restrict__ sorted, int nbins) {
   __shared__ unsigned sh[kNumBinsAll];
-  for (int i = threadIdx.x; i < kNumBinsAll; i += kSortBlock) sh[i] = 0;
+  for (int i = threadIdx.x; i < nbins; i += kSortBlock) sh[i] = 0;
   __syncthreads();
   const long long base = (long long)blockIdx.x * kSortBlock * kSortItems;
   int key[kSortItems];
@@ -489,7 +489,7 @@ sort_scatter_kernel(StoreView<T> s1, StoreView<T> s2, const int* __restrict__ id
   }
   __syncthreads();
   // reserve a contiguous range per key for this block
-  for (int i = threadIdx.x; i < kNumBinsAll; i += kSortBlock) {
+  for (int i = threadIdx.x; i < nbins; i += kSortBlock) {
     const unsigned c = sh[i];
     if (c) sh[i] = start[i] + atomicAdd(&cursor[i], c);
   }
