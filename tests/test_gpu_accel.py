@@ -156,3 +156,27 @@ def test_tables_with_epa(eng):
         outs.append([x.cpu().numpy().tobytes() for x in (simp, dist, w1, w2, nr)])
         store.close()
     assert outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("prec,dt", PRECS)
+def test_two_stores_unindexed_and_mixed_thresholds(eng, prec, dt):
+    """Un-indexed form over two different stores (pair p = polytope p of each), the stores built
+    with different table thresholds; one store without tables at all falls back to plain scans."""
+    import torch
+    w = W.large_hull_pool(1500, 64, 300, 1500, 15, dtype=dt)
+    dref, sref = Oracle(prec).batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1)
+    c1, o1, k1, c2, o2, k2 = w.two_pools()
+    sdt = api.SIMPLEX_F64 if prec == "f64" else api.SIMPLEX_F32
+    dev = torch.device("cuda:0")
+    for amin1, amin2 in ((256, 512), (512, 0), (0, 0), (64, 1024)):
+        eng.set_accel_min(amin1)
+        s1 = eng.store_create(c1, o1, k1)
+        eng.set_accel_min(amin2)
+        s2 = eng.store_create(c2, o2, k2)
+        assert (s1.table_bytes > 0) == (amin1 > 0) and (s2.table_bytes > 0) == (amin2 > 0)
+        simp = torch.zeros(w.npairs * sdt.itemsize, dtype=torch.uint8, device=dev)
+        dist = torch.zeros(w.npairs, dtype=torch.float64 if prec == "f64" else torch.float32, device=dev)
+        eng.store_gjk(s1, None, s2, None, w.npairs, simp, dist, 0)
+        torch.cuda.synchronize()
+        _assert_same(f"two_stores/{amin1}/{amin2}", dist.cpu().numpy(), simp.cpu().numpy().view(sdt).reshape(-1), dref, sref, prec)
+        s1.close(); s2.close()
