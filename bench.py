@@ -245,6 +245,8 @@ def main():
     eng.set_classes(CLASS_TABLE)
     if os.environ.get("OGJK_ACCEL_MIN"):  # tuning hook: 0 = no cluster tables in the resident store
         eng.set_accel_min(int(os.environ["OGJK_ACCEL_MIN"]))
+    if os.environ.get("OGJK_PASSES"):  # e.g. "2:4:3" = passes:iters1:iters2
+        eng.set_passes(*[int(x) for x in os.environ["OGJK_PASSES"].split(":")])
     if os.environ.get("OGJK_TABLE_LANES"):
         eng.set_table_lanes(int(os.environ["OGJK_TABLE_LANES"]))
     hbm_peak, peak_src = peaks()

@@ -127,6 +127,11 @@ OGJK_API int ogjk_store_create_f64(ogjk_ctx* ctx, int64_t npoly, int64_t nverts,
  * lets the warp-per-pair kernel skip clusters which provably cannot change the support
  * point.  Results are bit-identical with and without the table. */
 OGJK_API int ogjk_ctx_set_accel_min(ogjk_ctx* ctx, int min_vertices);
+/* Multi-pass scheduling of the small-group size classes (1..8 lanes per pair): with passes = 2
+ * or 3, pairs still iterating after `iters1` (then `iters1 + iters2`) GJK iterations are parked
+ * and resumed densely packed in the next pass, so that warps do not idle on their slowest
+ * pair.  passes = 1 is the one-pass kernel.  A tuning knob; results do not depend on it. */
+OGJK_API int ogjk_ctx_set_passes(ogjk_ctx* ctx, int passes, int iters1, int iters2);
 /* Lanes cooperating on one pair in the kernel that uses the cluster tables: 8, 16 or
  * 32 (default).  A tuning knob; results do not depend on it. */
 OGJK_API int ogjk_ctx_set_table_lanes(ogjk_ctx* ctx, int lanes);

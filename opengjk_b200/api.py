@@ -177,6 +177,10 @@ class Engine:
         """Vertex count from which stores created afterwards get a cluster table (0 = off)."""
         check(_lib.lib().ogjk_ctx_set_accel_min(self._h, int(min_vertices)))
 
+    def set_passes(self, passes, iters1=4, iters2=3):
+        """Multi-pass scheduling of the small-group classes (1 = one-pass kernel)."""
+        check(_lib.lib().ogjk_ctx_set_passes(self._h, int(passes), int(iters1), int(iters2)))
+
     def set_table_lanes(self, lanes):
         """Lanes per pair (8, 16, 32) of the kernel that uses the cluster tables."""
         check(_lib.lib().ogjk_ctx_set_table_lanes(self._h, int(lanes)))

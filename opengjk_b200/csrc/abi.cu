@@ -97,6 +97,11 @@ struct ogjk_ctx_ {
   int class_hi[kMaxClasses] = {4, 32, 128, 2048, 2048, 2048};
   int class_lanes[kMaxClasses] = {0, 2, 8, 32, 32, 32};
   int accel_min = 512;  // persistent stores: cluster tables for polytopes with >= this many vertices (0 = none)
+  // multi-pass scheduling of the small-group classes (lanes 1..8): pairs still running after
+  // pass_iters[0] iterations are parked and resumed densely packed (gjk_pass_kernel)
+  int passes = 1;
+  int pass_iters[2] = {4, 3};
+  DevBuf pass_list[2], pass_f[2], pass_i[2];
   int table_lanes = 32;  // lanes per pair of the pruned-scan kernel (8, 16 or 32; B200 sweep: profiles/r1_lanes_sweep.txt)
   bool timing = false;
   cudaEvent_t ev[2 * kPhases] = {};
@@ -105,7 +110,7 @@ struct ogjk_ctx_ {
   cudaStream_t in_stream = nullptr, out_stream = nullptr;  // H2D / D2H legs of the chunked host pipeline
   cudaEvent_t chunk_in[16] = {}, chunk_done[16] = {};
   int pipeline_chunks = 8;            // 0/1 disables chunking
-  DevBuf counters;                    // 16 x u64 work-queue heads
+  DevBuf counters;                    // kCounterSlots x u64: work-queue heads (the first kQueueSlots are reset per batch)
   DevBuf sort_tmp;                    // hist | start | cursor (u32 each, kMaxKey+2)
   DevBuf sorted_list;                 // pair ids, size-sorted
   DevBuf epa_list;                    // pair ids that need EPA (distance <= eps)
@@ -129,11 +134,17 @@ void mark(ogjk_ctx* ctx, cudaStream_t st, int phase, int edge) {
   }
 }
 
+// Counter slots: [0, kQueueSlots) are the work-queue heads run_store_batch / launch_raw reset
+// at every batch (classes 0..5, table segment 6, EPA 8..9); kLayoutSlot holds the chunked
+// pipeline's layout verdict, which must survive the per-chunk resets.
+constexpr int kQueueSlots = 48;   // 16 + 4*c + {0,1,2,3}: parked-pair counts and queue heads of class c's later passes
+constexpr int kLayoutSlot = 56;
+constexpr int kCounterSlots = 64;
 int reset_counters(ogjk_ctx* ctx, cudaStream_t st, unsigned long long** out) {
-  int rc = ctx->counters.reserve(16 * sizeof(unsigned long long));
+  int rc = ctx->counters.reserve(kCounterSlots * sizeof(unsigned long long));
   if (rc) return rc;
   *out = static_cast<unsigned long long*>(ctx->counters.p);
-  CU(cudaMemsetAsync(*out, 0, 16 * sizeof(unsigned long long), st));
+  CU(cudaMemsetAsync(*out, 0, kQueueSlots * sizeof(unsigned long long), st));
   return OGJK_OK;
 }
 
@@ -288,6 +299,48 @@ void launch_group(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const u
   gjk_group_kernel<T, G><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, list, b, e, head);
 }
 
+// One size class in 2 or 3 passes (see gjk_pass_kernel).  Falls back to the one-pass kernel
+// when the parking buffers cannot be allocated.
+template <typename T, int G>
+void launch_passes(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const unsigned* b, const unsigned* e,
+                   unsigned long long* counters, int c, cudaStream_t st) {
+  const int passes = ctx->passes > 3 ? 3 : ctx->passes;
+  const size_t rows = (size_t)a.npairs;
+  bool ok = true;
+  for (int j = 0; j + 1 < passes && ok; ++j)
+    ok = ctx->pass_list[j].reserve(rows * sizeof(int)) == OGJK_OK &&
+         ctx->pass_f[j].reserve(rows * kParkF * sizeof(T)) == OGJK_OK &&
+         ctx->pass_i[j].reserve(rows * kParkI * sizeof(int)) == OGJK_OK;
+  if (!ok) {
+    cudaGetLastError();
+    launch_group<T, G>(ctx, a, list, b, e, counters + c, st);
+    return;
+  }
+  long long blocks = (a.npairs * G + 127) / 128, cap = (long long)ctx->sm_count * 16;
+  const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+  unsigned long long* extra = counters + 16 + 4 * c;  // count A, head A, count B, head B
+  int* list_a = static_cast<int*>(ctx->pass_list[0].p);
+  T* f_a = static_cast<T*>(ctx->pass_f[0].p);
+  int* i_a = static_cast<int*>(ctx->pass_i[0].p);
+  unsigned* count_a = reinterpret_cast<unsigned*>(extra + 0);
+  const int k1 = ctx->pass_iters[0], k2 = k1 + ctx->pass_iters[1];
+  gjk_pass_kernel<T, G><<<grid, 128, 0, st>>>(a, list, b, e, counters + c, PassArgs<T>{0, k1, nullptr, nullptr, list_a, count_a, f_a, i_a});
+  if (passes == 2) {
+    gjk_pass_kernel<T, G><<<grid, 128, 0, st>>>(a, list_a, nullptr, count_a, extra + 1,
+                                                PassArgs<T>{1, kMaxIter, f_a, i_a, nullptr, nullptr, nullptr, nullptr});
+    ctx->launches += 1;
+    return;
+  }
+  int* list_b = static_cast<int*>(ctx->pass_list[1].p);
+  T* f_b = static_cast<T*>(ctx->pass_f[1].p);
+  int* i_b = static_cast<int*>(ctx->pass_i[1].p);
+  unsigned* count_b = reinterpret_cast<unsigned*>(extra + 2);
+  gjk_pass_kernel<T, G><<<grid, 128, 0, st>>>(a, list_a, nullptr, count_a, extra + 1, PassArgs<T>{1, k2, f_a, i_a, list_b, count_b, f_b, i_b});
+  gjk_pass_kernel<T, G><<<grid, 128, 0, st>>>(a, list_b, nullptr, count_b, extra + 3,
+                                              PassArgs<T>{1, kMaxIter, f_b, i_b, nullptr, nullptr, nullptr, nullptr});
+  ctx->launches += 2;
+}
+
 template <typename T, int G>
 void launch_table(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const unsigned* b, const unsigned* e,
                   unsigned long long* head, cudaStream_t st) {
@@ -431,10 +484,10 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
         long long blocks = (a.npairs + 127) / 128, cap = (long long)ctx->sm_count * 16;
         gjk_small_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, sorted, b, e, head);
       } break;
-      case 1: launch_group<T, 1>(ctx, a, sorted, b, e, head, st); break;
-      case 2: launch_group<T, 2>(ctx, a, sorted, b, e, head, st); break;
-      case 4: launch_group<T, 4>(ctx, a, sorted, b, e, head, st); break;
-      case 8: launch_group<T, 8>(ctx, a, sorted, b, e, head, st); break;
+      case 1: if (ctx->passes > 1) launch_passes<T, 1>(ctx, a, sorted, b, e, counters, c, st); else launch_group<T, 1>(ctx, a, sorted, b, e, head, st); break;
+      case 2: if (ctx->passes > 1) launch_passes<T, 2>(ctx, a, sorted, b, e, counters, c, st); else launch_group<T, 2>(ctx, a, sorted, b, e, head, st); break;
+      case 4: if (ctx->passes > 1) launch_passes<T, 4>(ctx, a, sorted, b, e, counters, c, st); else launch_group<T, 4>(ctx, a, sorted, b, e, head, st); break;
+      case 8: if (ctx->passes > 1) launch_passes<T, 8>(ctx, a, sorted, b, e, counters, c, st); else launch_group<T, 8>(ctx, a, sorted, b, e, head, st); break;
       case 16: launch_group<T, 16>(ctx, a, sorted, b, e, head, st); break;
       case 32: launch_group<T, 32>(ctx, a, sorted, b, e, head, st); break;
       case 502: rc = launch_cta<T, 2>(ctx, a, sorted, b, e, head, hi, st); break;
@@ -474,7 +527,7 @@ template <typename T>
 int run_store_epa(ogjk_ctx* ctx, const EpaArgs<T>& a, cudaStream_t st) {
   if (a.npairs <= 0) return OGJK_OK;
   if (a.npairs > 0x7fffffffll) return fail(OGJK_ERR_ARG, "npairs exceeds 2^31-1 per call%s");
-  int rc = ctx->counters.reserve(16 * sizeof(unsigned long long));
+  int rc = ctx->counters.reserve(kCounterSlots * sizeof(unsigned long long));
   if (rc) return rc;
   if ((rc = ctx->epa_list.reserve((size_t)a.npairs * sizeof(int)))) return rc;
   auto* counters = static_cast<unsigned long long*>(ctx->counters.p);
@@ -596,8 +649,8 @@ int host_pipeline_chunked(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const
   if ((rc = store_build<T>(ctx, &ctx->scratch2, npairs, nverts2, dc2, do2, dk2, false, sc, false))) return rc;
   // Every polytope of a chunk must lie inside the chunk's coordinate range: checked on
   // the device (optimistically -- the verdict is read after the pipeline has drained).
-  if ((rc = ctx->counters.reserve(16 * sizeof(unsigned long long)))) return rc;
-  int* bad_layout = reinterpret_cast<int*>(static_cast<unsigned long long*>(ctx->counters.p) + 12);
+  if ((rc = ctx->counters.reserve(kCounterSlots * sizeof(unsigned long long)))) return rc;
+  int* bad_layout = reinterpret_cast<int*>(static_cast<unsigned long long*>(ctx->counters.p) + kLayoutSlot);
   CU(cudaMemsetAsync(bad_layout, 0, sizeof(int), sc));
   {
     long long cb = (npairs + 255) / 256, ccap = (long long)ctx->sm_count * 8;
@@ -1138,6 +1191,7 @@ void ogjk_ctx_destroy(ogjk_ctx* c) {
   ogjk_store_* ss[] = {&c->scratch1, &c->scratch2};
   for (ogjk_store_* q : ss) { q->data.release(); q->boff.release(); q->cnt.release(); q->scan_tmp.release(); }
   c->sort_tmp.release(); c->sorted_list.release(); c->epa_list.release(); c->bp_tmp.release();
+  for (int j = 0; j < 2; ++j) { c->pass_list[j].release(); c->pass_f[j].release(); c->pass_i[j].release(); }
   c->d_w1.release(); c->d_w2.release(); c->d_nrm.release();
   DevBuf* bufs[] = {&c->counters, &c->small_list, &c->large_list, &c->d_coords1, &c->d_coords2, &c->d_off1, &c->d_off2,
                     &c->d_cnt1,   &c->d_cnt2,     &c->d_idx1,     &c->d_idx2,    &c->d_simp,    &c->d_dist};
@@ -1370,6 +1424,15 @@ OGJK_BROADPHASE_IMPL(f64, double)
 int ogjk_ctx_set_accel_min(ogjk_ctx* c, int min_vertices) {
   if (!c || min_vertices < 0) return fail(OGJK_ERR_ARG, "min_vertices must be >= 0%s");
   c->accel_min = (min_vertices > 0 && min_vertices < 64) ? 64 : min_vertices;
+  return OGJK_OK;
+}
+
+int ogjk_ctx_set_passes(ogjk_ctx* c, int passes, int iters1, int iters2) {
+  if (!c || passes < 1 || passes > 3 || iters1 < 1 || iters2 < 1 || iters1 + iters2 >= kMaxIter)
+    return fail(OGJK_ERR_ARG, "passes must be 1..3 with 1 <= iters1, iters2 and iters1 + iters2 < 25%s");
+  c->passes = passes;
+  c->pass_iters[0] = iters1;
+  c->pass_iters[1] = iters2;
   return OGJK_OK;
 }
 

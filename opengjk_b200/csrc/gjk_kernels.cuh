@@ -672,6 +672,121 @@ gjk_group_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* _
   }
 }
 
+// ---- multi-pass scheduling of the group kernel ---------------------------------------
+// The pairs of a warp finish after different numbers of GJK iterations (1..25, mean 5 on
+// 8-64-vertex hulls), and a warp keeps iterating until its slowest pair is done: the plain
+// kernel runs at 13 of 32 active lanes.  Here a pass runs at most `iter_cap` iterations; a pair
+// that is not finished by then parks its iteration state (24 values + 12 ints) and its id in
+// a compacted list, and the next pass resumes the parked pairs densely packed.  Every pair
+// executes exactly the instruction sequence of the one-pass kernel, so results are unchanged.
+constexpr int kParkF = 24;  // v, sa, sb, q0..q3 xyz, wmax2 (+2 pad: 16-byte rows in fp32 too)
+constexpr int kParkI = 12;  // ia, ib, n, k, q0..q3 (ia, ib)
+
+template <typename T> OGJK_DI void park_state(const GjkState<T>& st, T* f, int* i) {
+  const MV<T>&q0 = st.s.q0, &q1 = st.s.q1, &q2 = st.s.q2, &q3 = st.s.q3;
+  const T vals[kParkF] = {st.v.x, st.v.y, st.v.z, st.sa.x, st.sa.y, st.sa.z, st.sb.x, st.sb.y, st.sb.z,
+                          q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, st.wmax2, (T)0, (T)0};
+  constexpr int CV = Chunk<T>::kVerts;
+#pragma unroll
+  for (int c = 0; c < kParkF / CV; ++c) {
+    if constexpr (CV == 4) *reinterpret_cast<float4*>(f + 4 * c) = make_float4(vals[4 * c], vals[4 * c + 1], vals[4 * c + 2], vals[4 * c + 3]);
+    else *reinterpret_cast<double2*>(f + 2 * c) = make_double2(vals[2 * c], vals[2 * c + 1]);
+  }
+  int4* o = reinterpret_cast<int4*>(i);
+  o[0] = make_int4(st.ia, st.ib, st.s.n, st.k);
+  o[1] = make_int4(q0.ia, q0.ib, q1.ia, q1.ib);
+  o[2] = make_int4(q2.ia, q2.ib, q3.ia, q3.ib);
+}
+
+template <typename T> OGJK_DI void unpark_state(GjkState<T>& st, const T* f, const int* i) {
+  T vals[kParkF];
+  constexpr int CV = Chunk<T>::kVerts;
+#pragma unroll
+  for (int c = 0; c < kParkF / CV; ++c) {
+    Chunk<T> ch;
+    ch.load(f + CV * c);
+#pragma unroll
+    for (int t = 0; t < CV; ++t) vals[CV * c + t] = ch.v[t];
+  }
+  const int4* in = reinterpret_cast<const int4*>(i);
+  const int4 a = in[0], b = in[1], c = in[2];
+  st.v = V3<T>{vals[0], vals[1], vals[2]};
+  st.sa = V3<T>{vals[3], vals[4], vals[5]};
+  st.sb = V3<T>{vals[6], vals[7], vals[8]};
+  st.ia = a.x; st.ib = a.y; st.s.n = a.z; st.k = a.w;
+  st.s.q0 = MV<T>{vals[9], vals[10], vals[11], b.x, b.y};
+  st.s.q1 = MV<T>{vals[12], vals[13], vals[14], b.z, b.w};
+  st.s.q2 = MV<T>{vals[15], vals[16], vals[17], c.x, c.y};
+  st.s.q3 = MV<T>{vals[18], vals[19], vals[20], c.z, c.w};
+  st.wmax2 = vals[21];
+}
+
+template <typename T> struct PassArgs {
+  int resume;          // 0: fresh pairs of the class segment; 1: `list` holds parked pair ids, state row = list position
+  int iter_cap;        // park pairs that are still running after this many iterations in total (kMaxIter: never park)
+  const T* in_f; const int* in_i;          // parked state to resume from
+  int* out_list; unsigned* out_count;      // where still-unfinished pairs are parked
+  T* out_f; int* out_i;
+};
+
+template <typename T, int G>
+__global__ void __launch_bounds__(128, (sizeof(T) == 8 ? OGJK_LB_GROUP_F64 : OGJK_LB_GROUP_F32))
+gjk_pass_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* __restrict__ seg_begin,
+                const unsigned* __restrict__ seg_end, unsigned long long* __restrict__ head, PassArgs<T> ps) {
+  constexpr int PER_WARP = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int g = lane % G;
+  const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - g));
+  const long long begin = seg_begin ? (long long)*seg_begin : 0;
+  const long long end = seg_end ? (long long)*seg_end : a.npairs;
+  for (;;) {
+    unsigned long long got = 0;
+    if (lane == 0) got = atomicAdd(head, (unsigned long long)PER_WARP);
+    got = __shfl_sync(0xffffffffu, got, 0);
+    const long long base = begin + (long long)got;
+    if (base >= end) break;
+    const long long slot = base + lane / G;
+    bool parked = false;
+    long long p = 0;
+    GjkState<T> st;
+    if (slot < end) {
+      p = list ? (long long)list[slot] : slot;
+      const long long h1 = a.idx1 ? (long long)a.idx1[p] : p;
+      const long long h2 = a.idx2 ? (long long)a.idx2[p] : p;
+      const int n1 = a.s1.cnt[h1], n2 = a.s2.cnt[h2];
+      GroupBody<T, G> b1{a.s1.data + a.s1.boff[h1], n1, pad4(n1), g, mask};
+      GroupBody<T, G> b2{a.s2.data + a.s2.boff[h2], n2, pad4(n2), g, mask};
+      if (ps.resume) unpark_state(st, ps.in_f + slot * kParkF, ps.in_i + slot * kParkI);
+      else gjk_init(b1, b2, st);
+      bool done;
+      do { done = gjk_step(b1, b2, st); } while (!done && st.k < ps.iter_cap);
+      if (done) {
+        Splx<T> s = st.s;
+        V3<T> w1, w2;
+        gjk_witnesses(b1, b2, s, w1, w2);
+        if (g == 0) {
+          a.distances[p] = sqrt(nrm2(st.v.x, st.v.y, st.v.z));
+          if (a.simplices) store_simplex(a.simplices + p, s, w1, w2);
+        }
+      } else {
+        parked = true;
+      }
+    }
+    // park the unfinished pairs of this warp: one atomic per warp, rows in lane order
+    const unsigned pm = __ballot_sync(0xffffffffu, parked && g == 0);
+    if (pm) {
+      unsigned row0 = 0;
+      if (lane == 0) row0 = atomicAdd(ps.out_count, (unsigned)__popc(pm));
+      row0 = __shfl_sync(0xffffffffu, row0, 0);
+      if (parked && g == 0) {
+        const long long row = (long long)row0 + __popc(pm & ((1u << lane) - 1u));
+        ps.out_list[row] = (int)p;
+        park_state(st, ps.out_f + row * kParkF, ps.out_i + row * kParkI);
+      }
+    }
+  }
+}
+
 // The group kernel for classes whose pairs (mostly) have cluster tables on both bodies
 // (persistent stores, large polytopes): same queue and outputs, pruned support scans.
 template <typename T, int G>

@@ -271,6 +271,54 @@ def test_chunk_pipelined_host_path(eng, prec, dt):
 
 
 @pytest.mark.parametrize("prec,dt", PRECS)
+def test_multi_pass_scheduling_is_invisible(eng, prec, dt):
+    """Pairs parked after a few iterations and resumed in later passes give the one-pass bytes, for
+    every split of the iteration budget (including parking after every single iteration)."""
+    o = Oracle(prec)
+    ws = [W.mixed_hulls(30000, seed=71, dtype=dt), W.random_hulls(6000, 40, 200, 72, 3.0, dt), W.tiny_bodies(60, 73, 1.0, dt)]
+    refs = [o.batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1) for w in ws]
+    try:
+        for passes, k1, k2 in ((2, 4, 3), (3, 4, 3), (2, 1, 1), (3, 1, 1), (3, 2, 20), (2, 23, 1)):
+            eng.set_passes(passes, k1, k2)
+            for w, (dref, sref) in zip(ws, refs):
+                d, s = _gpu(eng, w)
+                _assert_same(f"{w.name}/passes{passes}:{k1}:{k2}", d, s, dref, sref, prec)
+    finally:
+        eng.set_passes(1)
+
+
+def test_chunked_path_falls_back_on_scattered_layouts(eng):
+    """Pools whose polytopes are NOT stored in pair order: the chunked pipeline's device-side layout
+    check must send the batch to the one-shot path -- both when whole chunks overlap (caught on the
+    host) and when only a few polytopes inside chunks are out of place (caught only on the device)."""
+    dt = np.float64
+    w = W.mixed_hulls(50_000, seed=63, dtype=dt)
+    dref, sref = Oracle("f64").batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1)
+    c1, o1, k1, c2, o2, k2 = w.two_pools()
+    rng = np.random.default_rng(64)
+
+    def relocate(c, o, k, movers):
+        """Same polytopes, same pair order, but the vertices of `movers` are stored at the end of the pool."""
+        c = c.copy(); o = o.copy()
+        tail = [c]
+        end = c.shape[0]
+        for h in movers:
+            tail.append(c[o[h]:o[h] + k[h]].copy())
+            c[o[h]:o[h] + k[h]] = 1e30            # poison the old place: reading it would change the result
+            o[h] = end
+            end += k[h]
+        return np.concatenate(tail), o
+
+    few = rng.choice(len(k1), 7, replace=False)                      # a handful inside chunks
+    many = rng.permutation(len(k1))[: len(k1) // 2]                  # half of the pool
+    for movers in (few, many):
+        cc1, oo1 = relocate(c1, o1, k1, movers)
+        cc2, oo2 = relocate(c2, o2, k2, movers[::-1])
+        d, s = eng.gjk_host_pools(cc1, oo1, k1, cc2, oo2, k2)
+        _assert_same(f"scattered{len(movers)}", d, s, dref, sref, "f64")
+
+
+@pytest.mark.parametrize("prec,dt", PRECS)
 def test_scheduler_edge_cases(eng, prec, dt):
     """Batch sizes around warp/block boundaries, one pair, a hull beyond the largest sort key
     (> 8192 vertices per pair), and a batch that populates every size class at once."""
