@@ -956,7 +956,7 @@ int store_aabbs(ogjk_ctx* ctx, const ogjk_store* s, T* d_boxes, void* stream) {
   if (s->prec != (int)sizeof(T)) return fail(OGJK_ERR_ARG, "store precision mismatch%s");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  long long blocks = (s->npoly * 8 + 255) / 256, cap = (long long)ctx->sm_count * 32;
+  long long blocks = (s->npoly * OGJK_AABB_LANES + 255) / 256, cap = (long long)ctx->sm_count * 64;
   aabb_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(view_of<T>(s), s->npoly, d_boxes);
   ctx->launches += 1;
   CU(cudaGetLastError());

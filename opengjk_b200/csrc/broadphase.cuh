@@ -14,7 +14,7 @@
 
 namespace ogjk {
 
-// ---- per-polytope boxes: eight lanes per polytope, 16-byte chunk loads -------------------
+// ---- per-polytope boxes: a few lanes per polytope, 16-byte chunk loads --------------------
 template <typename T> struct BoxChunk;
 template <> struct BoxChunk<float> {
   static constexpr int kVerts = 4;
@@ -34,25 +34,29 @@ template <> struct BoxChunk<double> {
 // out[6 h .. 6 h + 5] = {min x, min y, min z, max x, max y, max z}.  Padding slots repeat
 // vertex 0, so whole chunks can be reduced without masking.  fmin/fmax skip NaN coordinates;
 // a polytope whose every coordinate on an axis is NaN keeps the NaN of vertex 0.
+#ifndef OGJK_AABB_LANES
+#define OGJK_AABB_LANES 8  // lanes per polytope (tools/aabb_ab.sh: 8 / 4 / 2 lanes = 87 / 73 / 45 % of HBM peak on 1000-vertex bodies, 47-50 % on 8-64-vertex ones)
+#endif
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 aabb_kernel(StoreView<T> s, long long npoly, T* __restrict__ out) {
   constexpr int CV = BoxChunk<T>::kVerts;
-  const int sub = threadIdx.x & 7;
-  const unsigned gm = 0xffu << ((threadIdx.x & 31) - sub);
-  const long long first = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  const long long stride = ((long long)gridDim.x * blockDim.x) >> 3;
+  constexpr int L = OGJK_AABB_LANES;
+  const int sub = threadIdx.x & (L - 1);
+  const unsigned gm = ((1u << L) - 1u) << ((threadIdx.x & 31) - sub);
+  const long long first = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  const long long stride = ((long long)gridDim.x * blockDim.x) / L;
   const long long rounds = (npoly + stride - 1) / stride;  // every lane of a warp loops equally often
   for (long long r = 0; r < rounds; ++r) {
     const long long h = first + r * stride;
-    if (h >= npoly) continue;  // uniform per 8-lane group; the shuffles below use the group mask
+    if (h >= npoly) continue;  // uniform per lane group; the shuffles below use the group mask
     const int np = pad4(s.cnt[h]);
     const T* blk = s.data + s.boff[h];
     const T* xs = blk;
     const T* ys = blk + np;
     const T* zs = blk + 2 * np;
     T lx = xs[0], ly = ys[0], lz = zs[0], hx = lx, hy = ly, hz = lz;
-    for (int c = sub * CV; c < np; c += 8 * CV) {
+    for (int c = sub * CV; c < np; c += L * CV) {
       T vx[CV], vy[CV], vz[CV];
       BoxChunk<T>::load(xs + c, vx);
       BoxChunk<T>::load(ys + c, vy);
@@ -65,7 +69,7 @@ aabb_kernel(StoreView<T> s, long long npoly, T* __restrict__ out) {
       }
     }
 #pragma unroll
-    for (int m = 4; m > 0; m >>= 1) {
+    for (int m = L / 2; m > 0; m >>= 1) {
       lx = fmin(lx, __shfl_xor_sync(gm, lx, m)); hx = fmax(hx, __shfl_xor_sync(gm, hx, m));
       ly = fmin(ly, __shfl_xor_sync(gm, ly, m)); hy = fmax(hy, __shfl_xor_sync(gm, hy, m));
       lz = fmin(lz, __shfl_xor_sync(gm, lz, m)); hz = fmax(hz, __shfl_xor_sync(gm, hz, m));
