@@ -52,6 +52,8 @@ WORKLOADS = {
                     lambda n, seed: W.large_hull_pool(n, 32768, 1000, 1000, seed, dtype=np.float32), 200_000),
     "hulls1k10k_f32": ("config4: indexed pairs of 1k-10k-vertex hulls, fp32", np.float32,
                        lambda n, seed: W.large_hull_pool(n, 2048, 1000, 10000, seed, dtype=np.float32), 50_000),
+    "hulls1k10k_full_f32": ("config4 at full size: 1 M indexed pairs over a pool of 8192 hulls with 1k-10k vertices (540 MB), fp32",
+                            np.float32, lambda n, seed: W.large_hull_pool(n, 8192, 1000, 10000, seed, dtype=np.float32), 1_000_000),
     "boxes100m_f32": ("config3 at full size: 100 M oriented box-box pairs generated on the device, fp32", np.float32,
                       None, 100_000_000),
     "epa_f32": ("config5: intersecting 8-64-vertex hull pairs, GJK + EPA, fp32", np.float32,
