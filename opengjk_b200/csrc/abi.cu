@@ -286,6 +286,7 @@ template <typename T> StoreView<T> view_of(const ogjk_store_* s) {
     v.accel = static_cast<const T*>(s->accel.p);
     v.aoff = static_cast<const long long*>(s->aoff.p);
     v.accel_min = s->accel_min;
+    v.npoly = s->npoly;
   }
   return v;
 }

@@ -32,6 +32,7 @@ template <typename T> struct StoreView {
   const T* accel = nullptr;
   const long long* aoff = nullptr;  // element offset of each polytope's accelerator block
   int accel_min = 0x7fffffff;       // polytopes with accel_min <= n <= kAccelMaxVerts have one
+  long long npoly = 0;              // polytopes in the store (only needed with tables)
 };
 
 // ---- cluster tables: exact pruning of the support scan for large polytopes --------
@@ -403,7 +404,14 @@ __device__ __forceinline__ int pair_key(const StoreView<T>& s1, const StoreView<
   const int np1 = pad4(n1), np2 = pad4(n2);
   int k = (np1 + np2) >> 2;
   if (s1.accel && s2.accel && n1 >= s1.accel_min && n1 <= kAccelMaxVerts && n2 >= s2.accel_min && n2 <= kAccelMaxVerts)
+#ifdef OGJK_TABLE_ORDER_BY_SIZE
     return kNumBins + (k > kMaxKey ? kMaxKey : k);
+#else
+    // The table kernel runs one pair per warp, so equal sizes inside a warp do not matter;
+    // ordering the segment by the first body's index instead keeps the bodies a pair list
+    // reuses (indexed batches) hot in L2.
+    return kNumBins + (int)(h1 * (long long)(kMaxKey + 1) / (s1.npoly > 0 ? s1.npoly : 1));
+#endif
   // keys 2..4 are reserved for pairs whose two polytopes both fit 8 register slots
   if ((np1 > 8 || np2 > 8) && k < kSmallKeyMax + 1) k = kSmallKeyMax + 1;
   if (k > kMaxKey) k = kMaxKey;
