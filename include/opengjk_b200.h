@@ -171,6 +171,13 @@ OGJK_API int ogjk_pairs_all_f32(ogjk_ctx* ctx, const float* d_boxes, int64_t npo
 OGJK_API int ogjk_pairs_all_f64(ogjk_ctx* ctx, const double* d_boxes, int64_t npoly, double margin, int64_t capacity,
                                 int* d_out1, int* d_out2, int64_t* d_count, void* stream);
 
+/* Intersect flag of every pair from its distance (device pointers): flag = !(distance > eps),
+ * eps = FLT_EPSILON / DBL_EPSILON -- the reference's own rule for "separated" (the EPA gate,
+ * gpu/opengjk_gpu.cu:2053; the reference has no flag field, openGJK.h:104-105 only documents
+ * that intersecting or touching bodies return 0).  1 = touching or intersecting. */
+OGJK_API int ogjk_intersect_flags_f32(ogjk_ctx* ctx, int64_t n, const float* d_distances, unsigned char* d_flags, void* stream);
+OGJK_API int ogjk_intersect_flags_f64(ogjk_ctx* ctx, int64_t n, const double* d_distances, unsigned char* d_flags, void* stream);
+
 /* Number of chunks (0..16, default 8) the un-indexed host-buffer entry points cut a
  * batch into so that H2D, kernels and D2H overlap; 0 or 1 = one shot. */
 OGJK_API int ogjk_ctx_set_pipeline_chunks(ogjk_ctx* ctx, int chunks);

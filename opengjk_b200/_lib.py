@@ -35,7 +35,7 @@ EXPORTS = [
     "ogjk_ctx_launch_count", "ogjk_ctx_set_warp_threshold", "ogjk_ctx_set_timing", "ogjk_ctx_last_timing",
     "ogjk_ctx_set_classes", "ogjk_ctx_set_pipeline_chunks", "ogjk_ctx_set_accel_min", "ogjk_ctx_set_table_lanes", "ogjk_ctx_set_passes", "ogjk_store_create_f32", "ogjk_store_create_f64", "ogjk_store_destroy", "ogjk_store_bytes",
     "ogjk_store_num_polytopes", "ogjk_store_table_bytes", "ogjk_store_aabbs_f32", "ogjk_store_aabbs_f64", "ogjk_pairs_cull_f32",
-    "ogjk_pairs_cull_f64", "ogjk_pairs_all_f32", "ogjk_pairs_all_f64", "ogjk_store_gjk_f32", "ogjk_store_gjk_f64",
+    "ogjk_pairs_cull_f64", "ogjk_pairs_all_f32", "ogjk_pairs_all_f64", "ogjk_intersect_flags_f32", "ogjk_intersect_flags_f64", "ogjk_store_gjk_f32", "ogjk_store_gjk_f64",
     "ogjk_store_epa_f32", "ogjk_store_epa_f64", "ogjk_store_gjk_epa_f32", "ogjk_store_gjk_epa_f64",
     "ogjk_gjk_epa_host_f32", "ogjk_gjk_epa_host_f64", "ogjk_compute_gjk_epa_f32", "ogjk_compute_gjk_epa_f64",
     "ogjk_compute_epa_f32", "ogjk_compute_epa_f64", "ogjk_test_subalgorithm_f32", "ogjk_test_subalgorithm_f64",
@@ -85,6 +85,8 @@ def lib():
                                                          ct, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         getattr(L, f"ogjk_pairs_all_{sfx}").argtypes = [C.c_void_p, C.c_void_p, C.c_int64, ct, C.c_int64, C.c_void_p,
                                                         C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ogjk_intersect_flags_f32.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ogjk_intersect_flags_f64.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ogjk_store_table_bytes.argtypes = [C.c_void_p]
     L.ogjk_store_table_bytes.restype = C.c_int64
     vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int

@@ -173,6 +173,10 @@ class Engine:
         check(getattr(_lib.lib(), f"ogjk_pairs_all_{prec}")(self._h, _p(boxes), int(npoly), float(margin), int(capacity),
                                                            _p(out1), _p(out2), _p(count), C.c_void_p(int(stream))))
 
+    def intersect_flags(self, prec, n, distances, flags, stream=0):
+        """flags[i] = !(distances[i] > eps) on the device (uint8; 1 = touching or intersecting)."""
+        check(getattr(_lib.lib(), f"ogjk_intersect_flags_{prec}")(self._h, int(n), _p(distances), _p(flags), C.c_void_p(int(stream))))
+
     def set_accel_min(self, min_vertices):
         """Vertex count from which stores created afterwards get a cluster table (0 = off)."""
         check(_lib.lib().ogjk_ctx_set_accel_min(self._h, int(min_vertices)))

@@ -1009,6 +1009,18 @@ int pairs_all(ogjk_ctx* ctx, const T* box, int64_t n, T margin, int64_t capacity
   return OGJK_OK;
 }
 
+template <typename T>
+int intersect_flags(ogjk_ctx* ctx, int64_t n, const T* d_distances, unsigned char* d_flags, void* stream, T eps) {
+  if (!ctx || n < 0 || (n && (!d_distances || !d_flags))) return fail(OGJK_ERR_ARG, "bad argument%s");
+  if (n == 0) return OGJK_OK;
+  CU(cudaSetDevice(ctx->device));
+  long long blocks = (n + 255) / 256, cap = (long long)ctx->sm_count * 16;
+  intersect_flags_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_distances, n, eps, d_flags);
+  ctx->launches += 1;
+  CU(cudaGetLastError());
+  return OGJK_OK;
+}
 template <typename T, typename S>
 int store_gjk(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_store* s2, const int* idx2, int64_t npairs,
               S* simplices, T* distances, void* stream) {
@@ -1402,6 +1414,13 @@ int ogjk_epa_device_structs_f64(ogjk_ctx* ctx, int64_t n, const ogjk_polytope_f6
                                 double* d_normals, void* stream) {
   return device_structs<double, ogjk_simplex_f64>(ctx, n, d_bd1, d_bd2, d_simplices, d_distances, d_w1, d_w2, d_normals,
                                                   false, true, stream);
+}
+
+int ogjk_intersect_flags_f32(ogjk_ctx* ctx, int64_t n, const float* d_distances, unsigned char* d_flags, void* stream) {
+  return intersect_flags<float>(ctx, n, d_distances, d_flags, stream, 1.1920928955078125e-07f);   // FLT_EPSILON = gkEpsilon
+}
+int ogjk_intersect_flags_f64(ogjk_ctx* ctx, int64_t n, const double* d_distances, unsigned char* d_flags, void* stream) {
+  return intersect_flags<double>(ctx, n, d_distances, d_flags, stream, 2.220446049250313e-16);   // DBL_EPSILON = gkEpsilon
 }
 
 // ---- broad-phase-adjacent pair production (broadphase.cuh) -------------------------------

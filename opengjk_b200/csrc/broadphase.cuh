@@ -188,4 +188,16 @@ allpairs_kernel(const T* __restrict__ box, long long n, T margin, long long* __r
   }
 }
 
+// ---- intersect flag ---------------------------------------------------------------------
+// The reference has no flag field; its consumers derive one from the distance.  This is the
+// EPA gate's rule (gpu/opengjk_gpu.cu:2053: `distance > gkEpsilon` means separated), so
+// flag = !(distance > eps): 1 for touching or intersecting pairs (and for NaN distances).
+template <typename T>
+__global__ void __launch_bounds__(256)
+intersect_flags_kernel(const T* __restrict__ distances, long long n, T eps, unsigned char* __restrict__ flags) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    flags[i] = !(distances[i] > eps) ? 1 : 0;
+}
+
 }  // namespace ogjk

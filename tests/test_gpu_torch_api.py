@@ -101,6 +101,26 @@ def test_indexed_and_store(prec, dt):
     store.close()
 
 
+def test_intersect_flags_entry():
+    """ogjk_intersect_flags_*: the device-side flag equals the rule applied to the oracle's distances."""
+    import torch
+    for prec, dt in PRECS:
+        A, ka = _ragged(4000, 20, 11, dt, scale=2.5)
+        B, kb = _ragged(4000, 20, 12, dt, scale=2.5)
+        ar = np.arange(4000)
+        dref, _ = _oracle(prec, A, ka, B, kb, ar, ar)
+        dev = torch.device("cuda:0")
+        out = torch_api.compute_minimum_distance(torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev),
+                                                 torch.from_numpy(ka).to(dev), torch.from_numpy(kb).to(dev))
+        flags = torch.zeros(4000, dtype=torch.uint8, device=dev)
+        api.default_engine().intersect_flags(prec, 4000, out["distances"], flags, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        want = ~(dref > np.finfo(dt).eps)
+        assert 0.05 < want.mean() < 0.95
+        assert np.array_equal(flags.cpu().numpy().astype(bool), want)
+        assert np.array_equal(out["intersecting"].cpu().numpy(), want)
+
+
 def test_async_on_side_stream():
     """Calls are enqueued on torch's current stream; no hidden synchronisation is needed for correctness."""
     import torch
