@@ -138,7 +138,7 @@ class ClockSampler:
                 "reasons": [n for n, b in self.REASONS.items() if self.bits & b], "samples": len(sm)}
 
 
-def cpu_baseline(w, prec, budget_s=12.0):
+def cpu_baseline(w, prec, budget_s=10.0):
     """Reference scalar library (or the oracle port) on all host cores, bounded sample."""
     from oracle.pyoracle import Oracle, Reference
     cores = os.cpu_count() or 1
@@ -156,7 +156,7 @@ def cpu_baseline(w, prec, budget_s=12.0):
     while True:
         run()
         reps += 1
-        if time.perf_counter() - t0 > budget_s or reps >= 200:
+        if time.perf_counter() - t0 > budget_s or reps >= 20000:
             break
     dt = time.perf_counter() - t0
     return {"value": n * reps / dt, "unit": "pairs/s", "cores": cores, "kind": kind,
