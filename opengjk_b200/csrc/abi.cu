@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/opengjk_b200.h"
@@ -827,8 +828,23 @@ int flatten(ogjk_ctx* ctx, size_t base, int n, const P* bd, size_t* bytes_used, 
   for (int i = 0; i < n; ++i) {
     o[i] = at;
     k[i] = bd[i].numpoints;
-    memcpy(c + 3 * at, bd[i].coord, (size_t)bd[i].numpoints * 3 * sizeof(T));
     at += bd[i].numpoints;
+  }
+  // gather the per-polytope vertex arrays (the reference copies each one to the device with its own
+  // cudaMemcpy, gpu/opengjk_gpu.cu:3105-3166); many small host copies, spread over a few threads
+  auto gather = [&](int lo, int hi) {
+    for (int i = lo; i < hi; ++i) memcpy(c + 3 * o[i], bd[i].coord, (size_t)bd[i].numpoints * 3 * sizeof(T));
+  };
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = nt > 16 ? 16 : (nt < 1 ? 1 : nt);
+  if (n < 4096 || nt == 1) {
+    gather(0, n);
+  } else {
+    std::vector<std::thread> pool;
+    pool.reserve(nt);
+    for (unsigned t = 0; t < nt; ++t)
+      pool.emplace_back(gather, (int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt));
+    for (auto& th : pool) th.join();
   }
   *coords = c; *off = o; *cnt = k; *nverts = total;
   *bytes_used = ((cbytes + (size_t)n * (sizeof(int64_t) + sizeof(int))) + 63) & ~(size_t)63;
