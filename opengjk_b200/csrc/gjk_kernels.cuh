@@ -787,8 +787,9 @@ gjk_pass_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* __
   }
 }
 
-// The group kernel for classes whose pairs (mostly) have cluster tables on both bodies
-// (persistent stores, large polytopes): same queue and outputs, pruned support scans.
+// The group kernel for the pairs whose two bodies both carry a cluster table (persistent
+// stores, large polytopes; the size sort puts them in a segment of their own): same queue
+// and outputs, pruned support scans.  A pair without two tables would take the plain scans.
 template <typename T, int G>
 __global__ void __launch_bounds__(128, (sizeof(T) == 8 ? OGJK_LB_TABLE_F64 : OGJK_LB_TABLE_F32))
 gjk_table_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* __restrict__ seg_begin,
