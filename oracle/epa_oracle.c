@@ -214,6 +214,11 @@ static int closest_face(const poly_t* p, real* closest_distance) {
   return best;
 }
 
+/* test probe: one support query (tests/test_epa_golden.py pins the tie rule with it) */
+void SUFFIX(oracle_epa_support)(int n1, const real* c1, int n2, const real* c2, const real* dir, real* out, int* out_idx) {
+  support_epa(n1, c1, n2, c2, dir, out, out_idx);
+}
+
 /* contact normal from witness1 to witness2 (:2061-2080 and the copies at :2146-2164 ...) */
 static void normal_from_witnesses(const real* w1, const real* w2, real* nrm_out) {
   real d[3];

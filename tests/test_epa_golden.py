@@ -84,3 +84,24 @@ def test_cuda_kernels_match_reference_cuda_outputs(prec, dt, tol, it):
         r = eng.gjk_epa_host(w.coords, w.off, w.cnt, w.pa, w.pb)
         _compare(name, prec, tol, it, g, r["distances"], r["witness1"], r["witness2"])
     eng.close()
+
+
+def test_tie_resolution_follows_the_reference_shuffle_tree():
+    """An exact tie between lanes is resolved by the reference's __shfl_down tree
+    (gpu/opengjk_gpu.cu:1780-1801), not by the lowest index: with 8 vertices (one per lane) whose
+    vertices 1 and 4 coincide at the extreme point, lane 0 takes lane 4's candidate at offset 4 and
+    keeps it when it meets lane 1 at offset 1 (strict >), so the answer is 4 where a first-index
+    argmax says 1.  Overlapping boxes hit such ties constantly; the restatement emulates the tree."""
+    import ctypes as C
+    o = Oracle("f64")
+    fn = o.lib.oracle_epa_support_f64
+    pts = np.array([[0.1, 0.2, 0.0], [2.0, 0.0, 0.0], [0.3, -0.4, 0.1], [0.5, 0.5, 0.5],
+                    [2.0, 0.0, 0.0], [-0.2, 0.1, 0.3], [0.0, -0.6, 0.2], [-1.0, 0.0, 0.0]], dtype=np.float64)
+    other = np.array([[0.0, 0.0, 0.0], [0.5, 0.1, 0.0], [-3.0, 0.2, 0.1], [0.2, 0.9, -0.3]], dtype=np.float64)
+    out = np.zeros(3); idx = np.zeros(2, dtype=np.int32)
+    d = np.array([1.0, 0.0, 0.0])
+    fn(C.c_int(8), pts.ctypes.data_as(C.c_void_p), C.c_int(4), other.ctypes.data_as(C.c_void_p),
+       d.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p))
+    assert int(np.argmax(pts @ d)) == 1          # the textbook rule
+    assert idx[0] == 4 and idx[1] == 2, idx      # the reference's rule; body 2 along -d has a unique maximum
+    assert np.array_equal(out, pts[4] - other[2])
