@@ -271,8 +271,10 @@ int store_build_accel(ogjk_ctx* ctx, ogjk_store_* s, cudaStream_t st) {
   v.accel = static_cast<const T*>(s->accel.p);
   v.aoff = aoff;
   v.accel_min = amin;
-  const long long cap = (long long)ctx->sm_count * (pcap <= 4096 ? 2 : 1);
-  accel_build_kernel<T><<<(unsigned)(npoly < cap ? npoly : cap), 1024, smem, st>>>(v, npoly, static_cast<T*>(s->accel.p), pcap);
+  // small polytopes: narrow CTAs, many per SM (the per-level sorts are barrier-latency bound)
+  const int threads = pcap <= 2048 ? 256 : 1024;
+  const long long cap = (long long)ctx->sm_count * (pcap <= 2048 ? 8 : pcap <= 4096 ? 2 : 1);
+  accel_build_kernel<T><<<(unsigned)(npoly < cap ? npoly : cap), threads, smem, st>>>(v, npoly, static_cast<T*>(s->accel.p), pcap);
   ctx->launches += 1;
   CU(cudaGetLastError());
   s->accel_min = amin;
