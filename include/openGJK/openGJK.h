@@ -54,6 +54,10 @@ OPENGJK_EXPORT void opengjk_test_S1D(gkSimplex* s, gkFloat* v);
 OPENGJK_EXPORT void opengjk_test_S2D(gkSimplex* s, gkFloat* v);
 OPENGJK_EXPORT void opengjk_test_S3D(gkSimplex* s, gkFloat* v);
 
+/* Entry point for C# callers (reference: scalar/openGJK.c:1154-1220 under CS_MONO_BUILD):
+ * component-major coordinates, inCoords[i * n + j] = component i of vertex j. */
+OPENGJK_EXPORT gkFloat csFunction(int nCoordsA, gkFloat* inCoordsA, int nCoordsB, gkFloat* inCoordsB);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,6 +3,7 @@
  * (the reference function is re-entrant, so concurrent callers are serialised here). */
 #include <math.h>
 #include <pthread.h>
+#include <stdlib.h>
 
 #include "openGJK/openGJK.h"
 #include "opengjk_b200.h"
@@ -43,3 +44,30 @@ static void sub(gkSimplex* s, gkFloat* v) {
 void opengjk_test_S1D(gkSimplex* s, gkFloat* v) { sub(s, v); }
 void opengjk_test_S2D(gkSimplex* s, gkFloat* v) { sub(s, v); }
 void opengjk_test_S3D(gkSimplex* s, gkFloat* v) { sub(s, v); }
+
+/* The reference's entry point for C# callers (scalar/openGJK.c:1154-1220, built there under
+ * CS_MONO_BUILD; P/Invoke in scalar/examples/cs/main.cs): coordinates arrive component-major,
+ * inCoords[i * n + j] = component i of vertex j; returns the distance. */
+OPENGJK_EXPORT gkFloat csFunction(int nCoordsA, gkFloat* inCoordsA, int nCoordsB, gkFloat* inCoordsB) {
+  if (nCoordsA < 1 || nCoordsB < 1 || !inCoordsA || !inCoordsB) return (gkFloat)NAN;
+  const int n = nCoordsA + nCoordsB;
+  gkFloat* rows = (gkFloat*)malloc((size_t)n * 3 * sizeof(gkFloat));
+  gkFloat** ptr = (gkFloat**)malloc((size_t)n * sizeof(gkFloat*));
+  gkFloat d = (gkFloat)NAN;
+  if (rows && ptr) {
+    for (int j = 0; j < nCoordsA; ++j)
+      for (int i = 0; i < 3; ++i) rows[3 * j + i] = inCoordsA[i * nCoordsA + j];
+    for (int j = 0; j < nCoordsB; ++j)
+      for (int i = 0; i < 3; ++i) rows[3 * (nCoordsA + j) + i] = inCoordsB[i * nCoordsB + j];
+    for (int j = 0; j < n; ++j) ptr[j] = rows + 3 * j;
+    gkPolytope a, b;
+    gkSimplex s;
+    a.numpoints = nCoordsA; a.coord = ptr; a.s_idx = 0; a.s[0] = a.s[1] = a.s[2] = 0;
+    b.numpoints = nCoordsB; b.coord = ptr + nCoordsA; b.s_idx = 0; b.s[0] = b.s[1] = b.s[2] = 0;
+    s.nvrtx = 0;
+    d = compute_minimum_distance(a, b, &s);
+  }
+  free(rows);
+  free(ptr);
+  return d;
+}

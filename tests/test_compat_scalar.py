@@ -54,7 +54,7 @@ def binding(path, cf):
 def test_flavour_libraries_export_the_reference_symbols():
     for path in (LIB64, LIB32):
         lib = ctypes.CDLL(path)
-        for sym in ("compute_minimum_distance", "opengjk_test_S1D", "opengjk_test_S2D", "opengjk_test_S3D"):
+        for sym in ("compute_minimum_distance", "opengjk_test_S1D", "opengjk_test_S2D", "opengjk_test_S3D", "csFunction"):
             assert hasattr(lib, sym), (path, sym)
     hdr = open(os.path.join(ROOT, "include", "openGJK", "openGJK.h")).read()
     for sym in ("compute_minimum_distance", "opengjk_test_S1D", "opengjk_test_S2D", "opengjk_test_S3D", "gkPolytope",
@@ -71,6 +71,20 @@ def test_example_two_bodies_by_value_call():
     _, q32 = binding(LIB32, c_float)
     d32, _ = q32(W.USER_P, W.USER_Q)
     assert np.float32(d32) == np.float32(3.6536495685577393)
+
+
+@pytest.mark.gpu
+def test_csharp_entry_point():
+    """csFunction (scalar/openGJK.c:1154-1220, the P/Invoke target of scalar/examples/cs/main.cs):
+    component-major coordinate arrays in, distance out."""
+    for path, cf, want in ((LIB64, c_double, 3.6536497222945008), (LIB32, c_float, float(np.float32(3.6536495685577393)))):
+        lib = ctypes.CDLL(path)
+        lib.csFunction.restype = cf
+        lib.csFunction.argtypes = [c_int, POINTER(cf), c_int, POINTER(cf)]
+        a = np.ascontiguousarray(np.asarray(W.USER_P, dtype=cf).T)   # (3, n): component-major
+        b = np.ascontiguousarray(np.asarray(W.USER_Q, dtype=cf).T)
+        d = lib.csFunction(a.shape[1], a.ctypes.data_as(POINTER(cf)), b.shape[1], b.ctypes.data_as(POINTER(cf)))
+        assert d == want
 
 
 @pytest.mark.gpu
