@@ -72,6 +72,18 @@ OGJK_API const char* ogjk_version(void);
 OGJK_API int ogjk_ctx_create(int device, ogjk_ctx** out);
 OGJK_API void ogjk_ctx_destroy(ogjk_ctx* ctx);
 OGJK_API int ogjk_ctx_device(const ogjk_ctx* ctx);
+/* Raw polytope pools (coords/off/cnt) are validated on the device while they are repacked:
+ * cnt[h] must lie in [1, nverts] and [off[h], off[h]+cnt[h]) inside [0, nverts).  The
+ * DEVICE-array entry points (ogjk_gjk_device_* AUTO, ogjk_store_create_* with on_device = 1)
+ * further require sum(cnt) <= nverts, i.e. polytopes that do not share vertices (the
+ * asynchronous repack sizes its buffer from nverts); host-buffer entry points accept shared
+ * and overlapping ranges.  An offending polytope is replaced by a dummy (never an
+ * out-of-bounds access) and a sticky flag is raised: the synchronising entry points
+ * (host-buffer calls, ogjk_store_create_*) report it as OGJK_ERR_ARG; after asynchronous
+ * device calls, ogjk_ctx_pool_status() synchronises the device and returns OGJK_ERR_ARG if
+ * any pool since the last report failed validation (results of that call are undefined),
+ * else OGJK_OK.  Reporting clears the flag. */
+OGJK_API int ogjk_ctx_pool_status(ogjk_ctx* ctx);
 /* Number of kernels launched by this context so far (bench "gpu_launches"). */
 OGJK_API int64_t ogjk_ctx_launch_count(const ogjk_ctx* ctx);
 /* Per-phase device timing for the roofline report: when enabled, CUDA events
@@ -89,7 +101,10 @@ OGJK_API int ogjk_ctx_last_timing(ogjk_ctx* ctx, float* ms8);
  * support scan uses all 32 lanes), or
  * lanes[i] = 0 for the register-resident thread-per-pair kernel (keys <= 4 only:
  * both polytopes have at most 8 vertices).  At most 6 classes; the last one
- * always extends to the largest key. */
+ * always extends to the largest key, so it cannot be the register-resident kernel.
+ * The product library carries the plain flavours (lanes 0, 1..32) only; the 100/200/300/500
+ * families are measured-and-lost experiments compiled into libopengjk_b200_exp.so
+ * (-DOGJK_EXPERIMENTAL) and rejected with OGJK_ERR_ARG elsewhere. */
 OGJK_API int ogjk_ctx_set_classes(ogjk_ctx* ctx, int n, const int* hi_keys, const int* lanes);
 /* Size (in vertices of body1+body2) from which AUTO uses the warp-cooperative kernel. */
 OGJK_API int ogjk_ctx_set_warp_threshold(ogjk_ctx* ctx, int nverts);
@@ -132,8 +147,10 @@ OGJK_API int ogjk_ctx_set_accel_min(ogjk_ctx* ctx, int min_vertices);
  * and resumed densely packed in the next pass, so that warps do not idle on their slowest
  * pair.  passes = 1 is the one-pass kernel.  A tuning knob; results do not depend on it. */
 OGJK_API int ogjk_ctx_set_passes(ogjk_ctx* ctx, int passes, int iters1, int iters2);
-/* Lanes cooperating on one pair in the kernel that uses the cluster tables: 8, 16 or
- * 32 (default).  A tuning knob; results do not depend on it. */
+/* Kernel that uses the cluster tables: 0 (default) = the warp-per-pair kernel with
+ * register-resident cluster boxes and cached support cluster (csrc/table_kernel.cuh);
+ * 8, 16 or 32 = the first-generation kernel with that many lanes per pair.  A tuning
+ * knob; results do not depend on it. */
 OGJK_API int ogjk_ctx_set_table_lanes(ogjk_ctx* ctx, int lanes);
 OGJK_API void ogjk_store_destroy(ogjk_store* store);
 OGJK_API int64_t ogjk_store_bytes(const ogjk_store* store);
@@ -276,6 +293,78 @@ OGJK_API int ogjk_epa_device_structs_f32(ogjk_ctx* ctx, int64_t n, const ogjk_po
 OGJK_API int ogjk_epa_device_structs_f64(ogjk_ctx* ctx, int64_t n, const ogjk_polytope_f64* d_bd1, const ogjk_polytope_f64* d_bd2,
                                          ogjk_simplex_f64* d_simplices, double* d_distances, double* d_witness1,
                                          double* d_witness2, double* d_normals, void* stream);
+
+/* ---- several GPUs of one box behind one call (north_star: contiguous pair slice per GPU,
+ * no collective on the hot path, NCCL only for the optional final gather).  The multi-device
+ * form of the one call a reference user makes, compute_minimum_distance(n, bd1, bd2, simplices,
+ * distances) (gpu/opengjk_gpu.cu:2977-3004, gpu/include/openGJK_GPU.h:153-159).
+ *
+ * ogjk_multi_create: devices[ndev] are CUDA ordinals (devices = NULL: 0..ndev-1; ndev = 0 with
+ *   NULL: every device of the box).  One context and one persistent host thread per device.
+ * ogjk_multi_shard_bounds: THE partition -- device slot i of ndev owns pairs [lo, hi); sizes
+ *   differ by at most one pair.  A pure function (callable without a GPU).
+ * ogjk_multi_gjk_host_* / ogjk_multi_gjk_epa_host_*: the arguments of ogjk_gjk_host_* /
+ *   ogjk_gjk_epa_host_*; every device computes its slice and copies its results straight into
+ *   [lo, hi) of the caller's arrays.  Un-indexed batches send a device only the coordinate
+ *   range its slice touches; indexed batches replicate the pool on every device.
+ * ogjk_multi_store_*: a pool replicated on every device (via_nccl = 0: each device uploads the
+ *   host arrays over its own PCIe link; 1: one upload + ncclBroadcast over NVLink), queried
+ *   with HOST index lists; _gjk / _gjk_epa return results in host arrays, _gjk_resident leaves
+ *   them on the devices: every device holds full-size result arrays (ogjk_multi_resident_*),
+ *   of which it has filled [lo, hi); ogjk_multi_allgather_* completes them on every device
+ *   (grouped ncclBroadcast per slice; NCCL is loaded with dlopen -- libnccl.so.2 or
+ *   $OGJK_NCCL_LIB -- and only these two paths need it).
+ * Not thread safe per multi context.  ogjk_multi_ctx exposes the per-device contexts for the
+ * tuning knobs. */
+typedef struct ogjk_multi_ ogjk_multi;
+typedef struct ogjk_multi_store_ ogjk_multi_store;
+OGJK_API int ogjk_multi_create(const int* devices, int ndev, ogjk_multi** out);
+OGJK_API void ogjk_multi_destroy(ogjk_multi* m);
+OGJK_API int ogjk_multi_num_devices(const ogjk_multi* m);
+OGJK_API ogjk_ctx* ogjk_multi_ctx(ogjk_multi* m, int i);
+OGJK_API int64_t ogjk_multi_launch_count(const ogjk_multi* m);
+OGJK_API void ogjk_multi_shard_bounds(int64_t npairs, int ndev, int i, int64_t* lo, int64_t* hi);
+OGJK_API void ogjk_multi_store_destroy(ogjk_multi_store* store);
+OGJK_API int64_t ogjk_multi_store_bytes(const ogjk_multi_store* store);
+OGJK_API int ogjk_multi_gjk_host_f32(ogjk_multi* m, int64_t npairs, const float* coords1, const int64_t* off1, const
+        int* cnt1, int64_t npoly1, int64_t nverts1, const int* idx1, const float* coords2, const int64_t* off2, const
+        int* cnt2, int64_t npoly2, int64_t nverts2, const int* idx2, ogjk_simplex_f32* simplices, float* distances);
+OGJK_API int ogjk_multi_gjk_epa_host_f32(ogjk_multi* m, int64_t npairs, const float* coords1, const int64_t* off1,
+        const int* cnt1, int64_t npoly1, int64_t nverts1, const int* idx1, const float* coords2, const int64_t* off2,
+        const int* cnt2, int64_t npoly2, int64_t nverts2, const int* idx2, ogjk_simplex_f32* simplices, float*
+        distances, float* witness1, float* witness2, float* normals);
+OGJK_API int ogjk_multi_store_create_f32(ogjk_multi* m, int64_t npoly, int64_t nverts, const float* coords, const
+        int64_t* off, const int* cnt, int via_nccl, ogjk_multi_store** out);
+OGJK_API int ogjk_multi_store_gjk_f32(ogjk_multi* m, const ogjk_multi_store* s1, const int* idx1, const
+        ogjk_multi_store* s2, const int* idx2, int64_t npairs, ogjk_simplex_f32* simplices, float* distances);
+OGJK_API int ogjk_multi_store_gjk_epa_f32(ogjk_multi* m, const ogjk_multi_store* s1, const int* idx1, const
+        ogjk_multi_store* s2, const int* idx2, int64_t npairs, ogjk_simplex_f32* simplices, float* distances, float*
+        witness1, float* witness2, float* normals);
+OGJK_API int ogjk_multi_store_gjk_resident_f32(ogjk_multi* m, const ogjk_multi_store* s1, const int* idx1, const
+        ogjk_multi_store* s2, const int* idx2, int64_t npairs);
+OGJK_API int ogjk_multi_allgather_f32(ogjk_multi* m);
+OGJK_API int ogjk_multi_resident_f32(ogjk_multi* m, int i, float** d_distances, ogjk_simplex_f32** d_simplices,
+        int64_t* lo, int64_t* hi);
+OGJK_API int ogjk_multi_gjk_host_f64(ogjk_multi* m, int64_t npairs, const double* coords1, const int64_t* off1, const
+        int* cnt1, int64_t npoly1, int64_t nverts1, const int* idx1, const double* coords2, const int64_t* off2,
+        const int* cnt2, int64_t npoly2, int64_t nverts2, const int* idx2, ogjk_simplex_f64* simplices, double*
+        distances);
+OGJK_API int ogjk_multi_gjk_epa_host_f64(ogjk_multi* m, int64_t npairs, const double* coords1, const int64_t* off1,
+        const int* cnt1, int64_t npoly1, int64_t nverts1, const int* idx1, const double* coords2, const int64_t*
+        off2, const int* cnt2, int64_t npoly2, int64_t nverts2, const int* idx2, ogjk_simplex_f64* simplices, double*
+        distances, double* witness1, double* witness2, double* normals);
+OGJK_API int ogjk_multi_store_create_f64(ogjk_multi* m, int64_t npoly, int64_t nverts, const double* coords, const
+        int64_t* off, const int* cnt, int via_nccl, ogjk_multi_store** out);
+OGJK_API int ogjk_multi_store_gjk_f64(ogjk_multi* m, const ogjk_multi_store* s1, const int* idx1, const
+        ogjk_multi_store* s2, const int* idx2, int64_t npairs, ogjk_simplex_f64* simplices, double* distances);
+OGJK_API int ogjk_multi_store_gjk_epa_f64(ogjk_multi* m, const ogjk_multi_store* s1, const int* idx1, const
+        ogjk_multi_store* s2, const int* idx2, int64_t npairs, ogjk_simplex_f64* simplices, double* distances,
+        double* witness1, double* witness2, double* normals);
+OGJK_API int ogjk_multi_store_gjk_resident_f64(ogjk_multi* m, const ogjk_multi_store* s1, const int* idx1, const
+        ogjk_multi_store* s2, const int* idx2, int64_t npairs);
+OGJK_API int ogjk_multi_allgather_f64(ogjk_multi* m);
+OGJK_API int ogjk_multi_resident_f64(ogjk_multi* m, int i, double** d_distances, ogjk_simplex_f64** d_simplices,
+        int64_t* lo, int64_t* hi);
 
 /* ---- sub-solver test hook, replacing opengjk_test_S1D/S2D/S3D (scalar/include/openGJK/openGJK.h:120-122,
  * scalar/openGJK.c:1232-1248): runs the device Signed-Volumes sub-solver once on `simplex`

@@ -33,14 +33,22 @@ def _p(a):
 class Engine:
     """One CUDA device (ogjk_ctx).  Raises OpenGJKError when no GPU is present."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, lib_path=None):
+        self._L = _lib.lib(lib_path)
         self._h = C.c_void_p()
-        check(_lib.lib().ogjk_ctx_create(int(device), C.byref(self._h)))
+        self._ck(self._L.ogjk_ctx_create(int(device), C.byref(self._h)))
         self.device = device
+
+    def _ck(self, rc):
+        check(rc, self._L)
+
+    def pool_status(self):
+        """Synchronises the device; raises if a raw pool failed validation since the last report."""
+        self._ck(self._L.ogjk_ctx_pool_status(self._h))
 
     def close(self):
         if self._h:
-            _lib.lib().ogjk_ctx_destroy(self._h)
+            self._L.ogjk_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -51,26 +59,26 @@ class Engine:
 
     @property
     def launch_count(self):
-        return int(_lib.lib().ogjk_ctx_launch_count(self._h))
+        return int(self._L.ogjk_ctx_launch_count(self._h))
 
     def set_timing(self, enable=True):
-        check(_lib.lib().ogjk_ctx_set_timing(self._h, int(bool(enable))))
+        self._ck(self._L.ogjk_ctx_set_timing(self._h, int(bool(enable))))
 
     def last_timing(self):
         """Milliseconds of the last device call: repack, sort, and one entry per size class."""
         ms = (C.c_float * 8)()
-        check(_lib.lib().ogjk_ctx_last_timing(self._h, ms))
+        self._ck(self._L.ogjk_ctx_last_timing(self._h, ms))
         return {"repack": ms[0], "sort": ms[1], "classes": [ms[i] for i in range(2, 8)]}
 
     def set_warp_threshold(self, nverts):
-        check(_lib.lib().ogjk_ctx_set_warp_threshold(self._h, int(nverts)))
+        self._ck(self._L.ogjk_ctx_set_warp_threshold(self._h, int(nverts)))
 
     def set_classes(self, table):
         """table: list of (hi_key, lanes); see ogjk_ctx_set_classes."""
         n = len(table)
         hi = (C.c_int * n)(*[int(t[0]) for t in table])
         ln = (C.c_int * n)(*[int(t[1]) for t in table])
-        check(_lib.lib().ogjk_ctx_set_classes(self._h, n, hi, ln))
+        self._ck(self._L.ogjk_ctx_set_classes(self._h, n, hi, ln))
 
     # -- device-resident batch over raw xyz-interleaved pools (torch CUDA tensors or raw pointers)
     def gjk_device(self, prec, npairs, coords1, off1, cnt1, idx1, coords2, off2, cnt2, idx2, simplices, distances,
@@ -79,8 +87,8 @@ class Engine:
             if given is not None:
                 return int(given)
             return int(t.numel() if hasattr(t, "numel") else t.size) // div
-        fn = getattr(_lib.lib(), f"ogjk_gjk_device_{prec}")
-        check(fn(self._h, int(npairs), _p(coords1), _p(off1), _p(cnt1), size(cnt1, npoly1), size(coords1, nverts1, 3),
+        fn = getattr(self._L, f"ogjk_gjk_device_{prec}")
+        self._ck(fn(self._h, int(npairs), _p(coords1), _p(off1), _p(cnt1), size(cnt1, npoly1), size(coords1, nverts1, 3),
                  _p(idx1), _p(coords2), _p(off2), _p(cnt2), size(cnt2, npoly2), size(coords2, nverts2, 3), _p(idx2),
                  _p(simplices), _p(distances), int(mode), C.c_void_p(int(stream))))
 
@@ -98,14 +106,14 @@ class Engine:
             cnt = np.ascontiguousarray(cnt, dtype=np.int32)
             npoly, nverts = int(cnt.shape[0]), int(coords.size) // 3
         h = C.c_void_p()
-        fn = getattr(_lib.lib(), f"ogjk_store_create_{prec}")
-        check(fn(self._h, npoly, nverts, _p(coords), _p(off), _p(cnt), int(on_device), C.c_void_p(int(stream)),
+        fn = getattr(self._L, f"ogjk_store_create_{prec}")
+        self._ck(fn(self._h, npoly, nverts, _p(coords), _p(off), _p(cnt), int(on_device), C.c_void_p(int(stream)),
                  C.byref(h)))
-        return Store(h, prec)
+        return Store(h, prec, self._L)
 
     def store_gjk(self, s1, idx1, s2, idx2, npairs, simplices, distances, stream=0):
-        fn = getattr(_lib.lib(), f"ogjk_store_gjk_{s1.prec}")
-        check(fn(self._h, s1._h, _p(idx1), s2._h, _p(idx2), int(npairs), _p(simplices), _p(distances),
+        fn = getattr(self._L, f"ogjk_store_gjk_{s1.prec}")
+        self._ck(fn(self._h, s1._h, _p(idx1), s2._h, _p(idx2), int(npairs), _p(simplices), _p(distances),
                  C.c_void_p(int(stream))))
 
     # -- host buffers, one pool shared by both bodies (indexed form) -------------
@@ -123,20 +131,20 @@ class Engine:
             simp = np.zeros(n, dtype=sdt) if want_simplices else None
         else:
             dist, simp = out
-        fn = getattr(_lib.lib(), f"ogjk_gjk_host_{prec}")
-        check(fn(self._h, n, _p(coords), _p(off), _p(cnt), cnt.shape[0], coords.shape[0], _p(pa), _p(coords), _p(off),
+        fn = getattr(self._L, f"ogjk_gjk_host_{prec}")
+        self._ck(fn(self._h, n, _p(coords), _p(off), _p(cnt), cnt.shape[0], coords.shape[0], _p(pa), _p(coords), _p(off),
                  _p(cnt), cnt.shape[0], coords.shape[0], _p(pb), _p(simp), _p(dist)))
         return dist, simp
 
     def store_epa(self, s1, idx1, s2, idx2, npairs, simplices, distances, witness1, witness2, normals=None, stream=0):
-        fn = getattr(_lib.lib(), f"ogjk_store_epa_{s1.prec}")
-        check(fn(self._h, s1._h, _p(idx1), s2._h, _p(idx2), int(npairs), _p(simplices), _p(distances), _p(witness1),
+        fn = getattr(self._L, f"ogjk_store_epa_{s1.prec}")
+        self._ck(fn(self._h, s1._h, _p(idx1), s2._h, _p(idx2), int(npairs), _p(simplices), _p(distances), _p(witness1),
                  _p(witness2), _p(normals), C.c_void_p(int(stream))))
 
     def store_gjk_epa(self, s1, idx1, s2, idx2, npairs, simplices, distances, witness1, witness2, normals=None,
                       stream=0):
-        fn = getattr(_lib.lib(), f"ogjk_store_gjk_epa_{s1.prec}")
-        check(fn(self._h, s1._h, _p(idx1), s2._h, _p(idx2), int(npairs), _p(simplices), _p(distances), _p(witness1),
+        fn = getattr(self._L, f"ogjk_store_gjk_epa_{s1.prec}")
+        self._ck(fn(self._h, s1._h, _p(idx1), s2._h, _p(idx2), int(npairs), _p(simplices), _p(distances), _p(witness1),
                  _p(witness2), _p(normals), C.c_void_p(int(stream))))
 
     def gjk_epa_host(self, coords, off, cnt, pa, pb, want_normals=True):
@@ -154,49 +162,55 @@ class Engine:
         w1 = np.zeros((n, 3), dtype=coords.dtype)
         w2 = np.zeros((n, 3), dtype=coords.dtype)
         nr = np.zeros((n, 3), dtype=coords.dtype) if want_normals else None
-        fn = getattr(_lib.lib(), f"ogjk_gjk_epa_host_{prec}")
-        check(fn(self._h, n, _p(coords), _p(off), _p(cnt), cnt.shape[0], coords.shape[0], _p(pa), _p(coords), _p(off),
+        fn = getattr(self._L, f"ogjk_gjk_epa_host_{prec}")
+        self._ck(fn(self._h, n, _p(coords), _p(off), _p(cnt), cnt.shape[0], coords.shape[0], _p(pa), _p(coords), _p(off),
                  _p(cnt), cnt.shape[0], coords.shape[0], _p(pb), _p(simp), _p(dist), _p(w1), _p(w2), _p(nr)))
         return {"distances": dist, "simplices": simp, "witness1": w1, "witness2": w2, "normals": nr}
 
     # -- broad-phase-adjacent pair production (device pointers; include/opengjk_b200.h) --------
     def store_aabbs(self, store, boxes, stream=0):
         """boxes: device buffer of 6*num_polytopes values, filled with {min xyz, max xyz} per polytope."""
-        check(getattr(_lib.lib(), f"ogjk_store_aabbs_{store.prec}")(self._h, store._h, _p(boxes), C.c_void_p(int(stream))))
+        self._ck(getattr(self._L, f"ogjk_store_aabbs_{store.prec}")(self._h, store._h, _p(boxes), C.c_void_p(int(stream))))
 
     def pairs_cull(self, prec, boxes1, boxes2, ncand, idx1, idx2, margin, capacity, out1, out2, count, stream=0):
-        check(getattr(_lib.lib(), f"ogjk_pairs_cull_{prec}")(self._h, _p(boxes1), _p(boxes2), int(ncand), _p(idx1), _p(idx2),
+        self._ck(getattr(self._L, f"ogjk_pairs_cull_{prec}")(self._h, _p(boxes1), _p(boxes2), int(ncand), _p(idx1), _p(idx2),
                                                             float(margin), int(capacity), _p(out1), _p(out2), _p(count),
                                                             C.c_void_p(int(stream))))
 
     def pairs_all(self, prec, boxes, npoly, margin, capacity, out1, out2, count, stream=0):
-        check(getattr(_lib.lib(), f"ogjk_pairs_all_{prec}")(self._h, _p(boxes), int(npoly), float(margin), int(capacity),
+        self._ck(getattr(self._L, f"ogjk_pairs_all_{prec}")(self._h, _p(boxes), int(npoly), float(margin), int(capacity),
                                                            _p(out1), _p(out2), _p(count), C.c_void_p(int(stream))))
 
     def intersect_flags(self, prec, n, distances, flags, stream=0):
         """flags[i] = !(distances[i] > eps) on the device (uint8; 1 = touching or intersecting)."""
-        check(getattr(_lib.lib(), f"ogjk_intersect_flags_{prec}")(self._h, int(n), _p(distances), _p(flags), C.c_void_p(int(stream))))
+        self._ck(getattr(self._L, f"ogjk_intersect_flags_{prec}")(self._h, int(n), _p(distances), _p(flags), C.c_void_p(int(stream))))
 
     def set_accel_min(self, min_vertices):
         """Vertex count from which stores created afterwards get a cluster table (0 = off)."""
-        check(_lib.lib().ogjk_ctx_set_accel_min(self._h, int(min_vertices)))
+        self._ck(self._L.ogjk_ctx_set_accel_min(self._h, int(min_vertices)))
 
     def set_passes(self, passes, iters1=4, iters2=3):
         """Multi-pass scheduling of the small-group classes (1 = one-pass kernel)."""
-        check(_lib.lib().ogjk_ctx_set_passes(self._h, int(passes), int(iters1), int(iters2)))
+        self._ck(self._L.ogjk_ctx_set_passes(self._h, int(passes), int(iters1), int(iters2)))
 
     def set_table_lanes(self, lanes):
         """Lanes per pair (8, 16, 32) of the kernel that uses the cluster tables."""
-        check(_lib.lib().ogjk_ctx_set_table_lanes(self._h, int(lanes)))
+        self._ck(self._L.ogjk_ctx_set_table_lanes(self._h, int(lanes)))
 
     def set_pipeline_chunks(self, chunks):
-        check(_lib.lib().ogjk_ctx_set_pipeline_chunks(self._h, int(chunks)))
+        self._ck(self._L.ogjk_ctx_set_pipeline_chunks(self._h, int(chunks)))
 
     def gjk_host_pools(self, c1, o1, k1, c2, o2, k2, out=None, epa=False):
         """Un-indexed form over two pools (pair p = polytope p of each pool), the shape of
         the reference's bd1[] / bd2[] arrays; large batches are chunk-pipelined over PCIe."""
         c1 = np.ascontiguousarray(c1); c2 = np.ascontiguousarray(c2)
+        if c1.dtype != c2.dtype:
+            raise ValueError(f"pools differ in precision: {c1.dtype} vs {c2.dtype}")
         prec, sdt = _PREC[c1.dtype]
+        o1 = np.ascontiguousarray(o1, dtype=np.int64); o2 = np.ascontiguousarray(o2, dtype=np.int64)
+        k1 = np.ascontiguousarray(k1, dtype=np.int32); k2 = np.ascontiguousarray(k2, dtype=np.int32)
+        if not (k1.shape[0] == k2.shape[0] == o1.shape[0] == o2.shape[0]):
+            raise ValueError("un-indexed form: both pools need one polytope per pair")
         n = int(k1.shape[0])
         if out is None:
             dist = np.zeros(n, dtype=c1.dtype)
@@ -207,9 +221,9 @@ class Engine:
                 _p(simp), _p(dist)]
         if epa:
             w1 = np.zeros((n, 3), dtype=c1.dtype); w2 = np.zeros((n, 3), dtype=c1.dtype); nr = np.zeros((n, 3), dtype=c1.dtype)
-            check(getattr(_lib.lib(), f"ogjk_gjk_epa_host_{prec}")(*args, _p(w1), _p(w2), _p(nr)))
+            self._ck(getattr(self._L, f"ogjk_gjk_epa_host_{prec}")(*args, _p(w1), _p(w2), _p(nr)))
             return {"distances": dist, "simplices": simp, "witness1": w1, "witness2": w2, "normals": nr}
-        check(getattr(_lib.lib(), f"ogjk_gjk_host_{prec}")(*args))
+        self._ck(getattr(self._L, f"ogjk_gjk_host_{prec}")(*args))
         return dist, simp
 
     def run_workload(self, w, want_simplices=True):
@@ -219,25 +233,181 @@ class Engine:
 class Store:
     """Handle of a packed device-resident polytope pool (ogjk_store)."""
 
-    def __init__(self, handle, prec):
-        self._h, self.prec = handle, prec
+    def __init__(self, handle, prec, L=None):
+        self._h, self.prec, self._L = handle, prec, L or _lib.lib()
 
     @property
     def nbytes(self):
-        return int(_lib.lib().ogjk_store_bytes(self._h))
+        return int(self._L.ogjk_store_bytes(self._h))
 
     @property
     def table_bytes(self):
         """Bytes of cluster tables (large polytopes' pruned-scan accelerator); 0 = none."""
-        return int(_lib.lib().ogjk_store_table_bytes(self._h))
+        return int(self._L.ogjk_store_table_bytes(self._h))
 
     @property
     def num_polytopes(self):
-        return int(_lib.lib().ogjk_store_num_polytopes(self._h))
+        return int(self._L.ogjk_store_num_polytopes(self._h))
 
     def close(self):
         if self._h:
-            _lib.lib().ogjk_store_destroy(self._h)
+            self._L.ogjk_store_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def shard_bounds(npairs, ndev, i, lib_path=None):
+    """[lo, hi) of the pair list that device slot i of ndev owns (ogjk_multi_shard_bounds: the
+    library owns the partition; a pure function, no GPU needed)."""
+    lo, hi = C.c_int64(), C.c_int64()
+    _lib.lib(lib_path).ogjk_multi_shard_bounds(int(npairs), int(ndev), int(i), C.byref(lo), C.byref(hi))
+    return int(lo.value), int(hi.value)
+
+
+class MultiEngine:
+    """Several GPUs of one box behind one call (ogjk_multi): every device owns a contiguous
+    slice of the pair list, results land in disjoint ranges of the caller's arrays."""
+
+    def __init__(self, devices=None, lib_path=None):
+        self._L = _lib.lib(lib_path)
+        self._h = C.c_void_p()
+        if devices is None:
+            rc = self._L.ogjk_multi_create(None, 0, C.byref(self._h))
+        else:
+            devices = [int(d) for d in devices]
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self._L.ogjk_multi_create(C.cast(arr, C.c_void_p), len(devices), C.byref(self._h))
+        check(rc, self._L)
+        self.ndev = int(self._L.ogjk_multi_num_devices(self._h))
+
+    def _ck(self, rc):
+        check(rc, self._L)
+
+    def close(self):
+        if self._h:
+            self._L.ogjk_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self):
+        return int(self._L.ogjk_multi_launch_count(self._h))
+
+    def bounds(self, npairs, i):
+        return shard_bounds(npairs, self.ndev, i)
+
+    def gjk_host(self, coords, off, cnt, pa, pb, want_simplices=True, out=None):
+        """Indexed form over one shared host pool (replicated on every device)."""
+        coords = np.ascontiguousarray(coords)
+        prec, sdt = _PREC[coords.dtype]
+        coords = coords.reshape(-1, 3)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        cnt = np.ascontiguousarray(cnt, dtype=np.int32)
+        pa = np.ascontiguousarray(pa, dtype=np.int32)
+        pb = np.ascontiguousarray(pb, dtype=np.int32)
+        n = pa.shape[0]
+        if out is None:
+            dist = np.zeros(n, dtype=coords.dtype)
+            simp = np.zeros(n, dtype=sdt) if want_simplices else None
+        else:
+            dist, simp = out
+        fn = getattr(self._L, f"ogjk_multi_gjk_host_{prec}")
+        self._ck(fn(self._h, n, _p(coords), _p(off), _p(cnt), cnt.shape[0], coords.shape[0], _p(pa), _p(coords), _p(off),
+                    _p(cnt), cnt.shape[0], coords.shape[0], _p(pb), _p(simp), _p(dist)))
+        return dist, simp
+
+    def gjk_host_pools(self, c1, o1, k1, c2, o2, k2, out=None, epa=False):
+        """Un-indexed form over two pools (pair p = polytope p of each): every device receives
+        only the coordinates of its own slice."""
+        c1 = np.ascontiguousarray(c1); c2 = np.ascontiguousarray(c2)
+        if c1.dtype != c2.dtype:
+            raise ValueError(f"pools differ in precision: {c1.dtype} vs {c2.dtype}")
+        prec, sdt = _PREC[c1.dtype]
+        o1 = np.ascontiguousarray(o1, dtype=np.int64); o2 = np.ascontiguousarray(o2, dtype=np.int64)
+        k1 = np.ascontiguousarray(k1, dtype=np.int32); k2 = np.ascontiguousarray(k2, dtype=np.int32)
+        n = int(k1.shape[0])
+        if out is None:
+            dist = np.zeros(n, dtype=c1.dtype)
+            simp = np.zeros(n, dtype=sdt)
+        else:
+            dist, simp = out
+        args = [self._h, n, _p(c1), _p(o1), _p(k1), n, c1.size // 3, None, _p(c2), _p(o2), _p(k2), n, c2.size // 3, None,
+                _p(simp), _p(dist)]
+        if epa:
+            w1 = np.zeros((n, 3), dtype=c1.dtype); w2 = np.zeros((n, 3), dtype=c1.dtype); nr = np.zeros((n, 3), dtype=c1.dtype)
+            self._ck(getattr(self._L, f"ogjk_multi_gjk_epa_host_{prec}")(*args, _p(w1), _p(w2), _p(nr)))
+            return {"distances": dist, "simplices": simp, "witness1": w1, "witness2": w2, "normals": nr}
+        self._ck(getattr(self._L, f"ogjk_multi_gjk_host_{prec}")(*args))
+        return dist, simp
+
+    def store_create(self, coords, off, cnt, via_nccl=False):
+        coords = np.ascontiguousarray(coords)
+        prec = _PREC[coords.dtype][0]
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        cnt = np.ascontiguousarray(cnt, dtype=np.int32)
+        h = C.c_void_p()
+        self._ck(getattr(self._L, f"ogjk_multi_store_create_{prec}")(self._h, int(cnt.shape[0]), int(coords.size) // 3,
+                                                                    _p(coords), _p(off), _p(cnt), int(bool(via_nccl)),
+                                                                    C.byref(h)))
+        return MultiStore(h, prec, self._L)
+
+    def store_gjk(self, s1, pa, s2, pb, out=None, epa=False):
+        """One batch over replicated stores; pa/pb are HOST index arrays."""
+        pa = np.ascontiguousarray(pa, dtype=np.int32)
+        pb = np.ascontiguousarray(pb, dtype=np.int32)
+        n = int(pa.shape[0])
+        ft, sdt = (np.float64, SIMPLEX_F64) if s1.prec == "f64" else (np.float32, SIMPLEX_F32)
+        dist, simp = out if out is not None else (np.zeros(n, dtype=ft), np.zeros(n, dtype=sdt))
+        if epa:
+            w1, w2, nr = (np.zeros((n, 3), dtype=ft) for _ in range(3))
+            self._ck(getattr(self._L, f"ogjk_multi_store_gjk_epa_{s1.prec}")(self._h, s1._h, _p(pa), s2._h, _p(pb), n,
+                                                                            _p(simp), _p(dist), _p(w1), _p(w2), _p(nr)))
+            return {"distances": dist, "simplices": simp, "witness1": w1, "witness2": w2, "normals": nr}
+        self._ck(getattr(self._L, f"ogjk_multi_store_gjk_{s1.prec}")(self._h, s1._h, _p(pa), s2._h, _p(pb), n, _p(simp),
+                                                                    _p(dist)))
+        return dist, simp
+
+    def store_gjk_resident(self, s1, pa, s2, pb, allgather=False):
+        """Results stay on the devices; returns [(device slot, d_dist ptr, d_simp ptr, lo, hi)].
+        With allgather=True every device ends up with all results (NCCL over NVLink)."""
+        pa = np.ascontiguousarray(pa, dtype=np.int32)
+        pb = np.ascontiguousarray(pb, dtype=np.int32)
+        n = int(pa.shape[0])
+        self._ck(getattr(self._L, f"ogjk_multi_store_gjk_resident_{s1.prec}")(self._h, s1._h, _p(pa), s2._h, _p(pb), n))
+        if allgather:
+            self._ck(getattr(self._L, f"ogjk_multi_allgather_{s1.prec}")(self._h))
+        out = []
+        for i in range(self.ndev):
+            dd, ds, lo, hi = C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
+            self._ck(getattr(self._L, f"ogjk_multi_resident_{s1.prec}")(self._h, i, C.byref(dd), C.byref(ds), C.byref(lo),
+                                                                       C.byref(hi)))
+            out.append((i, dd.value, ds.value, int(lo.value), int(hi.value)))
+        return out
+
+
+class MultiStore:
+    """A pool replicated on every device of a MultiEngine (ogjk_multi_store)."""
+
+    def __init__(self, handle, prec, L):
+        self._h, self.prec, self._L = handle, prec, L
+
+    @property
+    def nbytes(self):
+        return int(self._L.ogjk_multi_store_bytes(self._h))
+
+    def close(self):
+        if self._h:
+            self._L.ogjk_multi_store_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -364,8 +534,8 @@ def compute_gjk_epa_structs(bodies1, bodies2, dtype=np.float32, engine=None):
     dist = np.zeros(n, dtype=dtype)
     w1 = np.zeros((n, 3), dtype=dtype)
     w2 = np.zeros((n, 3), dtype=dtype)
-    fn = getattr(_lib.lib(), f"ogjk_compute_gjk_epa_{prec}")
-    check(fn(eng._h, n, C.cast(a1, C.c_void_p), C.cast(a2, C.c_void_p), _p(simp), _p(dist), _p(w1), _p(w2)))
+    fn = getattr(eng._L, f"ogjk_compute_gjk_epa_{prec}")
+    eng._ck(fn(eng._h, n, C.cast(a1, C.c_void_p), C.cast(a2, C.c_void_p), _p(simp), _p(dist), _p(w1), _p(w2)))
     return dist, simp, w1, w2
 
 
@@ -381,8 +551,8 @@ def compute_epa_structs(bodies1, bodies2, simplices, distances, dtype=np.float32
     w1 = np.zeros((n, 3), dtype=dtype)
     w2 = np.zeros((n, 3), dtype=dtype)
     nr = np.zeros((n, 3), dtype=dtype)
-    fn = getattr(_lib.lib(), f"ogjk_compute_epa_{prec}")
-    check(fn(eng._h, n, C.cast(a1, C.c_void_p), C.cast(a2, C.c_void_p), _p(simp), _p(dist), _p(w1), _p(w2), _p(nr)))
+    fn = getattr(eng._L, f"ogjk_compute_epa_{prec}")
+    eng._ck(fn(eng._h, n, C.cast(a1, C.c_void_p), C.cast(a2, C.c_void_p), _p(simp), _p(dist), _p(w1), _p(w2), _p(nr)))
     return dist, w1, w2, nr
 
 
@@ -420,8 +590,8 @@ def compute_minimum_distance_structs(bodies1, bodies2, dtype=np.float32, engine=
     n = len(bodies1)
     simp = np.zeros(n, dtype=sdt)
     dist = np.zeros(n, dtype=dtype)
-    fn = getattr(_lib.lib(), f"ogjk_compute_minimum_distance_{prec}")
-    check(fn(eng._h, n, C.cast(a1, C.c_void_p), C.cast(a2, C.c_void_p), _p(simp), _p(dist)))
+    fn = getattr(eng._L, f"ogjk_compute_minimum_distance_{prec}")
+    eng._ck(fn(eng._h, n, C.cast(a1, C.c_void_p), C.cast(a2, C.c_void_p), _p(simp), _p(dist)))
     return dist, simp
 
 
@@ -433,8 +603,8 @@ def compute_minimum_distance_indexed_structs(bodies, pairs, dtype=np.float32, en
     n = pairs.shape[0]
     simp = np.zeros(n, dtype=sdt)
     dist = np.zeros(n, dtype=dtype)
-    fn = getattr(_lib.lib(), f"ogjk_compute_minimum_distance_indexed_{prec}")
-    check(fn(eng._h, len(bodies), n, C.cast(a, C.c_void_p), _p(pairs), _p(simp), _p(dist)))
+    fn = getattr(eng._L, f"ogjk_compute_minimum_distance_indexed_{prec}")
+    eng._ck(fn(eng._h, len(bodies), n, C.cast(a, C.c_void_p), _p(pairs), _p(simp), _p(dist)))
     return dist, simp
 
 
@@ -450,7 +620,7 @@ def subalgorithm(vrtx, idx=None, dtype=np.float64, engine=None):
     if idx is not None:
         s["vrtx_idx"][0, : vrtx.shape[0]] = idx
     v = np.ones(3, dtype=dtype)
-    check(getattr(_lib.lib(), f"ogjk_test_subalgorithm_{prec}")(eng._h, _p(s), _p(v)))
+    eng._ck(getattr(eng._L, f"ogjk_test_subalgorithm_{prec}")(eng._h, _p(s), _p(v)))
     return v, s[0]
 
 
@@ -466,7 +636,7 @@ def single_query(vertices0, vertices1, dtype=np.float64, engine=None):
     rows_b = (C.POINTER(cf) * b.shape[0])(*[b[i].ctypes.data_as(C.POINTER(cf)) for i in range(b.shape[0])])
     simp = np.zeros(1, dtype=sdt)
     dist = np.zeros(1, dtype=dtype)
-    fn = getattr(_lib.lib(), f"ogjk_single_rows_{prec}")
-    check(fn(eng._h, a.shape[0], C.cast(rows_a, C.c_void_p), b.shape[0], C.cast(rows_b, C.c_void_p), _p(simp),
+    fn = getattr(eng._L, f"ogjk_single_rows_{prec}")
+    eng._ck(fn(eng._h, a.shape[0], C.cast(rows_a, C.c_void_p), b.shape[0], C.cast(rows_b, C.c_void_p), _p(simp),
              _p(dist)))
     return float(dist[0]), simp[0]

@@ -17,6 +17,10 @@
 
 #include "../../include/opengjk_b200.h"
 #include "gjk_kernels.cuh"
+#include "table_kernel.cuh"
+#ifdef OGJK_EXPERIMENTAL
+#include "gjk_experimental.cuh"
+#endif
 #include "epa_kernels.cuh"
 #include "broadphase.cuh"
 
@@ -103,7 +107,7 @@ struct ogjk_ctx_ {
   int passes = 1;
   int pass_iters[2] = {4, 3};
   DevBuf pass_list[2], pass_f[2], pass_i[2];
-  int table_lanes = 32;  // lanes per pair of the pruned-scan kernel (8, 16 or 32; B200 sweep: profiles/r1_lanes_sweep.txt)
+  int table_lanes = 0;   // 0: second-generation warp-per-pair table kernel (table_kernel.cuh); 8/16/32: the first one
   bool timing = false;
   cudaEvent_t ev[2 * kPhases] = {};
   int timed_mask = 0;
@@ -140,6 +144,7 @@ void mark(ogjk_ctx* ctx, cudaStream_t st, int phase, int edge) {
 // pipeline's layout verdict, which must survive the per-chunk resets.
 constexpr int kQueueSlots = 48;   // 16 + 4*c + {0,1,2,3}: parked-pair counts and queue heads of class c's later passes
 constexpr int kLayoutSlot = 56;
+constexpr int kPoolErrSlot = 57;  // sticky: a raw pool failed validation (store.cuh); cleared when reported
 constexpr int kCounterSlots = 64;
 int reset_counters(ogjk_ctx* ctx, cudaStream_t st, unsigned long long** out) {
   int rc = ctx->counters.reserve(kCounterSlots * sizeof(unsigned long long));
@@ -172,12 +177,40 @@ int launch_raw(ogjk_ctx* ctx, const BatchArgs<T>& a, int mode, cudaStream_t st) 
   return OGJK_OK;
 }
 
+// Sticky pool-error flag (counter slot kPoolErrSlot): raised on the device by the pool
+// validation in store.cuh, read by the synchronising entry points and ogjk_ctx_pool_status.
+int* pool_flag(ogjk_ctx* ctx) {
+  return reinterpret_cast<int*>(static_cast<unsigned long long*>(ctx->counters.p) + kPoolErrSlot);
+}
+
+// Reads the flag after the work queued on `st` has finished; clears it when set.
+int pool_verdict(ogjk_ctx* ctx, cudaStream_t st) {
+  int bad = 0;
+  CU(cudaMemcpyAsync(&bad, pool_flag(ctx), sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (!bad) return OGJK_OK;
+  CU(cudaMemsetAsync(pool_flag(ctx), 0, sizeof(int), st));
+  CU(cudaStreamSynchronize(st));
+  return fail(OGJK_ERR_ARG,
+              "polytope pool failed validation: a count outside [1, nverts], an offset range outside the coordinate "
+              "array, or (device-array entry points) polytopes sharing vertices so that sum(cnt) > nverts%s");
+}
+
+long long host_sum(const int* cnt, long long n) {
+  long long t = 0;
+  for (long long i = 0; i < n; ++i) t += cnt[i] > 0 ? cnt[i] : 0;
+  return t;
+}
+
 // Build a packed store from xyz-interleaved DEVICE arrays.  `exact` sizes the
 // allocation from the scanned total (one stream sync); otherwise an upper bound
-// (every polytope padded by 3 vertices) keeps the call asynchronous.
+// (cap_verts vertices, every polytope padded by 3) keeps the call asynchronous.
+// cap_verts >= nverts is the caller's bound on sum(cnt) (host paths know the sum;
+// device paths pass nverts, i.e. assume polytopes do not share vertices -- a pool that
+// breaks the bound is neutralised by overflow_guard_kernel and flagged, never overrun).
 template <typename T>
 int store_build(ogjk_ctx* ctx, ogjk_store_* s, long long npoly, long long nverts, const T* coords, const int64_t* off,
-                const int* cnt, bool exact, cudaStream_t st, bool pack_now = true) {
+                const int* cnt, bool exact, cudaStream_t st, bool pack_now = true, long long cap_verts = 0) {
   s->device = ctx->device;
   s->prec = (int)sizeof(T);
   s->npoly = npoly;
@@ -187,26 +220,36 @@ int store_build(ogjk_ctx* ctx, ogjk_store_* s, long long npoly, long long nverts
   if ((rc = s->cnt.reserve((size_t)npoly * sizeof(int)))) return rc;
   const long long nblocks = (npoly + kScanBlock - 1) / kScanBlock;
   if ((rc = s->scan_tmp.reserve((size_t)(nblocks + 1) * sizeof(long long)))) return rc;
-  CU(cudaMemcpyAsync(s->cnt.p, cnt, (size_t)npoly * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  int* flag = pool_flag(ctx);
+  int* scnt = static_cast<int*>(s->cnt.p);
+  const long long gb = (npoly + 255) / 256, gcap = (long long)ctx->sm_count * 32;
+  const unsigned ggrid = (unsigned)(gb < gcap ? gb : gcap);
+  sanitize_counts_kernel<<<ggrid, 256, 0, st>>>(cnt, npoly, nverts, scnt, flag);
   auto* sums = static_cast<long long*>(s->scan_tmp.p);
   auto* boff = static_cast<long long*>(s->boff.p);
-  scan_block_sums_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(cnt, npoly, sums, BlockElems{});
+  scan_block_sums_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(scnt, npoly, sums, BlockElems{});
   scan_spine_kernel<<<1, 1024, 0, st>>>(sums, nblocks, sums + nblocks);
-  scan_finish_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(cnt, npoly, sums, boff, BlockElems{});
-  long long elems = 3 * (nverts + 3 * npoly);
+  scan_finish_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(scnt, npoly, sums, boff, BlockElems{});
+  if (cap_verts < nverts) cap_verts = nverts;
+  long long elems = 3 * (cap_verts + 3 * npoly);
   if (exact) {
     long long total = 0;
     CU(cudaMemcpyAsync(&total, sums + nblocks, sizeof(long long), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     elems = total;
   }
-  if ((rc = s->data.reserve((size_t)(elems > 0 ? elems : 4) * sizeof(T)))) return rc;
+  if (elems < 12) elems = 12;  // room for the guard's dummy block
+  if ((rc = s->data.reserve((size_t)elems * sizeof(T)))) return rc;
   s->capacity = elems;
-  ctx->launches += 3;
+  ctx->launches += 4;
+  if (!exact) {
+    overflow_guard_kernel<<<ggrid, 256, 0, st>>>(sums + nblocks, elems, npoly, scnt, boff, flag);
+    ctx->launches += 1;
+  }
   if (pack_now) {
     long long pblocks = (npoly * 8 + 255) / 256, cap = (long long)ctx->sm_count * 32;
     pack_kernel<T><<<(unsigned)(pblocks < cap ? pblocks : cap), 256, 0, st>>>(
-        coords, reinterpret_cast<const long long*>(off), cnt, npoly, boff, static_cast<T*>(s->data.p));
+        coords, reinterpret_cast<const long long*>(off), scnt, npoly, boff, static_cast<T*>(s->data.p), nverts, flag);
     ctx->launches += 1;
   }
   CU(cudaGetLastError());
@@ -216,13 +259,13 @@ int store_build(ogjk_ctx* ctx, ogjk_store_* s, long long npoly, long long nverts
 // Repack polytopes [lo, hi) of a prepared store (offsets already scanned).
 template <typename T>
 int store_pack_range(ogjk_ctx* ctx, ogjk_store_* s, long long lo, long long hi, const T* coords, const int64_t* off,
-                     const int* cnt, cudaStream_t st) {
+                     cudaStream_t st) {
   const long long n = hi - lo;
   if (n <= 0) return OGJK_OK;
   long long pblocks = (n * 8 + 255) / 256, cap = (long long)ctx->sm_count * 32;
   pack_kernel<T><<<(unsigned)(pblocks < cap ? pblocks : cap), 256, 0, st>>>(
-      coords, reinterpret_cast<const long long*>(off) + lo, cnt + lo, n, static_cast<const long long*>(s->boff.p) + lo,
-      static_cast<T*>(s->data.p));
+      coords, reinterpret_cast<const long long*>(off) + lo, static_cast<const int*>(s->cnt.p) + lo, n,
+      static_cast<const long long*>(s->boff.p) + lo, static_cast<T*>(s->data.p), s->nverts, pool_flag(ctx));
   ctx->launches += 1;
   CU(cudaGetLastError());
   return OGJK_OK;
@@ -303,6 +346,7 @@ void launch_group(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const u
   gjk_group_kernel<T, G><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, list, b, e, head);
 }
 
+#ifdef OGJK_EXPERIMENTAL
 // One size class in 2 or 3 passes (see gjk_pass_kernel).  Falls back to the one-pass kernel
 // when the parking buffers cannot be allocated.
 template <typename T, int G>
@@ -345,6 +389,8 @@ void launch_passes(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const 
   ctx->launches += 2;
 }
 
+#endif  // OGJK_EXPERIMENTAL
+
 template <typename T, int G>
 void launch_table(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const unsigned* b, const unsigned* e,
                   unsigned long long* head, cudaStream_t st) {
@@ -352,6 +398,7 @@ void launch_table(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const u
   gjk_table_kernel<T, G><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, list, b, e, head);
 }
 
+#ifdef OGJK_EXPERIMENTAL
 // Shared-memory slot size for a staged class: room for 4*hi_key vertices, rounded so
 // that slot_bytes = 16*G (mod 128) (bank spreading, see gjk_staged_kernel).
 template <typename T> int staged_slot_bytes(int hi_key, int G) {
@@ -371,11 +418,8 @@ int launch_staged(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const u
     return OGJK_OK;
   }
   const size_t smem = (size_t)(128 / G) * slot;
-  static size_t configured = 0;  // per instantiation
-  if (smem > configured) {
-    CU(cudaFuncSetAttribute(gjk_staged_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  // per device and cheap: set on every launch (a process-wide cache would miss other devices)
+  CU(cudaFuncSetAttribute(gjk_staged_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long blocks = (a.npairs * G + 127) / 128, cap = (long long)ctx->sm_count * 16;
   gjk_staged_kernel<T, G><<<(unsigned)(blocks < cap ? blocks : cap), 128, smem, st>>>(a, list, b, e, head, slot);
   return OGJK_OK;
@@ -390,11 +434,7 @@ int launch_cta(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const unsi
     launch_group<T, 32>(ctx, a, list, b, e, head, st);
     return OGJK_OK;
   }
-  static long long configured = 0;  // per instantiation
-  if (bytes > configured) {
-    CU(cudaFuncSetAttribute(gjk_cta_kernel<T, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    configured = bytes;
-  }
+  CU(cudaFuncSetAttribute(gjk_cta_kernel<T, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   long long per_sm = (220ll * 1024) / (bytes + 1024);
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 2048 / (32 * WARPS)) per_sm = 2048 / (32 * WARPS);
@@ -425,6 +465,8 @@ void launch_persist(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const
     ctx->launches += 1;
   }
 }
+
+#endif  // OGJK_EXPERIMENTAL
 
 // The batch scheduler: counting sort by size, then one launch per size class.
 template <typename T>
@@ -479,7 +521,11 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
       switch (ctx->table_lanes) {
         case 8: launch_table<T, 8>(ctx, a, sorted, tb, te, counters + 6, st); break;
         case 16: launch_table<T, 16>(ctx, a, sorted, tb, te, counters + 6, st); break;
-        default: launch_table<T, 32>(ctx, a, sorted, tb, te, counters + 6, st); break;
+        case 32: launch_table<T, 32>(ctx, a, sorted, tb, te, counters + 6, st); break;
+        default: {
+          long long blocks = (a.npairs * 32 + 127) / 128, cap = (long long)ctx->sm_count * 16;
+          gjk_table2_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, sorted, tb, te, counters + 6);
+        } break;
       }
       ctx->launches += 1;
     }
@@ -488,12 +534,20 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
         long long blocks = (a.npairs + 127) / 128, cap = (long long)ctx->sm_count * 16;
         gjk_small_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, sorted, b, e, head);
       } break;
+#ifdef OGJK_EXPERIMENTAL
       case 1: if (ctx->passes > 1) launch_passes<T, 1>(ctx, a, sorted, b, e, counters, c, st); else launch_group<T, 1>(ctx, a, sorted, b, e, head, st); break;
       case 2: if (ctx->passes > 1) launch_passes<T, 2>(ctx, a, sorted, b, e, counters, c, st); else launch_group<T, 2>(ctx, a, sorted, b, e, head, st); break;
       case 4: if (ctx->passes > 1) launch_passes<T, 4>(ctx, a, sorted, b, e, counters, c, st); else launch_group<T, 4>(ctx, a, sorted, b, e, head, st); break;
       case 8: if (ctx->passes > 1) launch_passes<T, 8>(ctx, a, sorted, b, e, counters, c, st); else launch_group<T, 8>(ctx, a, sorted, b, e, head, st); break;
+#else
+      case 1: launch_group<T, 1>(ctx, a, sorted, b, e, head, st); break;
+      case 2: launch_group<T, 2>(ctx, a, sorted, b, e, head, st); break;
+      case 4: launch_group<T, 4>(ctx, a, sorted, b, e, head, st); break;
+      case 8: launch_group<T, 8>(ctx, a, sorted, b, e, head, st); break;
+#endif
       case 16: launch_group<T, 16>(ctx, a, sorted, b, e, head, st); break;
       case 32: launch_group<T, 32>(ctx, a, sorted, b, e, head, st); break;
+#ifdef OGJK_EXPERIMENTAL
       case 502: rc = launch_cta<T, 2>(ctx, a, sorted, b, e, head, hi, st); break;
       case 504: rc = launch_cta<T, 4>(ctx, a, sorted, b, e, head, hi, st); break;
       case 508: rc = launch_cta<T, 8>(ctx, a, sorted, b, e, head, hi, st); break;
@@ -514,7 +568,9 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
       case 104: rc = launch_staged<T, 4>(ctx, a, sorted, b, e, head, hi, st); break;
       case 108: rc = launch_staged<T, 8>(ctx, a, sorted, b, e, head, hi, st); break;
       case 116: rc = launch_staged<T, 16>(ctx, a, sorted, b, e, head, hi, st); break;
-      default: rc = launch_staged<T, 32>(ctx, a, sorted, b, e, head, hi, st); break;
+      case 132: rc = launch_staged<T, 32>(ctx, a, sorted, b, e, head, hi, st); break;
+#endif
+      default: return fail(OGJK_ERR_ARG, "kernel flavour of the class table is not compiled into this build%s");
     }
     if (rc) return rc;
     mark(ctx, st, 2 + c, 1);
@@ -649,8 +705,8 @@ int host_pipeline_chunked(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const
   const int* dk1 = static_cast<const int*>(ctx->d_cnt1.p);
   const int* dk2 = static_cast<const int*>(ctx->d_cnt2.p);
   ctx->timed_mask = 0;
-  if ((rc = store_build<T>(ctx, &ctx->scratch1, npairs, nverts1, dc1, do1, dk1, false, sc, false))) return rc;
-  if ((rc = store_build<T>(ctx, &ctx->scratch2, npairs, nverts2, dc2, do2, dk2, false, sc, false))) return rc;
+  if ((rc = store_build<T>(ctx, &ctx->scratch1, npairs, nverts1, dc1, do1, dk1, false, sc, false, host_sum(cnt1, npairs)))) return rc;
+  if ((rc = store_build<T>(ctx, &ctx->scratch2, npairs, nverts2, dc2, do2, dk2, false, sc, false, host_sum(cnt2, npairs)))) return rc;
   // Every polytope of a chunk must lie inside the chunk's coordinate range: checked on
   // the device (optimistically -- the verdict is read after the pipeline has drained).
   if ((rc = ctx->counters.reserve(kCounterSlots * sizeof(unsigned long long)))) return rc;
@@ -674,8 +730,8 @@ int host_pipeline_chunked(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const
   for (int c = 0; c < K; ++c) {
     const int64_t lo = r[c].lo, n = r[c].hi - r[c].lo;
     CU(cudaStreamWaitEvent(sc, ctx->chunk_in[c], 0));
-    if ((rc = store_pack_range<T>(ctx, &ctx->scratch1, lo, r[c].hi, dc1, do1, dk1, sc))) return rc;
-    if ((rc = store_pack_range<T>(ctx, &ctx->scratch2, lo, r[c].hi, dc2, do2, dk2, sc))) return rc;
+    if ((rc = store_pack_range<T>(ctx, &ctx->scratch1, lo, r[c].hi, dc1, do1, sc))) return rc;
+    if ((rc = store_pack_range<T>(ctx, &ctx->scratch2, lo, r[c].hi, dc2, do2, sc))) return rc;
     StoreArgs<T> sa;
     sa.s1 = view_of<T>(&ctx->scratch1); sa.s1.boff += lo; sa.s1.cnt += lo;
     sa.s2 = view_of<T>(&ctx->scratch2); sa.s2.boff += lo; sa.s2.cnt += lo;
@@ -709,8 +765,8 @@ int host_pipeline_chunked(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const
   int bad = 0;
   CU(cudaMemcpyAsync(&bad, bad_layout, sizeof(int), cudaMemcpyDeviceToHost, sc));
   CU(cudaStreamSynchronize(so));
-  CU(cudaStreamSynchronize(sc));
   CU(cudaStreamSynchronize(si));
+  if ((rc = pool_verdict(ctx, sc))) return rc;
   return bad ? 1 : OGJK_OK;  // 1: polytopes not in pair order -> caller reruns the one-shot path
 }
 
@@ -757,11 +813,13 @@ int host_pipeline(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t
   }
   ctx->timed_mask = 0;
   if ((rc = store_build<T>(ctx, &ctx->scratch1, npoly1, nverts1, static_cast<const T*>(ctx->d_coords1.p),
-                           static_cast<const int64_t*>(ctx->d_off1.p), static_cast<const int*>(ctx->d_cnt1.p), false, st)))
+                           static_cast<const int64_t*>(ctx->d_off1.p), static_cast<const int*>(ctx->d_cnt1.p), false, st, true,
+                           host_sum(cnt1, npoly1))))
     return rc;
   if (!shared_pool &&
       (rc = store_build<T>(ctx, &ctx->scratch2, npoly2, nverts2, static_cast<const T*>(ctx->d_coords2.p),
-                           static_cast<const int64_t*>(ctx->d_off2.p), static_cast<const int*>(ctx->d_cnt2.p), false, st)))
+                           static_cast<const int64_t*>(ctx->d_off2.p), static_cast<const int*>(ctx->d_cnt2.p), false, st, true,
+                           host_sum(cnt2, npoly2))))
     return rc;
   const int* di1 = idx1 ? static_cast<const int*>(ctx->d_idx1.p) : nullptr;
   const int* di2 = idx2 ? static_cast<const int*>(ctx->d_idx2.p) : nullptr;
@@ -797,8 +855,7 @@ int host_pipeline(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t
   CU(cudaMemcpyAsync(distances, ctx->d_dist.p, (size_t)npairs * sizeof(T), cudaMemcpyDeviceToHost, st));
   if (simplices && run_gjk)
     CU(cudaMemcpyAsync(simplices, ctx->d_simp.p, (size_t)npairs * sizeof(S), cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  return OGJK_OK;
+  return pool_verdict(ctx, st);  // synchronises
 }
 
 template <typename T, typename S>
@@ -941,6 +998,7 @@ int store_create(ogjk_ctx* ctx, int64_t npoly, int64_t nverts, const T* coords, 
   if (on_device) {
     rc = store_build<T>(ctx, s, npoly, nverts, coords, off, cnt, true, st);
     if (!rc) rc = store_build_accel<T>(ctx, s, st);
+    if (!rc) rc = pool_verdict(ctx, st);  // synchronises: the store is complete when the call returns
   } else {
     DevBuf dc, doff, dcnt;
     if (!(rc = dc.reserve((size_t)nverts * 3 * sizeof(T))) && !(rc = doff.reserve((size_t)npoly * sizeof(int64_t))) &&
@@ -955,7 +1013,7 @@ int store_create(ogjk_ctx* ctx, int64_t npoly, int64_t nverts, const T* coords, 
         rc = store_build<T>(ctx, s, npoly, nverts, static_cast<const T*>(dc.p), static_cast<const int64_t*>(doff.p),
                             static_cast<const int*>(dcnt.p), true, st);
         if (!rc) rc = store_build_accel<T>(ctx, s, st);
-        if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(OGJK_ERR_CUDA, "store pack failed%s");
+        if (!rc) rc = pool_verdict(ctx, st);  // synchronises
       }
     }
     dc.release(); doff.release(); dcnt.release();
@@ -1176,6 +1234,8 @@ int store_epa(ogjk_ctx* ctx, const ogjk_store* s1, const int* idx1, const ogjk_s
 
 }  // namespace
 
+#include "multi.cuh"
+
 extern "C" {
 
 const char* ogjk_last_error(void) { return g_err; }
@@ -1206,9 +1266,11 @@ int ogjk_ctx_create(int device, ogjk_ctx** out) {
     e = cudaEventCreateWithFlags(&c->chunk_in[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->chunk_done[i], cudaEventDisableTiming);
   }
+  if (e == cudaSuccess && c->counters.reserve(kCounterSlots * sizeof(unsigned long long)) != OGJK_OK) e = cudaErrorMemoryAllocation;
+  if (e == cudaSuccess) e = cudaMemset(c->counters.p, 0, kCounterSlots * sizeof(unsigned long long));
   if (e != cudaSuccess) {
-    delete c;
-    snprintf(g_err, sizeof(g_err), "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    ogjk_ctx_destroy(c);
+    snprintf(g_err, sizeof(g_err), "context setup failed: %s", cudaGetErrorString(e));
     return OGJK_ERR_CUDA;
   }
   *out = c;
@@ -1240,6 +1302,12 @@ void ogjk_ctx_destroy(ogjk_ctx* c) {
 }
 
 int ogjk_ctx_device(const ogjk_ctx* c) { return c ? c->device : -1; }
+int ogjk_ctx_pool_status(ogjk_ctx* c) {
+  if (!c) return fail(OGJK_ERR_ARG, "ctx is NULL%s");
+  CU(cudaSetDevice(c->device));
+  CU(cudaDeviceSynchronize());
+  return pool_verdict(c, c->own_stream);
+}
 int64_t ogjk_ctx_launch_count(const ogjk_ctx* c) { return c ? c->launches : 0; }
 int ogjk_ctx_set_timing(ogjk_ctx* c, int enable) {
   if (!c) return fail(OGJK_ERR_ARG, "ctx is NULL%s");
@@ -1273,11 +1341,19 @@ int ogjk_ctx_set_classes(ogjk_ctx* c, int n, const int* hi_keys, const int* lane
     const bool pow2 = gl == 1 || gl == 2 || gl == 4 || gl == 8 || gl == 16 || gl == 32;
     bool ok = false;
     if (fam == 0) ok = gl == 0 || pow2;
+#ifdef OGJK_EXPERIMENTAL
     else if (fam == 1) ok = pow2;
     else if (fam == 2) ok = gl == 0 || pow2;
     else if (fam == 3 || fam == 5) ok = gl == 2 || gl == 4 || gl == 8 || gl == 16;
+#else
+    else if (l >= 0 && (fam == 1 || fam == 2 || fam == 3 || fam == 5))
+      return fail(OGJK_ERR_ARG, "experimental kernel flavour: only libopengjk_b200_exp.so (-DOGJK_EXPERIMENTAL) carries it%s");
+#endif
     if (l < 0 || !ok) return fail(OGJK_ERR_ARG, "unknown kernel flavour in class table%s");
-    if (gl == 0 && hi_keys[i] > kSmallKeyMax) return fail(OGJK_ERR_ARG, "register-resident class is limited to key <= 4%s");
+    // the last class is extended to the largest key below, so it is validated against that
+    const int hi = i == n - 1 ? kMaxKey : hi_keys[i];
+    if (gl == 0 && hi > kSmallKeyMax)
+      return fail(OGJK_ERR_ARG, "register-resident class is limited to key <= 4 and cannot be the last (open-ended) class%s");
     if (hi_keys[i] <= prev) return fail(OGJK_ERR_ARG, "class keys must increase%s");
     prev = hi_keys[i];
   }
@@ -1468,6 +1544,9 @@ int ogjk_ctx_set_accel_min(ogjk_ctx* c, int min_vertices) {
 int ogjk_ctx_set_passes(ogjk_ctx* c, int passes, int iters1, int iters2) {
   if (!c || passes < 1 || passes > 3 || iters1 < 1 || iters2 < 1 || iters1 + iters2 >= kMaxIter)
     return fail(OGJK_ERR_ARG, "passes must be 1..3 with 1 <= iters1, iters2 and iters1 + iters2 < 25%s");
+#ifndef OGJK_EXPERIMENTAL
+  if (passes > 1) return fail(OGJK_ERR_ARG, "multi-pass scheduling is compiled into libopengjk_b200_exp.so only%s");
+#endif
   c->passes = passes;
   c->pass_iters[0] = iters1;
   c->pass_iters[1] = iters2;
@@ -1475,7 +1554,7 @@ int ogjk_ctx_set_passes(ogjk_ctx* c, int passes, int iters1, int iters2) {
 }
 
 int ogjk_ctx_set_table_lanes(ogjk_ctx* c, int lanes) {
-  if (!c || (lanes != 8 && lanes != 16 && lanes != 32)) return fail(OGJK_ERR_ARG, "table lanes must be 8, 16 or 32%s");
+  if (!c || (lanes != 0 && lanes != 8 && lanes != 16 && lanes != 32)) return fail(OGJK_ERR_ARG, "table lanes must be 0, 8, 16 or 32%s");
   c->table_lanes = lanes;
   return OGJK_OK;
 }

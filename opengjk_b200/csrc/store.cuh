@@ -168,25 +168,60 @@ check_monotone_kernel(const long long* __restrict__ off, const int* __restrict__
     if (off[p] < off[p - 1] + cnt[p - 1]) *flag = 1;
 }
 
+// ---- pool validation (raw pools come from the caller; nothing below may index out of bounds) ----
+// The store keeps its OWN sanitised copy of the vertex counts: a count outside [1, nverts]
+// becomes 1 and raises *flag (the sticky pool-error flag of the context).
+__global__ void __launch_bounds__(256)
+sanitize_counts_kernel(const int* __restrict__ cnt_in, long long npoly, long long nverts, int* __restrict__ cnt_out,
+                       int* __restrict__ flag) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long h = (long long)blockIdx.x * blockDim.x + threadIdx.x; h < npoly; h += stride) {
+    int n = cnt_in[h];
+    if (n < 1 || (long long)n > nverts) { n = 1; *flag = 1; }
+    cnt_out[h] = n;
+  }
+}
+// Asynchronous builds size the block array from an upper bound (nverts + 3 per polytope), which
+// holds only when the polytopes' vertex ranges do not add up to more than nverts (no sharing).
+// When the scanned total exceeds the allocation every polytope is collapsed onto one dummy
+// 4-vertex block at offset 0 (defined results, no out-of-bounds access) and *flag is raised.
+__global__ void __launch_bounds__(256)
+overflow_guard_kernel(const long long* __restrict__ total, long long capacity, long long npoly, int* __restrict__ cnt,
+                      long long* __restrict__ boff, int* __restrict__ flag) {
+  if (*total <= capacity) return;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long h = (long long)blockIdx.x * blockDim.x + threadIdx.x; h < npoly; h += stride) {
+    cnt[h] = 1;
+    boff[h] = 0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *flag = 1;
+}
+
 // ---- repack: xyz-interleaved blocks -> padded SoA blocks ------------------------
 // Eight lanes per polytope, four polytopes per warp, warp-strided over polytopes.
+// `cnt` is the store's sanitised copy.  A polytope whose source range leaves [0, nverts)
+// is packed as zeros and raises *flag.
 template <typename T>
 __global__ void __launch_bounds__(256)
 pack_kernel(const T* __restrict__ coords, const long long* __restrict__ off, const int* __restrict__ cnt,
-            long long npoly, const long long* __restrict__ boff, T* __restrict__ out) {
+            long long npoly, const long long* __restrict__ boff, T* __restrict__ out, long long nverts,
+            int* __restrict__ flag) {
   const int sub = threadIdx.x & 7;
   const long long first = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   const long long stride = ((long long)gridDim.x * blockDim.x) >> 3;
   for (long long h = first; h < npoly; h += stride) {
     const int n = cnt[h];
     const int np = pad4(n);
-    const T* src = coords + 3 * off[h];
+    const long long o = off[h];
+    const bool ok = o >= 0 && o + n <= nverts;
+    if (!ok && sub == 0) *flag = 1;
+    const T* src = coords + 3 * (ok ? o : 0);
     T* dst = out + boff[h];
     for (int i = sub; i < np; i += 8) {
       const int j = i < n ? i : 0;  // padding repeats vertex 0
-      dst[i] = src[3 * j];
-      dst[np + i] = src[3 * j + 1];
-      dst[2 * np + i] = src[3 * j + 2];
+      dst[i] = ok ? src[3 * j] : (T)0;
+      dst[np + i] = ok ? src[3 * j + 1] : (T)0;
+      dst[2 * np + i] = ok ? src[3 * j + 2] : (T)0;
     }
   }
 }

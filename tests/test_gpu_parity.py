@@ -28,6 +28,15 @@ def eng():
     e.close()
 
 
+@pytest.fixture(scope="module")
+def eng_exp():
+    """Engine over libopengjk_b200_exp.so: same ABI plus the measured-and-lost kernel flavours."""
+    from opengjk_b200 import _lib
+    e = api.Engine(0, lib_path=_lib.EXP_LIB_PATH)
+    yield e
+    e.close()
+
+
 def _assert_same(name, d, s, dref, sref, prec):
     # tolerance form of the bar first (readable failure), then byte equality
     ok = ~np.isnan(dref)
@@ -110,8 +119,16 @@ DEFAULT_CLASSES = [(4, 0), (32, 2), (128, 8), (2048, 32)]
 
 
 @pytest.mark.parametrize("prec,dt", PRECS)
-def test_scheduler_classes_do_not_change_results(eng, prec, dt):
-    """Any lanes-per-pair choice (1..32, register-resident or not) gives the same bytes."""
+def test_scheduler_classes_do_not_change_results(eng, eng_exp, prec, dt):
+    """Any lanes-per-pair choice (1..32, register-resident or not) gives the same bytes; the
+    experimental flavours (staged, persistent, scan-assist, CTA-per-pair) are swept in the
+    -DOGJK_EXPERIMENTAL build and rejected by the product library."""
+    with pytest.raises(api.OpenGJKError):
+        eng.set_classes([(80, 108), (2048, 32)])
+    with pytest.raises(api.OpenGJKError):
+        eng.set_classes([(4, 0)])  # the last class is open-ended: it cannot be the register-resident kernel
+    plain = eng
+    eng = eng_exp
     w = W.random_hulls(30000, 1, 150, 55, 3.0, dt)
     base = _gpu(eng, w, api.MODE_THREAD)
     tables = [[(2048, g)] for g in (1, 2, 4, 8, 16, 32)] + [
@@ -131,8 +148,13 @@ def test_scheduler_classes_do_not_change_results(eng, prec, dt):
             eng.set_classes(t)
             d, s = _gpu(eng, w, api.MODE_AUTO)
             _assert_same(f"classes{t}", d, s, base[0], base[1], prec)
+        for t in tables[:9]:  # the plain flavours through the product library as well
+            plain.set_classes(t)
+            d, s = _gpu(plain, w, api.MODE_AUTO)
+            _assert_same(f"product classes{t}", d, s, base[0], base[1], prec)
     finally:
         eng.set_classes(DEFAULT_CLASSES)
+        plain.set_classes(DEFAULT_CLASSES)
 
 
 @pytest.mark.parametrize("prec,dt", PRECS)
@@ -271,9 +293,11 @@ def test_chunk_pipelined_host_path(eng, prec, dt):
 
 
 @pytest.mark.parametrize("prec,dt", PRECS)
-def test_multi_pass_scheduling_is_invisible(eng, prec, dt):
+def test_multi_pass_scheduling_is_invisible(eng_exp, prec, dt):
     """Pairs parked after a few iterations and resumed in later passes give the one-pass bytes, for
-    every split of the iteration budget (including parking after every single iteration)."""
+    every split of the iteration budget (including parking after every single iteration).
+    Experimental build only (the flavour lost to the one-pass kernel on B200)."""
+    eng = eng_exp
     o = Oracle(prec)
     ws = [W.mixed_hulls(30000, seed=71, dtype=dt), W.random_hulls(6000, 40, 200, 72, 3.0, dt), W.tiny_bodies(60, 73, 1.0, dt)]
     refs = [o.batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1) for w in ws]

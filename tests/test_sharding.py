@@ -1,5 +1,5 @@
-"""Multi-GPU host logic on CPU: two gloo ranks shard a pair list the way bench.py
-does (contiguous slice per rank, no data-path collective), each computes its slice
+"""Multi-GPU host logic on CPU: two gloo ranks shard a pair list with the library's own
+partition function (contiguous slice per rank, no data-path collective), each computes its slice
 (with the CPU oracle standing in for the device), and an all_gather reassembles
 results identical to the single-process run.  Also checks the max-over-ranks timing
 reduction bench.py uses."""
@@ -17,10 +17,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def shard_bounds(npairs, world, rank):
-    """Contiguous slice of the pair list owned by `rank`."""
-    base, extra = divmod(npairs, world)
-    lo = rank * base + min(rank, extra)
-    return lo, lo + base + (1 if rank < extra else 0)
+    """Contiguous slice of the pair list owned by `rank`: the LIBRARY's partition
+    (ogjk_multi_shard_bounds, csrc/multi.cuh) -- the same function the multi-GPU entry points
+    and bench.py use.  Pure host arithmetic, callable without a GPU."""
+    sys.path.insert(0, ROOT)
+    from opengjk_b200 import api
+    return api.shard_bounds(npairs, world, rank)
 
 
 def _worker(rank, world, port, npairs, out_path):
@@ -52,7 +54,7 @@ def _worker(rank, world, port, npairs, out_path):
 
 
 def test_shard_bounds_cover_exactly():
-    for n in (0, 1, 7, 1000, 1001):
+    for n in (0, 1, 7, 1000, 1001, 100_000_000, 2**31 + 5):
         for world in (1, 2, 3, 8):
             spans = [shard_bounds(n, world, r) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == n
