@@ -1,25 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- GJK pair-queries/sec on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--extra a,b|none]
+                    [--impl reference]
 
-A "step" is one pass of the batched GJK hot path over one batch of synthetic
-pairs.  Default workload = BASELINE.json configs[1]: 1 M random convex-hull
-pairs, 8-64 vertices, fp64 (per GPU; weak scaling, each rank owns its own
-contiguous slice of pairs, no data-path collective).
+A "step" is one pass of the batched GJK hot path over one batch of synthetic pairs.
+Main workload = BASELINE.json configs[1]: 1 M random convex-hull pairs, 8-64 vertices,
+fp64, per GPU (weak scaling: every rank owns its own contiguous slice of the job, no
+data-path collective).  By default the other north-star configurations are measured in
+the same run and reported under `other_workloads`:
+  boxes100m_f32        config 3: ONE 100 M-pair oriented-box batch split over the N GPUs (strong)
+  hulls1k_f32          config 4a: 1000-vertex hulls (the ">= 70 % of HBM" target)
+  hulls1k10k_full_f32  config 4: 1 M indexed pairs over 8192 hulls with 1 k-10 k vertices
+  epa10m_f32           config 5: 10 M intersecting pairs, GJK + EPA
 
 Printed JSON line (rank 0):
-  value      whole-job pairs/s with inputs resident in HBM (CUDA events on the
-             launching stream, barrier + synchronize on both sides, max over ranks)
-  e2e        same metric through the host-buffer C-ABI call (ogjk_gjk_host_*):
-             pinned host inputs -> H2D -> kernels -> D2H of distances + gkSimplex
+  value      whole-job pairs/s with inputs resident in HBM (CUDA events on the launching
+             stream, barrier + synchronize on both sides, max over ranks)
+  e2e        same metric through the host-buffer C-ABI call: pinned host inputs -> H2D ->
+             kernels -> D2H of distances + gkSimplex, with a bare-copy probe beside it
   roofline   dominant kernel vs the measured HBM peak (MEASURED_PEAKS.json)
-  cpu_baseline  the reference scalar library (oracle/_ref) or the oracle port on
-             the box's host cores, bounded sample
-`--impl reference` times the reference CPU implementation alone.
+  cpu_baseline  the unmodified reference scalar library (oracle/_ref) on the box's host
+             cores (all cores and one thread), bounded strided sample
+`--impl reference` times the reference CPU implementation alone on the same workload.
 """
 import argparse
-import ctypes
+import contextlib
 import json
 import os
 import subprocess
@@ -37,37 +43,60 @@ from opengjk_b200 import workloads as W  # noqa: E402
 L2_BYTES = 126e6
 # scheduler table: (hi_key, lanes per pair); key = (pad4(n1)+pad4(n2))/4; lanes 0 = register-resident kernel
 CLASS_TABLE = [(4, 0), (32, 2), (128, 8), (2048, 32)]
+DEFAULT_EXTRAS = ["boxes100m_f32", "hulls1k_f32", "hulls1k10k_full_f32", "epa10m_f32"]
 
 WORKLOADS = {
-    # name: (description, dtype, maker(npairs, seed), default pairs per GPU[, epa])
+    # name: (description, dtype, maker(npairs, seed) or None for device-generated, default pairs[, epa])
     "hulls64_f64": ("config2: random convex-hull pairs, 8-64 vertices, fp64", np.float64,
                     lambda n, seed: W.mixed_hulls(n, 8, 64, seed, np.float64), 1_000_000),
     "hulls64_f32": ("config2 in fp32: random convex-hull pairs, 8-64 vertices", np.float32,
                     lambda n, seed: W.mixed_hulls(n, 8, 64, seed, np.float32), 1_000_000),
-    "boxes_f32": ("config3: oriented box-box (8-vertex) pairs, fp32", np.float32,
+    "boxes_f32": ("config3 (8 M sample): oriented box-box (8-vertex) pairs, fp32", np.float32,
                   lambda n, seed: W.boxes(n, True, seed, dtype=np.float32), 8_000_000),
     "boxes_aligned_f32": ("config3a: axis-aligned unit cubes (tie stress), fp32", np.float32,
                           lambda n, seed: W.boxes(n, False, seed, dtype=np.float32), 8_000_000),
     "hulls1k_f32": ("config4a: indexed pairs of 1000-vertex hulls, fp32", np.float32,
                     lambda n, seed: W.large_hull_pool(n, 32768, 1000, 1000, seed, dtype=np.float32), 200_000),
-    "hulls1k10k_f32": ("config4: indexed pairs of 1k-10k-vertex hulls, fp32", np.float32,
+    "hulls1k_f64": ("config4a in fp64: indexed pairs of 1000-vertex hulls", np.float64,
+                    lambda n, seed: W.large_hull_pool(n, 16384, 1000, 1000, seed, dtype=np.float64), 100_000),
+    "hulls1k10k_f32": ("config4 (small pool): indexed pairs of 1k-10k-vertex hulls, fp32", np.float32,
                        lambda n, seed: W.large_hull_pool(n, 2048, 1000, 10000, seed, dtype=np.float32), 50_000),
-    "hulls1k10k_full_f32": ("config4 at full size: 1 M indexed pairs over a pool of 8192 hulls with 1k-10k vertices (540 MB), fp32",
+    "hulls1k10k_full_f32": ("config4: 1 M indexed pairs over a pool of 8192 hulls with 1k-10k vertices (540 MB), fp32",
                             np.float32, lambda n, seed: W.large_hull_pool(n, 8192, 1000, 10000, seed, dtype=np.float32), 1_000_000),
-    "boxes100m_f32": ("config3 at full size: 100 M oriented box-box pairs generated on the device, fp32", np.float32,
+    "boxes100m_f32": ("config3: 100 M oriented box-box pairs generated on the device, fp32", np.float32,
                       None, 100_000_000),
-    "epa_f32": ("config5: intersecting 8-64-vertex hull pairs, GJK + EPA, fp32", np.float32,
+    "epa_f32": ("config5 (1 M sample): intersecting 8-64-vertex hull pairs, GJK + EPA, fp32", np.float32,
                 lambda n, seed: W.random_hulls(n, 8, 64, seed, 1.0, np.float32, 0.5), 1_000_000, True),
+    "epa10m_f32": ("config5: 10 M intersecting 8-64-vertex hull pairs generated on the device, GJK + EPA, fp32", np.float32,
+                   None, 10_000_000, True),
+}
+STRONG = {"boxes100m_f32"}  # ONE batch of the stated size split over the ranks (everything else: per-rank size)
+
+# What limits each kernel, with the figures of the committed ncu capture (profiles/): the
+# HBM fraction is always reported, but only the large-hull kernels are HBM-shaped.
+NCU_NOTES = {
+    "hulls64_f64": {"limiter": "issue slots / FP64 pipe / warp divergence (not HBM-bound)",
+                    "lanes_active": 13.3, "issue_active_pct": 40.7, "pipe_pct": {"fp64": 30.3},
+                    "source": "profiles/r1k_hulls64_f64_ncu_summary.txt"},
+    "boxes100m_f32": {"limiter": "issue slots / warp divergence (not HBM-bound)", "lanes_active": 11.3,
+                      "issue_active_pct": 68.0, "pipe_pct": {"alu": 53.0, "fma": 34.0},
+                      "source": "profiles/r1d_boxes_f32_ncu_summary.txt"},
+    "epa10m_f32": {"limiter": "issue slots / shared-memory latency (not HBM-bound)", "lanes_active": 20.5,
+                   "issue_active_pct": 69.0, "source": "profiles/r1d_epa_f32_ncu_summary.txt"},
 }
 
 
 def traffic_for(name):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    try:
-        return json.load(open(p)).get(name)
-    except Exception:
-        return None
+    """DRAM bytes per launch of the dominant kernel from the committed ncu captures, with the file it came from."""
+    for f in ("r2_traffic.json", "r1_traffic.json"):
+        p = os.path.join(ROOT, "profiles", f)
+        try:
+            v = json.load(open(p)).get(name)
+        except Exception:
+            v = None
+        if v is not None:
+            return v, f"profiles/{f} (ncu --set full capture of the same kernel, committed; not measured in this run)"
+    return None, None
 
 
 def peaks():
@@ -78,6 +107,22 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+@contextlib.contextmanager
+def quiet_stdout():
+    """The reference prints a banner on its iteration-cap path; keep it out of our stdout
+    (and its terminal cost out of the CPU timing) while reference code runs."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    null = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(null, 1)
+    try:
+        yield
+    finally:
+        os.dup2(saved, 1)
+        os.close(null)
+        os.close(saved)
 
 
 class ClockSampler:
@@ -138,65 +183,123 @@ class ClockSampler:
                 "reasons": [n for n, b in self.REASONS.items() if self.bits & b], "samples": len(sm)}
 
 
-def cpu_baseline(w, prec, budget_s=10.0):
-    """Reference scalar library (or the oracle port) on all host cores, bounded sample."""
-    from oracle.pyoracle import Oracle, Reference
-    cores = os.cpu_count() or 1
-    n = min(w.npairs, 100_000)
-    if Reference.available(prec):
-        kind, ref = "reference", Reference(prec)
-        prep = Reference.Prepared(ref, w.coords, w.off, w.cnt, w.pa[:n], w.pb[:n])
-        run = lambda: prep.run(cores)
-    else:
-        kind, o = "port", Oracle(prec)
-        run = lambda: o.batch(w.coords, w.off, w.cnt, w.pa[:n], w.pb[:n], nthreads=cores)
+def strided_sample(w, m):
+    """m pairs of the workload taken at a fixed stride (keeps the mix of a workload built from slices)."""
+    if w.npairs <= m:
+        return w, f"all {w.npairs} pairs"
+    st = w.npairs // m
+    return W.Workload(w.name, w.coords, w.off, w.cnt, w.pa[::st][:m].copy(), w.pb[::st][:m].copy()), \
+        f"{m} pairs at stride {st} over the workload"
+
+
+def _timed_passes(run, n, budget_s, max_reps=20000):
     run()  # warm
     t0 = time.perf_counter()
     reps = 0
     while True:
         run()
         reps += 1
-        if time.perf_counter() - t0 > budget_s or reps >= 20000:
+        if time.perf_counter() - t0 > budget_s or reps >= max_reps:
             break
     dt = time.perf_counter() - t0
-    return {"value": n * reps / dt, "unit": "pairs/s", "cores": cores, "kind": kind,
-            "sample": f"first {n} pairs of the workload x {reps} passes ({dt:.1f} s), OpenMP split over pairs"}
+    return n * reps / dt, reps, dt
+
+
+def cpu_baseline(w, prec, budget_s=10.0, epa=False, sample_note=None):
+    """The reference's scalar code (oracle/_ref; the oracle port when it is absent or for EPA,
+    which the reference has only in CUDA) on the host cores: all cores and one thread."""
+    from oracle.pyoracle import Oracle, Reference
+    cores = os.cpu_count() or 1
+    ws, note = strided_sample(w, 20_000 if epa else 100_000)
+    note = sample_note or note
+    n = ws.npairs
+    if epa:
+        kind, o = "port", Oracle(prec)
+        run = lambda nt: (lambda: o.gjk_epa_batch(ws.coords, ws.off, ws.cnt, ws.pa, ws.pb, nthreads=nt))
+    elif Reference.available(prec):
+        kind, ref = "reference", Reference(prec)
+        prep = Reference.Prepared(ref, ws.coords, ws.off, ws.cnt, ws.pa, ws.pb)
+        run = lambda nt: (lambda: prep.run(nt))
+    else:
+        kind, o = "port", Oracle(prec)
+        run = lambda nt: (lambda: o.batch(ws.coords, ws.off, ws.cnt, ws.pa, ws.pb, nthreads=nt))
+    with quiet_stdout():
+        v_all, reps, dt = _timed_passes(run(cores), n, budget_s)
+        # one thread: a 1/8 slice of the sample, a quarter of the budget
+        m1 = max(1, n // 8)
+        w1 = W.Workload(ws.name, ws.coords, ws.off, ws.cnt, ws.pa[:m1 * 8:8].copy(), ws.pb[:m1 * 8:8].copy())
+        if epa:
+            run1 = lambda: o.gjk_epa_batch(w1.coords, w1.off, w1.cnt, w1.pa, w1.pb, nthreads=1)
+        elif kind == "reference":
+            prep1 = Reference.Prepared(ref, w1.coords, w1.off, w1.cnt, w1.pa, w1.pb)
+            run1 = lambda: prep1.run(1)
+        else:
+            run1 = lambda: o.batch(w1.coords, w1.off, w1.cnt, w1.pa, w1.pb, nthreads=1)
+        v_one, reps1, dt1 = _timed_passes(run1, w1.npairs, max(1.0, budget_s / 4))
+    return {"value": v_all, "unit": "pairs/s", "cores": cores, "kind": kind,
+            "sample": f"{note} x {reps} passes ({dt:.1f} s), OpenMP split over pairs"
+                      + (" (GJK + EPA restatement: the reference has no CPU EPA)" if epa else ""),
+            "single_thread": {"value": v_one, "unit": "pairs/s", "cores": 1,
+                              "sample": f"{w1.npairs} pairs (every 8th of the sample) x {reps1} passes ({dt1:.1f} s)"},
+            "simd_baseline": "unavailable (Google Highway is not present offline; simd/CMakeLists.txt:58-75 fetches it)"}
+
+
+def config_of(name, n_total, world):
+    """The `config` object: identical for our arm and the reference arm."""
+    desc = WORKLOADS[name][0]
+    return {"workload": desc, "pairs_per_step": int(n_total), "pairs_per_gpu": int(n_total // max(world, 1)),
+            "precision": "f64" if WORKLOADS[name][1] == np.float64 else "f32", "seed": 42}
 
 
 def run_reference_arm(args, rank, world):
-    """--impl reference: the reference's own CPU implementation, rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on the SAME workload
+    (same generator, seed, pair count per GPU and mix), all host threads, rank 0 only."""
     if rank != 0:
         return
-    desc, dt, maker, default_pairs = WORKLOADS[args.workload][:4]
+    name = args.workload
+    desc, dt, maker, default_pairs = WORKLOADS[name][:4]
+    epa = len(WORKLOADS[name]) > 4 and WORKLOADS[name][4]
     prec = "f64" if dt == np.float64 else "f32"
     from oracle.pyoracle import Oracle, Reference
     cores = os.cpu_count() or 1
-    n = min(args.pairs or default_pairs, args.ref_sample)
-    maker = maker or (lambda n_, seed_: W.boxes(n_, True, seed_, dtype=np.float32))  # device-generated workloads
-    w = maker(n, args.seed)
-    if Reference.available(prec):
+    n = args.pairs or default_pairs
+    # one GPU's share of the job per step (weak scaling: every GPU adds its own n pairs)
+    n_step = min(n, args.ref_sample) if args.ref_sample else n
+    if maker is None:  # device-generated workloads: the host construction of the same distribution
+        maker = (lambda n_, s_: W.random_hulls(n_, 8, 64, s_, 1.0, np.float32, 0.5)) if epa else \
+            (lambda n_, s_: W.boxes(n_, True, s_, dtype=np.float32))
+        n_step = min(n_step, 2_000_000)
+    w = maker(n_step, args.seed)
+    if epa:
+        kind, o = "port", Oracle(prec)
+        run = lambda: o.gjk_epa_batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=cores)
+    elif Reference.available(prec):
         kind, ref = "reference", Reference(prec)
         prep = Reference.Prepared(ref, w.coords, w.off, w.cnt, w.pa, w.pb)
         run = lambda: prep.run(cores)
     else:
         kind, o = "port", Oracle(prec)
         run = lambda: o.batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=cores)
-    for _ in range(args.warmup):
-        run()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        run()
-    dt_s = time.perf_counter() - t0
-    v = n * args.steps / dt_s
+    with quiet_stdout():
+        for _ in range(args.warmup):
+            run()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            run()
+        dt_s = time.perf_counter() - t0
+    v = n_step * args.steps / dt_s
+    sample = (f"the full per-GPU batch ({n_step} pairs) per step" if n_step == n else f"{n_step} of {n} pairs per step")
     line = {
         "impl": "reference", "metric": "gjk_pair_queries_per_sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt_s / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": prec, "data": "synthetic",
-        "config": {"workload": desc, "pairs_per_step": n, "note": "CPU reference, bounded sample of the workload"},
+        "config": config_of(name, n * max(args.gpus, 1), max(args.gpus, 1)),
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind,
-                         "sample": f"{n} pairs per step, all host threads (OpenMP static split over pairs)"},
+                         "sample": f"{sample}, all host threads (OpenMP dynamic split over pairs); one host serves the whole job"},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "unmodified scalar/openGJK.c (oracle/_ref) called once per pair through compute_minimum_distance; "
+                "the host's cores do not grow with --gpus, so this rate is the same at every N",
     }
     print(json.dumps(line), flush=True)
 
@@ -210,9 +313,12 @@ def main():
     ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (default: the workload's full size)")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-sample", type=int, default=200_000)
+    ap.add_argument("--ref-sample", type=int, default=0, help="reference arm: cap on pairs per step (0 = the full batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--extra", default="", help="comma list of further workloads reported under other_workloads")
+    ap.add_argument("--extra", default=None,
+                    help="comma list of further workloads reported under other_workloads "
+                         f"(default: {','.join(DEFAULT_EXTRAS)} when --workload is the default; 'none' disables)")
+    ap.add_argument("--no-multi", action="store_true", help="skip the one-process MultiEngine measurement at N > 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -224,6 +330,14 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    if args.extra is None:
+        extras = list(DEFAULT_EXTRAS) if (args.workload == "hulls64_f64" and not args.pairs) else []
+    else:
+        extras = [x for x in args.extra.split(",") if x and x != "none"]
+    for x in extras:
+        if x not in WORKLOADS:
+            raise SystemExit(f"unknown workload {x}")
+
     import torch
     import torch.distributed as dist
     from opengjk_b200 import api
@@ -232,14 +346,22 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")  # host-side barrier for the phases where only rank 0 drives the GPUs
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     eng = api.Engine(local_rank)
     if os.environ.get("OGJK_CLASSES"):  # e.g. "4:0,24:4,64:8,192:16,2048:32"
@@ -247,42 +369,144 @@ def main():
     eng.set_classes(CLASS_TABLE)
     if os.environ.get("OGJK_ACCEL_MIN"):  # tuning hook: 0 = no cluster tables in the resident store
         eng.set_accel_min(int(os.environ["OGJK_ACCEL_MIN"]))
-    if os.environ.get("OGJK_PASSES"):  # e.g. "2:4:3" = passes:iters1:iters2
-        eng.set_passes(*[int(x) for x in os.environ["OGJK_PASSES"].split(":")])
     if os.environ.get("OGJK_TABLE_LANES"):
         eng.set_table_lanes(int(os.environ["OGJK_TABLE_LANES"]))
     hbm_peak, peak_src = peaks()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
 
-    def measure(name, pairs, steps, warmup, with_cpu):
+    # ---- bare pinned-copy probe: the same H2D + D2H byte counts, no kernels -----------------
+    def copy_probe(h2d_bytes, d2h_bytes, reps=3):
+        """Wall time of moving h2d_bytes in and d2h_bytes out over this GPU's PCIe link on two
+        streams (full duplex), capped at 1 GiB buffers walked repeatedly; every rank at once."""
+        cap = 1 << 30
+        hb, db = min(int(h2d_bytes), cap), min(int(d2h_bytes), cap)
+        h_in = torch.empty(max(hb, 1), dtype=torch.uint8).pin_memory()
+        h_out = torch.empty(max(db, 1), dtype=torch.uint8).pin_memory()
+        d_in = torch.empty(max(hb, 1), dtype=torch.uint8, device=dev)
+        d_out = torch.empty(max(db, 1), dtype=torch.uint8, device=dev)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+        def once():
+            left_in, left_out = int(h2d_bytes), int(d2h_bytes)
+            with torch.cuda.stream(s_in):
+                while left_in > 0:
+                    k = min(left_in, hb)
+                    d_in[:k].copy_(h_in[:k], non_blocking=True)
+                    left_in -= k
+            with torch.cuda.stream(s_out):
+                while left_out > 0:
+                    k = min(left_out, db)
+                    h_out[:k].copy_(d_out[:k], non_blocking=True)
+                    left_out -= k
+            s_in.synchronize()
+            s_out.synchronize()
+        once()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            once()
+        barrier()
+        return max_over_ranks((time.perf_counter() - t0) / reps)
+
+    # ---- device-side generators (inputs never exist on the host) -----------------------------
+    def device_boxes(n, seed):
+        """Config #3 inputs generated on the GPU in 10 M-pair slabs (same construction as
+        workloads.boxes: half-extents U[0.5,1.5], uniform random rotation, body 2 offset 6(u-0.5))."""
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+        coords = torch.empty(2 * n * 8 * 3, dtype=torch.float32, device=dev)
+        box = torch.tensor(W._BOX, dtype=torch.float32, device=dev)
+        slab = 10_000_000
+        for lo in range(0, n, slab):
+            m = min(slab, n - lo)
+            nb = 2 * m
+            half = 0.5 + torch.rand((nb, 1, 3), generator=g, device=dev)
+            q = torch.randn((nb, 4), generator=g, device=dev)
+            q = q / q.norm(dim=1, keepdim=True)
+            qw, qx, qy, qz = q.unbind(1)
+            rot = torch.stack([1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw),
+                               2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw),
+                               2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)], 1).view(nb, 3, 3)
+            pts = torch.einsum("bij,bvj->bvi", rot, box[None] * half)
+            shift = torch.zeros((nb, 1, 3), device=dev)
+            shift[1::2, 0] = 6.0 * (torch.rand((m, 3), generator=g, device=dev) - 0.5)
+            coords[2 * lo * 24:2 * (lo + m) * 24] = (pts + shift).reshape(-1)
+            del half, q, rot, pts, shift
+        cnt = torch.full((2 * n,), 8, dtype=torch.int32, device=dev)
+        off = torch.arange(2 * n, dtype=torch.int64, device=dev) * 8
+        pa = torch.arange(0, 2 * n, 2, dtype=torch.int32, device=dev)
+        return coords, off, cnt, pa, pa + 1
+
+    def device_hulls(n, seed, nmin=8, nmax=64, center_scale=1.0, radius_jitter=0.5):
+        """Config #5 inputs generated on the GPU in 1 M-pair slabs (same construction as
+        workloads.random_hulls: U{8..64} vertices on a sphere of radius 1 + 0.5u, body 2 centred
+        at (u - 0.5) per axis; computed in fp64, rounded once to fp32)."""
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+        cnt = torch.randint(nmin, nmax + 1, (2 * n,), generator=g, device=dev, dtype=torch.int32)
+        off = torch.cumsum(cnt.to(torch.int64), 0) - cnt
+        total = int(off[-1].item()) + int(cnt[-1].item())
+        coords = torch.empty(total * 3, dtype=torch.float32, device=dev)
+        slab = 1_000_000
+        for lo in range(0, n, slab):
+            m = min(slab, n - lo)
+            k = cnt[2 * lo:2 * (lo + m)].to(torch.int64)
+            v0 = int(off[2 * lo].item())
+            nv = int(k.sum().item())
+            pid = torch.repeat_interleave(torch.arange(2 * m, device=dev), k)
+            u = torch.rand((nv, 2), generator=g, device=dev, dtype=torch.float64)
+            z = 2.0 * u[:, 0] - 1.0
+            th = 2.0 * np.pi * u[:, 1]
+            r = torch.sqrt(torch.clamp(1.0 - z * z, min=0.0))
+            rad = 1.0 + radius_jitter * torch.rand(2 * m, generator=g, device=dev, dtype=torch.float64)
+            centre = torch.zeros((2 * m, 3), device=dev, dtype=torch.float64)
+            centre[1::2] = center_scale * (torch.rand((m, 3), generator=g, device=dev, dtype=torch.float64) - 0.5)
+            pts = torch.stack([r * torch.cos(th), r * torch.sin(th), z], 1) * rad[pid, None] + centre[pid]
+            coords[3 * v0:3 * (v0 + nv)] = pts.to(torch.float32).reshape(-1)
+            del pid, u, z, th, r, rad, centre, pts
+        pa = torch.arange(0, 2 * n, 2, dtype=torch.int32, device=dev)
+        return coords, off, cnt, pa, pa + 1
+
+    def measure(name, pairs, steps, warmup, with_cpu, cpu_budget):
         desc, dt, maker, default_pairs = WORKLOADS[name][:4]
         epa = len(WORKLOADS[name]) > 4 and WORKLOADS[name][4]
         prec = "f64" if dt == np.float64 else "f32"
-        n = pairs or default_pairs
-        w = maker(n, args.seed + rank)  # each rank owns its own slice of the job
         sdt = api.SIMPLEX_F64 if prec == "f64" else api.SIMPLEX_F32
-
-        # ---- pinned host copies (e2e inputs) and device-resident copies (value) ----
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        h_coords, h_off, h_cnt, h_pa, h_pb = pin(w.coords.reshape(-1)), pin(w.off), pin(w.cnt), pin(w.pa), pin(w.pb)
-        h_dist = torch.empty(n, dtype=h_coords.dtype).pin_memory()
-        h_simp = torch.empty(n * sdt.itemsize, dtype=torch.uint8).pin_memory()
-        d_coords, d_off, d_cnt, d_pa, d_pb = (t.to(dev) for t in (h_coords, h_off, h_cnt, h_pa, h_pb))
-        d_dist = torch.empty(n, dtype=h_coords.dtype, device=dev)
-        d_simp = torch.empty(n * sdt.itemsize, dtype=torch.uint8, device=dev)
+        tdt = torch.float64 if prec == "f64" else torch.float32
+        strong = name in STRONG
+        n_total = (pairs or default_pairs) * (1 if strong else world)
+        if strong:
+            lo, hi = api.shard_bounds(n_total, world, rank)  # the library's partition of ONE batch
+            n = hi - lo
+        else:
+            n = pairs or default_pairs
         stream = torch.cuda.current_stream().cuda_stream
-        in_bytes = sum(t.numel() * t.element_size() for t in (h_coords, h_off, h_cnt, h_pa, h_pb))
-        out_bytes = h_dist.numel() * h_dist.element_size() + h_simp.numel()
+        w = None
+        if maker is not None:
+            w = maker(n, args.seed + rank)  # each rank owns its own slice of the job
+            h_coords, h_off, h_cnt, h_pa, h_pb = pin(w.coords.reshape(-1)), pin(w.off), pin(w.cnt), pin(w.pa), pin(w.pb)
+            d_coords, d_off, d_cnt, d_pa, d_pb = (t.to(dev) for t in (h_coords, h_off, h_cnt, h_pa, h_pb))
+            alg_bytes = w.algorithmic_bytes()
+        else:
+            gen = device_hulls if epa else device_boxes
+            d_coords, d_off, d_cnt, d_pa, d_pb = gen(n, args.seed + 1000 * rank)
+            verts = d_coords.numel() // 3
+            alg_bytes = verts * 3 * 4 + n * (108 + 4)
+        in_bytes = int(sum(t.numel() * t.element_size() for t in (d_coords, d_off, d_cnt, d_pa, d_pb)))
+        d_dist = torch.empty(n, dtype=tdt, device=dev)
+        d_simp = torch.empty(n * sdt.itemsize, dtype=torch.uint8, device=dev)
+        if epa:
+            d_w1, d_w2, d_nr = (torch.empty(n * 3, dtype=tdt, device=dev) for _ in range(3))
+            alg_bytes += n * 36
 
-        # The engine's device-resident format is the packed polytope store (built once,
-        # outside the timed region -- the counterpart of the reference's
-        # allocate_and_copy_device_arrays); a step is one ogjk_store_gjk_* call over it.
+        # The engine's device-resident format is the packed polytope store (built once, outside the
+        # timed region -- the counterpart of the reference's allocate_and_copy_device_arrays); a step
+        # is one ogjk_store_gjk_* (ogjk_store_gjk_epa_*) call over it.
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         store = eng.store_create(d_coords, d_off, d_cnt, stream)
         torch.cuda.synchronize()
         store_build_ms = 1e3 * (time.perf_counter() - t0)
-
-        if epa:
-            d_w1, d_w2, d_nr = (torch.empty(n * 3, dtype=h_coords.dtype, device=dev) for _ in range(3))
 
         def step():
             if epa:
@@ -315,25 +539,23 @@ def main():
                 step()
                 torch.cuda.synchronize()
                 time.sleep(0)  # let the sampler thread run
-        ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_max = float(t.item())
-        value = n * world * steps / (ms_max * 1e-3)
+        ms_max = max_over_ranks(e0.elapsed_time(e1))
+        value = n_total * steps / (ms_max * 1e-3)
 
         # same job starting from the raw xyz-interleaved arrays (repack inside the step)
-        raw_ms = float("nan")
-        if not epa:
+        raw = None
+        if not epa and in_bytes < 8e9:
             for _ in range(2):
                 step_from_raw()
             torch.cuda.synchronize()
+            reps = max(2, steps // 2)
             e0.record()
-            for _ in range(max(2, steps // 2)):
+            for _ in range(reps):
                 step_from_raw()
             e1.record()
             torch.cuda.synchronize()
-            raw_ms = e0.elapsed_time(e1) / max(2, steps // 2)
+            raw_ms = e0.elapsed_time(e1) / reps
+            raw = {"value": n * world / (raw_ms * 1e-3), "ms_per_step": raw_ms, "note": "repack into the store inside the step"}
 
         # ---- per-phase durations (events around each launch, same stream) -----------
         eng.set_timing(True)
@@ -347,11 +569,11 @@ def main():
         eng.set_timing(False)
         class_avg = [float(x) for x in np.mean(np.array(class_ms), axis=0)]
         dom = int(np.argmax(class_avg))
-        alg_bytes = w.algorithmic_bytes()
         # the dominant kernel is charged the whole batch's algorithmic bytes (conservative:
         # other size classes, if any, moved some of them)
         achieved = alg_bytes / (class_avg[dom] * 1e-3) / 1e9
         tname = "double" if prec == "f64" else "float"
+        min_cnt = int(d_cnt.min().item())
         if epa and dom == 5:
             kname = f"epa_warp_kernel<{tname}>"
         else:
@@ -359,236 +581,197 @@ def main():
             amin = int(os.environ.get("OGJK_ACCEL_MIN", 512))
             # as run_store_batch routes: pairs whose two bodies both carry a table run the table kernel,
             # timed with the last class
-            if store.table_bytes > 0 and dom == len(CLASS_TABLE) - 1 and int(w.cnt.min()) >= amin:
-                kname = f"gjk_table_kernel<{tname},{int(os.environ.get('OGJK_TABLE_LANES', 32))}>"
+            if store.table_bytes > 0 and dom == len(CLASS_TABLE) - 1 and min_cnt >= amin:
+                tl = int(os.environ.get("OGJK_TABLE_LANES", 0))
+                kname = f"gjk_table3_kernel<{tname}>" if tl == 0 else f"gjk_table_kernel<{tname},{tl}>"
             else:
                 kname = f"gjk_small_kernel<{tname}>" if lanes == 0 else f"gjk_group_kernel<{tname},{lanes}>"
+        traffic, traffic_src = traffic_for(name)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": traffic_for(name), "kernel": kname, "kernel_ms": class_avg[dom],
+                    "traffic": traffic, "traffic_source": traffic_src, "kernel": kname, "kernel_ms": class_avg[dom],
                     "step_phases_ms": {"sort": float(np.mean(sort_ms)), "classes": class_avg},
-                    "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
+                    "algorithmic_bytes_per_launch": int(alg_bytes), "peak_source": peak_src}
+        if name in NCU_NOTES:
+            roofline.update(NCU_NOTES[name])
+        else:
+            roofline["limiter"] = "HBM-shaped: one compulsory read of both hulls per pair (large hulls)"
+        if store.table_bytes > 0:
+            # a one-shot caller pays the cluster-table build once per pool
+            roofline["one_shot"] = {"store_build_ms": store_build_ms, "pairs_per_s_including_build":
+                                    n / ((ms_max / steps + store_build_ms) * 1e-3),
+                                    "note": "persistent stores amortise the table build; this is one batch with the build inside"}
 
         # ---- end to end through the host-buffer C-ABI call --------------------------
-        o = (h_dist.numpy(), h_simp.numpy().view(sdt))
-        hc, ho, hk, ha, hb = (t.numpy() for t in (h_coords, h_off, h_cnt, h_pa, h_pb))
         e2e_steps = max(2, min(steps, 5))
-        pair_owned = bool(np.array_equal(w.pa, np.arange(0, 2 * n, 2)) and np.array_equal(w.pb, w.pa + 1))
-        if pair_owned and not epa:
-            # the reference's bd1[] / bd2[] call shape: two pinned pools, pair p = polytope p of each
-            # (chunk-pipelined H2D / kernels / D2H inside the library)
-            pools = [pin(x).numpy() for x in w.two_pools()]
-            e2e_call = lambda: eng.gjk_host_pools(*pools, out=o)
-            in_bytes = sum(x.nbytes for x in pools)
-        elif epa:
-            e2e_call = lambda: eng.gjk_epa_host(hc, ho, hk, ha, hb)
+        if w is not None:
+            m = n
+            out_bytes = m * (d_dist.element_size() + sdt.itemsize) + (m * 9 * d_dist.element_size() if epa else 0)
+            h_dist = torch.empty(m, dtype=tdt).pin_memory()
+            h_simp = torch.empty(m * sdt.itemsize, dtype=torch.uint8).pin_memory()
+            o = (h_dist.numpy(), h_simp.numpy().view(sdt))
+            hc, ho, hk, ha, hb = (t.numpy() for t in (h_coords, h_off, h_cnt, h_pa, h_pb))
+            pair_owned = bool(np.array_equal(w.pa, np.arange(0, 2 * n, 2)) and np.array_equal(w.pb, w.pa + 1))
+            e2e_in = in_bytes
+            if pair_owned and not epa:
+                # the reference's bd1[] / bd2[] call shape: two pinned pools, pair p = polytope p of each
+                # (chunk-pipelined H2D / kernels / D2H inside the library)
+                pools = [pin(x).numpy() for x in w.two_pools()]
+                e2e_call = lambda: eng.gjk_host_pools(*pools, out=o)
+                e2e_in = int(sum(x.nbytes for x in pools))
+            elif epa:
+                e2e_call = lambda: eng.gjk_epa_host(hc, ho, hk, ha, hb)
+            else:
+                e2e_call = lambda: eng.gjk_host(hc, ho, hk, ha, hb, True, o)
+            e2e_note = "the whole batch"
         else:
-            e2e_call = lambda: eng.gjk_host(hc, ho, hk, ha, hb, True, o)
+            # device-generated workloads: a sub-batch is copied to pinned host memory and goes through
+            # the host-buffer API (two pools, pair p = polytope p of each)
+            m = min(n, 1_000_000 if epa else 8_000_000)
+            k_h = d_cnt[:2 * m].cpu().numpy()
+            nv = int(k_h.astype(np.int64).sum())
+            c_h = d_coords[:3 * nv].cpu().numpy().reshape(-1, 3)
+            ws = W.Workload("sub", c_h, W._offsets(k_h), k_h, np.arange(0, 2 * m, 2, dtype=np.int32),
+                            np.arange(1, 2 * m, 2, dtype=np.int32))
+            pools = [pin(x).numpy() for x in ws.two_pools()]
+            e2e_in = int(sum(x.nbytes for x in pools))
+            out_bytes = m * (4 + sdt.itemsize) + (m * 36 if epa else 0)
+            if epa:
+                e2e_call = lambda: eng.gjk_host_pools(*pools, epa=True)
+            else:
+                o = (torch.empty(m, dtype=tdt).pin_memory().numpy(),
+                     torch.empty(m * sdt.itemsize, dtype=torch.uint8).pin_memory().numpy().view(sdt))
+                e2e_call = lambda: eng.gjk_host_pools(*pools, out=o)
+            e2e_note = f"a {m}-pair sub-batch copied back from the device-generated inputs"
+            del ws, c_h
         e2e_call()  # warm (allocates staging)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             e2e_call()
         barrier()
-        e2e_s = time.perf_counter() - t0
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": n * world * e2e_steps / float(t.item()), "unit": "pairs/s", "h2d_bytes_per_step": in_bytes,
-               "d2h_bytes_per_step": out_bytes + (n * 9 * h_dist.element_size() if epa else 0), "steps": e2e_steps,
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        probe_s = copy_probe(e2e_in, out_bytes)
+        e2e_rate = m * world * e2e_steps / e2e_s
+        e2e = {"value": e2e_rate, "unit": "pairs/s", "h2d_bytes_per_step": e2e_in, "d2h_bytes_per_step": int(out_bytes),
+               "steps": e2e_steps, "pairs_per_step_per_gpu": m, "batch": e2e_note,
                "api": (f"ogjk_gjk_epa_host_{prec}" if epa else f"ogjk_gjk_host_{prec}")
-               + " (pinned host buffers in, distances + gkSimplex" + (" + witnesses + normals" if epa else "") + " out)"}
+               + " (pinned host buffers in, distances + gkSimplex" + (" + witnesses + normals" if epa else "") + " out)",
+               "copy_probe": {"pairs_per_s": m * world / probe_s, "seconds_per_step": probe_s,
+                              "h2d_gb_s_per_gpu": e2e_in / probe_s / 1e9,
+                              "note": "the same H2D and D2H byte counts on two streams, no kernels, every rank at once"},
+               "frac_of_copy_probe": e2e_rate / (m * world / probe_s)}
 
-        # quick self-check on a sample against the oracle (checker only, outside any timed region)
-        res = {"workload": desc, "value": value, "from_raw_arrays": (None if epa else {"value": n * world / (raw_ms * 1e-3), "ms_per_step": raw_ms,
-                                                                                   "note": "repack into the store inside the step"}),
-               "store_build_ms": store_build_ms, "store_bytes": store.nbytes, "ms_per_step": ms_max / steps, "launches": launches, "roofline": roofline,
-               "e2e": e2e, "clocks": clk.summary(), "prec": prec, "pairs_per_gpu": n,
-               "input_bytes_per_gpu": in_bytes}
-        if with_cpu and rank == 0 and epa:
+        res = {"workload": desc, "value": value, "scaling": "strong" if strong else "weak", "from_raw_arrays": raw,
+               "store_build_ms": store_build_ms, "store_bytes": store.nbytes, "ms_per_step": ms_max / steps,
+               "launches": launches, "roofline": roofline, "e2e": e2e, "clocks": clk.summary(), "prec": prec,
+               "pairs_per_gpu": n, "pairs_total": n_total, "input_bytes_per_gpu": in_bytes}
+
+        # ---- parity sample against the oracle + CPU baseline (checker only, outside any timed region) ----
+        if rank == 0 and with_cpu:
             from oracle.pyoracle import Oracle
-            o_ = Oracle(prec)
-            m = min(n, 20000)
-            cores = os.cpu_count() or 1
-            t0 = time.perf_counter()
-            ref = o_.gjk_epa_batch(w.coords, w.off, w.cnt, w.pa[:m], w.pb[:m], nthreads=cores)
-            dt_s = time.perf_counter() - t0
-            res["cpu_baseline"] = {"value": m / dt_s, "unit": "pairs/s", "cores": cores, "kind": "port",
-                                   "sample": f"first {m} pairs, GJK + EPA restatement (the reference has no CPU EPA)"}
-            res["sample_parity"] = {"pairs": m, "distance_bits_equal": bool(
-                d_dist[:m].cpu().numpy().tobytes() == ref["distances"].tobytes()),
-                "witness_bits_equal": bool(d_w1[:3 * m].cpu().numpy().tobytes() == ref["witness1"].tobytes())}
-        elif with_cpu and rank == 0:
-            res["cpu_baseline"] = cpu_baseline(w, prec)
-            from oracle.pyoracle import Oracle
-            m = min(n, 20000)
-            dref, sref = Oracle(prec).batch(w.coords, w.off, w.cnt, w.pa[:m], w.pb[:m], nthreads=os.cpu_count() or 1)
-            got_d = d_dist[:m].cpu().numpy()
-            res["sample_parity"] = {"pairs": m, "distance_bits_equal": bool(got_d.tobytes() == dref.tobytes()),
-                                    "simplex_bytes_equal": bool(
-                                        d_simp[:m * sdt.itemsize].cpu().numpy().tobytes() == sref.tobytes())}
+            mchk = min(n, 20000)
+            if w is not None:
+                wchk = w.slice_pairs(0, mchk)
+                cpu_w, cpu_note = w, None
+            else:
+                k_h = d_cnt[:2 * 100_000].cpu().numpy() if n >= 100_000 else d_cnt.cpu().numpy()
+                npoly = k_h.shape[0]
+                nv = int(k_h.astype(np.int64).sum())
+                c_h = d_coords[:3 * nv].cpu().numpy().reshape(-1, 3)
+                cpu_w = W.Workload("device_sample", c_h, W._offsets(k_h), k_h, np.arange(0, npoly, 2, dtype=np.int32),
+                                   np.arange(1, npoly, 2, dtype=np.int32))
+                wchk = cpu_w.slice_pairs(0, mchk)
+                cpu_note = f"the first {npoly // 2} pairs of the device-generated batch (i.i.d. generator)"
+            with quiet_stdout():
+                if epa:
+                    ref = Oracle(prec).gjk_epa_batch(wchk.coords, wchk.off, wchk.cnt, wchk.pa, wchk.pb, nthreads=os.cpu_count() or 1)
+                    res["sample_parity"] = {"pairs": mchk, "distance_bits_equal": bool(
+                        d_dist[:mchk].cpu().numpy().tobytes() == ref["distances"].tobytes()),
+                        "witness_bits_equal": bool(d_w1[:3 * mchk].cpu().numpy().tobytes() == ref["witness1"].tobytes()
+                                                   and d_w2[:3 * mchk].cpu().numpy().tobytes() == ref["witness2"].tobytes()),
+                        "mean_epa_iterations": float(ref["epa_iters"].mean())}
+                else:
+                    dref, sref = Oracle(prec).batch(wchk.coords, wchk.off, wchk.cnt, wchk.pa, wchk.pb, nthreads=os.cpu_count() or 1)
+                    res["sample_parity"] = {"pairs": mchk, "distance_bits_equal": bool(
+                        d_dist[:mchk].cpu().numpy().tobytes() == dref.tobytes()),
+                        "simplex_bytes_equal": bool(d_simp[:mchk * sdt.itemsize].cpu().numpy().tobytes() == sref.tobytes())}
+            res["cpu_baseline"] = cpu_baseline(cpu_w, prec, cpu_budget, epa, cpu_note)
         store.close()
-        del d_coords, d_simp, d_dist
+        del d_coords, d_simp, d_dist, store
         torch.cuda.empty_cache()
         return res
 
-    def device_boxes(n, seed):
-        """Config #3 inputs generated on the GPU in 10 M-pair slabs (same construction as
-        workloads.boxes: half-extents U[0.5,1.5], uniform random rotation, body 2 offset 6(u-0.5))."""
-        g = torch.Generator(device=dev)
-        g.manual_seed(seed)
-        coords = torch.empty(2 * n * 8 * 3, dtype=torch.float32, device=dev)
-        box = torch.tensor(W._BOX, dtype=torch.float32, device=dev)
-        slab = 10_000_000
-        for lo in range(0, n, slab):
-            m = min(slab, n - lo)
-            nb = 2 * m
-            half = 0.5 + torch.rand((nb, 1, 3), generator=g, device=dev)
-            q = torch.randn((nb, 4), generator=g, device=dev)
-            q = q / q.norm(dim=1, keepdim=True)
-            qw, qx, qy, qz = q.unbind(1)
-            rot = torch.stack([1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw),
-                               2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw),
-                               2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)], 1).view(nb, 3, 3)
-            pts = torch.einsum("bij,bvj->bvi", rot, box[None] * half)
-            shift = torch.zeros((nb, 1, 3), device=dev)
-            shift[1::2, 0] = 6.0 * (torch.rand((m, 3), generator=g, device=dev) - 0.5)
-            coords[2 * lo * 24:2 * (lo + m) * 24] = (pts + shift).reshape(-1)
-            del half, q, rot, pts, shift
-        cnt = torch.full((2 * n,), 8, dtype=torch.int32, device=dev)
-        off = torch.arange(2 * n, dtype=torch.int64, device=dev) * 8
-        pa = torch.arange(0, 2 * n, 2, dtype=torch.int32, device=dev)
-        return coords, off, cnt, pa, pa + 1
-
-    def measure_device_boxes(name, pairs, steps, warmup, with_cpu):
-        """100 M-pair box batch: inputs never exist on the host; parity is checked on samples
-        copied back (first 20 k pairs and a strided 20 k), e2e on an 8 M-pair sub-batch."""
-        desc = WORKLOADS[name][0]
-        n = pairs or WORKLOADS[name][3]
-        prec, sdt = "f32", api.SIMPLEX_F32
-        d_coords, d_off, d_cnt, d_pa, d_pb = device_boxes(n, args.seed + rank)
-        d_dist = torch.empty(n, dtype=torch.float32, device=dev)
-        d_simp = torch.empty(n * sdt.itemsize, dtype=torch.uint8, device=dev)
-        stream = torch.cuda.current_stream().cuda_stream
-        t0 = time.perf_counter()
-        store = eng.store_create(d_coords, d_off, d_cnt, stream)
+    def multi_engine_run():
+        """N > 1: ONE process (rank 0) drives all N GPUs through the product's multi-device entry
+        (ogjk_multi_gjk_host_*): the main workload's whole job (N x pairs) in one call, host buffers
+        in and out.  The other ranks idle on a host-side barrier."""
+        name = args.workload
+        desc, dt, maker, default_pairs = WORKLOADS[name][:4]
+        if maker is None:
+            return None
+        out = None
         torch.cuda.synchronize()
-        store_build_ms = 1e3 * (time.perf_counter() - t0)
-        step = lambda: eng.store_gjk(store, d_pa, store, d_pb, n, d_simp, d_dist, stream)
-        eng.set_timing(False)
-        for _ in range(warmup):
-            step()
-        barrier()
-        launches0 = eng.launch_count
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local_rank) as clk:
-            e0.record()
-            for _ in range(steps):
-                step()
-            e1.record()
-            launches = eng.launch_count - launches0
-            barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_max = float(t.item())
-        eng.set_timing(True)
-        cls = []
-        for _ in range(3):
-            step()
-            torch.cuda.synchronize()
-            lt = eng.last_timing()
-            cls.append([lt["sort"]] + lt["classes"])
-        eng.set_timing(False)
-        avg = [float(x) for x in np.mean(np.array(cls), axis=0)]
-        alg_bytes = n * (16 * 12 + 108 + 4)
-        kms = avg[1]  # class 0 = register-resident kernel
-        roofline = {"bound": "hbm", "achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "kernel": "gjk_small_kernel<float>",
-                    "kernel_ms": kms, "step_phases_ms": {"sort": avg[0], "classes": avg[1:]},
-                    "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
-        # samples back to the host: parity vs the oracle, CPU baseline, e2e sub-batch
-        def host_sample(idx):
-            idx = np.asarray(idx)
-            c = torch.cat([d_coords.view(-1, 48)[idx], ]).cpu().numpy().reshape(-1, 3)  # both boxes of a pair are adjacent
-            m = len(idx)
-            cnt = np.full(2 * m, 8, dtype=np.int32)
-            off = np.arange(2 * m, dtype=np.int64) * 8
-            pa = np.arange(0, 2 * m, 2, dtype=np.int32)
-            return W.Workload("boxes_sample", c, off, cnt, pa, pa + 1)
-        res = {"workload": desc, "value": n * world * steps / (ms_max * 1e-3), "ms_per_step": ms_max / steps,
-               "launches": launches, "roofline": roofline, "clocks": clk.summary(), "prec": prec, "pairs_per_gpu": n,
-               "input_bytes_per_gpu": int(d_coords.numel() * 4 + d_off.numel() * 8 + d_cnt.numel() * 4 + 2 * d_pa.numel() * 4),
-               "from_raw_arrays": None, "store_build_ms": store_build_ms, "store_bytes": store.nbytes}
+        dist.barrier(group=cpu_group)
         if rank == 0:
-            from oracle.pyoracle import Oracle
-            checks = {}
-            for label, idx in (("first", np.arange(20000)), ("strided", np.arange(0, n, max(1, n // 20000))[:20000])):
-                ws = host_sample(idx)
-                dref, sref = Oracle(prec).batch(ws.coords, ws.off, ws.cnt, ws.pa, ws.pb, nthreads=os.cpu_count() or 1)
-                ti = torch.from_numpy(idx).to(dev)
-                got_d = d_dist[ti].cpu().numpy()
-                got_s = d_simp.view(-1, sdt.itemsize)[ti].cpu().numpy().reshape(-1).view(sdt)
-                checks[label] = {"pairs": len(idx), "distance_bits_equal": bool(got_d.tobytes() == dref.tobytes()),
-                                 "simplex_bytes_equal": bool(got_s.tobytes() == sref.tobytes())}
-            res["sample_parity"] = checks
-            if with_cpu:
-                res["cpu_baseline"] = cpu_baseline(host_sample(np.arange(100000)), prec)
-        # e2e on an 8 M-pair sub-batch through the host-buffer API (two pinned pools)
-        m = min(n, 8_000_000)
-        sub = d_coords[: m * 48].view(m, 2, 24)
-        pin = lambda a: a.contiguous().cpu().pin_memory().numpy()
-        c1, c2 = pin(sub[:, 0].reshape(-1)), pin(sub[:, 1].reshape(-1))
-        k = torch.full((m,), 8, dtype=torch.int32).pin_memory().numpy()
-        o = (torch.arange(m, dtype=torch.int64) * 8).pin_memory().numpy()
-        out = (torch.empty(m, dtype=torch.float32).pin_memory().numpy(),
-               torch.empty(m * sdt.itemsize, dtype=torch.uint8).pin_memory().numpy().view(sdt))
-        eng.gjk_host_pools(c1, o, k, c2, o, k, out=out)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            eng.gjk_host_pools(c1, o, k, c2, o, k, out=out)
-        barrier()
-        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        res["e2e"] = {"value": m * world * 3 / float(t.item()), "unit": "pairs/s",
-                      "h2d_bytes_per_step": int(c1.nbytes + c2.nbytes + 2 * (k.nbytes + o.nbytes)),
-                      "d2h_bytes_per_step": int(out[0].nbytes + out[1].nbytes), "steps": 3,
-                      "api": "ogjk_gjk_host_f32 on an 8 M-pair sub-batch (two pinned pools, chunk-pipelined)"}
-        store.close()
-        del d_coords, d_simp, d_dist
-        torch.cuda.empty_cache()
-        return res
+            try:
+                prec = "f64" if dt == np.float64 else "f32"
+                sdt = api.SIMPLEX_F64 if prec == "f64" else api.SIMPLEX_F32
+                n = (args.pairs or default_pairs) * world
+                w = maker(n, args.seed)
+                pools = [pin(x).numpy() for x in w.two_pools()]
+                o = (torch.empty(n, dtype=torch.float64 if prec == "f64" else torch.float32).pin_memory().numpy(),
+                     torch.empty(n * sdt.itemsize, dtype=torch.uint8).pin_memory().numpy().view(sdt))
+                m = api.MultiEngine(list(range(world)))
+                m.gjk_host_pools(*pools, out=o)
+                l0 = m.launch_count
+                t0 = time.perf_counter()
+                reps = 3
+                for _ in range(reps):
+                    m.gjk_host_pools(*pools, out=o)
+                dt_s = (time.perf_counter() - t0) / reps
+                launches = (m.launch_count - l0) // reps
+                m.close()
+                # one-device answer for the same job: byte equality of a strided sample
+                idx = np.arange(0, n, max(1, n // 20000))[:20000]
+                from oracle.pyoracle import Oracle
+                with quiet_stdout():
+                    dref, sref = Oracle(prec).batch(w.coords, w.off, w.cnt, w.pa[idx], w.pb[idx], nthreads=os.cpu_count() or 1)
+                same = bool(o[0][idx].tobytes() == dref.tobytes() and o[1][idx].tobytes() == sref.tobytes())
+                out = {"api": f"ogjk_multi_gjk_host_{prec} (one process, one call, {world} devices; host buffers in and out)",
+                       "devices": world, "pairs_per_call": n, "value": n / dt_s, "unit": "pairs/s", "seconds_per_call": dt_s,
+                       "h2d_bytes_per_call": int(sum(x.nbytes for x in pools)), "gpu_launches_per_call": int(launches),
+                       "sample_parity": {"pairs": int(len(idx)), "bytes_equal_to_oracle": same}}
+            except Exception as e:  # report, do not lose the main line
+                out = {"error": repr(e)}
+        dist.barrier(group=cpu_group)
+        return out
 
-    _measure = measure
-
-    def measure(name, pairs, steps, warmup, with_cpu):
-        if WORKLOADS[name][2] is None:
-            return measure_device_boxes(name, pairs, steps, warmup, with_cpu)
-        return _measure(name, pairs, steps, warmup, with_cpu)
-
-    main_res = measure(args.workload, args.pairs, args.steps, args.warmup, not args.no_cpu_baseline)
+    with_cpu = not args.no_cpu_baseline
+    main_res = measure(args.workload, args.pairs, args.steps, args.warmup, with_cpu, 10.0)
     others = {}
-    for name in [x for x in args.extra.split(",") if x]:
-        r = measure(name, 0, max(3, args.steps // 2), 3, not args.no_cpu_baseline)
-        others[name] = {k: r[k] for k in ("workload", "value", "ms_per_step", "roofline", "e2e", "prec", "pairs_per_gpu", "from_raw_arrays")
-                        if k in r}
-        if "cpu_baseline" in r:
-            others[name]["cpu_baseline"] = r["cpu_baseline"]
-            others[name]["sample_parity"] = r.get("sample_parity")
+    for name in extras:
+        if name == args.workload:
+            continue
+        r = measure(name, 0, max(3, args.steps // 2), 3, with_cpu, 4.0)
+        others[name] = {k: r[k] for k in ("workload", "value", "scaling", "ms_per_step", "launches", "roofline", "e2e", "prec",
+                                          "pairs_per_gpu", "pairs_total", "from_raw_arrays", "store_build_ms", "clocks") if k in r}
+        for k in ("cpu_baseline", "sample_parity"):
+            if k in r:
+                others[name][k] = r[k]
+    multi = multi_engine_run() if (world > 1 and not args.no_multi) else None
 
     if rank == 0:
         line = {
             "metric": "gjk_pair_queries_per_sec", "value": main_res["value"], "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": main_res["prec"], "data": "synthetic",
-            "config": {"workload": main_res["workload"], "pairs_per_gpu": main_res["pairs_per_gpu"],
-                       "sharding": "contiguous pair slice per rank, no data-path collective",
-                       "l2": (f"inputs {main_res['input_bytes_per_gpu'] / 1e6:.0f} MB per GPU "
-                              + ("> 126 MB L2 (no flush needed)" if main_res["input_bytes_per_gpu"] > L2_BYTES
-                                 else "< L2: numbers are L2-warm")),
-                       "resident_format": "packed polytope store (ogjk_store_create, outside the timed region)",
-                       "scheduler_classes": [list(c) for c in CLASS_TABLE]},
+            "config": config_of(args.workload, main_res["pairs_total"], world),
+            "run": {"sharding": "contiguous pair slice per rank (ogjk_multi_shard_bounds), no data-path collective",
+                    "l2": (f"inputs {main_res['input_bytes_per_gpu'] / 1e6:.0f} MB per GPU "
+                           + ("> 126 MB L2 (no flush needed)" if main_res["input_bytes_per_gpu"] > L2_BYTES
+                              else "< L2: numbers are L2-warm")),
+                    "resident_format": "packed polytope store (ogjk_store_create, outside the timed region)",
+                    "scheduler_classes": [list(c) for c in CLASS_TABLE]},
             "roofline": main_res["roofline"], "e2e": main_res["e2e"], "gpu_launches": main_res["launches"],
             "from_raw_arrays": main_res["from_raw_arrays"], "store_build_ms": main_res["store_build_ms"],
             "clocks": main_res["clocks"],
@@ -598,6 +781,8 @@ def main():
             line["sample_parity"] = main_res["sample_parity"]
         if others:
             line["other_workloads"] = others
+        if multi is not None:
+            line["multi_engine"] = multi
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

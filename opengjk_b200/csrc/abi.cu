@@ -524,7 +524,7 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
         case 32: launch_table<T, 32>(ctx, a, sorted, tb, te, counters + 6, st); break;
         default: {
           long long blocks = (a.npairs * 32 + 127) / 128, cap = (long long)ctx->sm_count * 16;
-          gjk_table2_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, sorted, tb, te, counters + 6);
+          gjk_table3_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, sorted, tb, te, counters + 6);
         } break;
       }
       ctx->launches += 1;

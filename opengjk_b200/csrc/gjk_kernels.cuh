@@ -472,7 +472,7 @@ template <typename T, int G> struct ScanSide {
     for (int j = 0; j < VPL; ++j) ub[j] = dot3(cx[j], cy[j], cz[j], dx, dy, dz);
   }
   OGJK_DI void fetch(int c, int g, Hit& h) const {
-    const T* r = acc + 6 * ncs + (long long)c * kAccelRecord<T> + g * VPL;
+    const T* r = acc + accel_records_at(ncs) + (long long)c * kAccelRecord<T> + g * VPL;
     load_vec<VPL>(r, h.x);
     load_vec<VPL>(r + kAccelCluster, h.y);
     load_vec<VPL>(r + 2 * kAccelCluster, h.z);

@@ -45,20 +45,26 @@ template <typename T> struct StoreView {
 // rounding is monotone), so a cluster with ub < best cannot hold a vertex that beats or
 // ties `best` and skipping it leaves the scan result bit-identical.
 // Block layout in T elements, nc = ceil(n/32), ncs = nc rounded up to 32:
-//   lox[ncs] loy[ncs] loz[ncs] hix[ncs] hiy[ncs] hiz[ncs] | nc cluster records
-//   cluster record = x[32] y[32] z[32] | int orig[32]          (kAccelRecord<T> elements)
+//   lox[ncs] loy[ncs] loz[ncs] hix[ncs] hiy[ncs] hiz[ncs]       cluster boxes
+//   6 x kAccelMaxTiles tile boxes (same order)                   box of each run of 32 clusters
+//   nc cluster records = x[32] y[32] z[32] | int orig[32]        (kAccelRecord<T> elements each)
 // (slots past n in the last cluster repeat that cluster's first vertex; table entries
-// past nc are zero and never used).
+// past nc are zero and never used).  The k-d order makes 32 consecutive clusters a compact
+// region, so a tile box prunes 1024 vertices with one dot product (bodies above 1024
+// vertices; same monotone-rounding argument as for the cluster boxes).
 constexpr int kAccelCluster = 32;
 constexpr int kAccelMaxVerts = 16384;
 constexpr int kAccelMaxClusters = kAccelMaxVerts / kAccelCluster;
+constexpr int kAccelMaxTiles = kAccelMaxClusters / 32;  // 16
 template <typename T> constexpr int kAccelRecord = 3 * kAccelCluster + kAccelCluster * (int)sizeof(int) / (int)sizeof(T);
 
 __host__ __device__ __forceinline__ int accel_table_stride(int nc) { return (nc + 31) & ~31; }
 template <typename T> __host__ __device__ __forceinline__ long long accel_elems(int n) {
   const int nc = (n + kAccelCluster - 1) / kAccelCluster;
-  return 6ll * accel_table_stride(nc) + (long long)nc * kAccelRecord<T>;
+  return 6ll * accel_table_stride(nc) + 6 * kAccelMaxTiles + (long long)nc * kAccelRecord<T>;
 }
+// Element offset of the cluster records inside a polytope's table.
+__host__ __device__ __forceinline__ int accel_records_at(int ncs) { return 6 * ncs + 6 * kAccelMaxTiles; }
 
 // Per-polytope element counts the three scan kernels below accumulate.
 struct BlockElems {
@@ -336,7 +342,7 @@ accel_build_kernel(StoreView<T> s, long long npoly, T* __restrict__ accel, int p
     // cluster records + original indices; a warp per cluster reduces its bounding box
     const int ncs = accel_table_stride(nc);
     T* out = accel + s.aoff[h];
-    T* rec = out + 6 * ncs;
+    T* rec = out + accel_records_at(ncs);
     for (int c = tid >> 5; c < ncs; c += nth >> 5) {
       const int lane = tid & 31;
       if (c >= nc) {  // table padding, never used by queries
@@ -359,6 +365,27 @@ accel_build_kernel(StoreView<T> s, long long npoly, T* __restrict__ accel, int p
       if (lane == 0) {
         out[c] = lx; out[ncs + c] = ly; out[2 * ncs + c] = lz;
         out[3 * ncs + c] = hx; out[4 * ncs + c] = hy; out[5 * ncs + c] = hz;
+      }
+    }
+    __syncthreads();
+    // tile boxes: a warp per run of 32 clusters reduces the cluster boxes just written
+    T* tb = out + 6 * ncs;
+    for (int t = tid >> 5; t < kAccelMaxTiles; t += nth >> 5) {
+      const int lane = tid & 31;
+      const int c = t * 32 + lane;
+      const bool in = c < nc;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        T l = in ? out[a * ncs + c] : (T)INFINITY, h = in ? out[(3 + a) * ncs + c] : (T)-INFINITY;
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+          l = fmin(l, __shfl_xor_sync(0xffffffffu, l, m));
+          h = fmax(h, __shfl_xor_sync(0xffffffffu, h, m));
+        }
+        if (lane == 0) {
+          tb[a * kAccelMaxTiles + t] = t * 32 < nc ? l : (T)0;
+          tb[(3 + a) * kAccelMaxTiles + t] = t * 32 < nc ? h : (T)0;
+        }
       }
     }
     __syncthreads();

@@ -1,193 +1,214 @@
-// table_kernel.cuh -- warp-per-pair GJK over the store's cluster tables, second generation.
+// table_kernel.cuh -- warp-per-pair GJK over the store's cluster tables (store.cuh).
 //
-// The first table kernel (gjk_table_kernel<T,32>, gjk_kernels.cuh) was latency-bound on
-// 1000-vertex hulls: every GJK iteration paid ~5 DEPENDENT memory round trips per body pair
-// (cluster boxes -> best cluster -> its vertices -> re-prune -> survivors -> ...) on top of
-// a 4-trip pair setup (queue -> list -> idx -> cnt/boff/aoff), at 16 warps per SM
-// (profiles/r1m_hulls1k_f32_tables_ncu_summary.txt: long_scoreboard 2.85 of 7.4 cycles per
-// issue, issue-active 54 %).  This kernel removes round trips instead of hiding them:
+// History (profiles/r2a_table_gen2_ab.jsonl).  The first table kernel
+// (gjk_table_kernel<T,32>, gjk_kernels.cuh) ran 1000-vertex hulls at 0.49-0.51 of the HBM
+// roofline: per iteration and body it read the 32 cluster boxes, fetched the best cluster,
+// re-pruned and fetched the survivors three per trip -- one cluster = 32 vertices = one
+// 4-byte load per lane and array, ~25 warp instructions per cluster, ~7 clusters per body
+// and iteration.  Its pruned scan therefore issued as many instructions as the plain scan
+// it replaced (which reads 128 vertices per 3 vector loads); the kernel sat at 54 % issue
+// utilisation with ~5 dependent round trips per iteration.  A second draft that only
+// removed round trips (boxes in registers, last winner's cluster cached in registers,
+// next pair's setup prefetched) was SLOWER (94 vs 129 M pairs/s): the added per-iteration
+// instructions cost more than the trips saved.  The kernel is instruction-bound first.
 //
-//   * the boxes of the first 32 clusters of each body live in registers for the whole
-//     query (lane c holds cluster c: 6 values per body), so the bound of every cluster is
-//     one dot product away in every iteration -- no memory trip;
-//   * the cluster that held the last support vertex stays in registers too (lane v holds
-//     vertex v of it).  GJK's search direction converges, so the next support vertex is
-//     usually in the same cluster: evaluating it first costs no memory access and gives a
-//     lower bound that prunes almost everything else;
-//   * the surviving clusters are fetched highest-bound first, several per trip, with
-//     unconditional loads issued back to back; the bound is re-tightened between trips;
-//   * the NEXT pair's setup chain (queue grab -> list -> indices -> counts / offsets) is
-//     advanced one dependent load per GJK iteration of the current pair, so its latency
-//     is covered by work instead of being paid at the top of every pair.
+// This version cuts instructions per vertex to the plain scan's level and keeps the
+// pruning:
+//   * cluster boxes of the first 32 clusters live in registers for the whole query
+//     (lane c = cluster c), tile boxes (one per 32 clusters) likewise for bodies above
+//     1024 vertices: bounds cost a dot product, no memory trip;
+//   * a fetch moves VPL clusters at once with 16-byte vector loads: 32/VPL lanes per
+//     cluster, VPL consecutive vertices per lane (fp32: 4 clusters = 128 vertices per
+//     4 loads; fp64: 2 clusters).  The highest bound goes first, the rest in index order;
+//   * the exact (value, lowest original index) update runs only when the max of a lane's
+//     VPL scores reaches its running best (the plain scan's max-tree fast path);
+//   * both bodies advance in lockstep so that their loads overlap.
 //
-// Exactness: a cluster is skipped only when its bound is below a value some vertex has
-// already reached, so it cannot hold a vertex that beats or ties the final maximum; the
-// order in which the other clusters are evaluated does not matter because the running
-// best is a total order on (dot, lowest original index) with the carried support point
-// ranked first among equals (openGJK.c:607-630).  Results are bit-identical to the plain
-// scans (tests/test_gpu_accel.py).
+// Exactness: a cluster (tile) is skipped only when its bound is below a value some vertex
+// has already reached, so it cannot hold a vertex that beats or ties the final maximum;
+// evaluation order does not matter because the running best is a total order on (dot,
+// lowest original index) with the carried support point first among equals
+// (openGJK.c:607-630).  Results are bit-identical to the plain scans (tests/test_gpu_accel.py).
 #pragma once
 #include "gjk_kernels.cuh"
 
 namespace ogjk {
 
-#ifndef OGJK_T2_K
-#define OGJK_T2_K 3  // clusters fetched per body per trip
+#ifndef OGJK_T3_VPL_F32
+#define OGJK_T3_VPL_F32 4
 #endif
-#ifndef OGJK_T2_CACHE
-#define OGJK_T2_CACHE 1  // keep the last winner's cluster in registers
+#ifndef OGJK_T3_VPL_F64
+#define OGJK_T3_VPL_F64 2
 #endif
-#ifndef OGJK_T2_PREFETCH
-#define OGJK_T2_PREFETCH 1  // software-pipelined setup of the next pair
+#ifndef OGJK_T3_PARK
+#define OGJK_T3_PARK 0  // park the simplex in shared memory while the support scans run
 #endif
-#ifndef OGJK_T2_PARK
-#define OGJK_T2_PARK 0  // park the simplex in shared memory while the support scans run
+#ifndef OGJK_LB_TABLE3_F32
+#define OGJK_LB_TABLE3_F32 4
 #endif
-#ifndef OGJK_LB_TABLE2_F32
-#define OGJK_LB_TABLE2_F32 4
-#endif
-#ifndef OGJK_LB_TABLE2_F64
-#define OGJK_LB_TABLE2_F64 3
+#ifndef OGJK_LB_TABLE3_F64
+#define OGJK_LB_TABLE3_F64 3
 #endif
 
+template <typename T> struct T3Vpl { static constexpr int value = sizeof(T) == 4 ? OGJK_T3_VPL_F32 : OGJK_T3_VPL_F64; };
+
 // Per-body state of one query.
-template <typename T> struct T2Side {
-  const T* acc;    // table: lox loy loz hix hiy hiz, each ncs long; records follow
-  int nc, ncs;
-  T lo[3], hi[3];  // lane c: box of cluster c (first tile)
-#if OGJK_T2_CACHE
-  T cx, cy, cz;    // lane v: vertex v of the cached cluster
-  int co, cc;      // its original index; cached cluster id (-1: none)
-#endif
-  OGJK_DI const T* record(int c) const { return acc + 6 * ncs + (long long)c * kAccelRecord<T>; }
+template <typename T> struct T3Side {
+  const T* acc;      // table base (cluster boxes | tile boxes | records)
+  int nc, ncs, ntiles;
+  T lo[3], hi[3];    // lane c: box of cluster c (tile 0)
+  T tlo[3], thi[3];  // lane t: box of tile t (bodies with more than one tile)
+  OGJK_DI const T* record(int c) const { return acc + accel_records_at(ncs) + (long long)c * kAccelRecord<T>; }
   OGJK_DI void open(const T* table, int n, int lane) {
     acc = table;
     nc = (n + kAccelCluster - 1) / kAccelCluster;
     ncs = accel_table_stride(nc);
+    ntiles = (nc + 31) >> 5;
 #pragma unroll
     for (int a = 0; a < 3; ++a) { lo[a] = acc[a * ncs + lane]; hi[a] = acc[(3 + a) * ncs + lane]; }
-#if OGJK_T2_CACHE
-    cc = -1; cx = cy = cz = (T)0; co = 0;
-#endif
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { tlo[a] = (T)0; thi[a] = (T)0; }
+    if (ntiles > 1) {
+      const T* tb = acc + 6 * ncs + (lane & (kAccelMaxTiles - 1));
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { tlo[a] = tb[a * kAccelMaxTiles]; thi[a] = tb[(3 + a) * kAccelMaxTiles]; }
+    }
   }
 };
 
-template <typename T> struct T2Hit { T sc, x, y, z; int o; };
-
-// Running best of one lane: value, original index (-1 = the carried point), cluster, vertex.
-template <typename T> struct T2Best {
-  T bl, px, py, pz; int il, bc;
-  OGJK_DI void take(const T2Hit<T>& h, int c, bool valid) {
-    if (valid && (h.sc > bl || (h.sc == bl && h.o < il))) { bl = h.sc; il = h.o; bc = c; px = h.x; py = h.y; pz = h.z; }
-  }
-};
+// Running best of one lane: value, original index (-1 = the carried point), vertex.
+template <typename T> struct T3Best { T bl, px, py, pz; int il; };
 
 template <typename T>
-OGJK_DI void t2_fetch(const T2Side<T>& s, int c, int lane, T dx, T dy, T dz, T2Hit<T>& h) {
-  const T* r = s.record(c) + lane;
-  h.x = r[0]; h.y = r[kAccelCluster]; h.z = r[2 * kAccelCluster];
-  h.o = reinterpret_cast<const int*>(r - lane + 3 * kAccelCluster)[lane];
-  h.sc = dot3(h.x, h.y, h.z, dx, dy, dz);
+OGJK_DI T t3_corner_dot(const T (&lo)[3], const T (&hi)[3], T dx, T dy, T dz) {
+  return dot3(dx >= (T)0 ? hi[0] : lo[0], dy >= (T)0 ? hi[1] : lo[1], dz >= (T)0 ? hi[2] : lo[2], dx, dy, dz);
 }
 
+// Lowest set lane of `bits` among those holding the largest key.
+template <typename K> OGJK_DI int t3_argmax_lane(unsigned bits, int lane, K key) {
+  const bool mine = (bits >> lane) & 1u;
+  const K k = mine ? key : K(0);
+  const K m = group_max_key(0xffffffffu, k);
+  return __ffs(__ballot_sync(0xffffffffu, mine && k == m)) - 1;
+}
+
+// Key of a bound for pruning in key space: NaN bounds (of either sign) must never prune.
+OGJK_DI unsigned t3_bound_key(float ub) { return ub != ub ? 0xffffffffu : okey(ub); }
+OGJK_DI unsigned long long t3_bound_key(double ub) { return ub != ub ? ~0ull : okey(ub); }
+
 // Both support calls of one iteration (openGJK.c:992-993) in lockstep.
+//
+// Cluster selection is lane-parallel: the 32/VPL-lane group q owns the clusters c of the
+// current tile with c % VPL == q and takes its lowest live one each trip (the k-d order makes
+// the live set a few runs of neighbouring indices, so the residue classes stay balanced);
+// one REDUX.OR clears what the groups took.  No serial "next cluster" chain per slot.
 template <typename T>
-OGJK_DI void t2_support_both(T2Side<T> (&S)[2], int lane, const V3<T>& v, V3<T>& sa, int& ia, V3<T>& sb, int& ib) {
-  constexpr int K = OGJK_T2_K;
+OGJK_DI void t3_support_both(const T3Side<T> (&S)[2], int lane, const V3<T>& v, V3<T>& sa, int& ia, V3<T>& sb, int& ib) {
+  constexpr int VPL = T3Vpl<T>::value;
+  constexpr int LPC = 32 / VPL;  // lanes per cluster
+  constexpr int NG = VPL;        // clusters per fetch
   constexpr unsigned FULL = 0xffffffffu;
-  T dx[2] = {-v.x, v.x}, dy[2] = {-v.y, v.y}, dz[2] = {-v.z, v.z};
-  T2Best<T> B[2];
+  const int q = lane / LPC, sub = lane % LPC;
+  const unsigned gmask = (NG == 4 ? 0x11111111u : NG == 2 ? 0x55555555u : 0xffffffffu) << q;
+  const T dx[2] = {-v.x, v.x}, dy[2] = {-v.y, v.y}, dz[2] = {-v.z, v.z};
+  T3Best<T> B[2];
+  decltype(okey(T(0))) tkey[2];  // key of this lane's tile bound
+  unsigned tl[2];                // tiles still to visit
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const V3<T>& cur = k == 0 ? sa : sb;
-    B[k].bl = dot3(cur.x, cur.y, cur.z, dx[k], dy[k], dz[k]);
+    B[k].bl = dot3(cur.x, cur.y, cur.z, dx[k], dy[k], dz[k]);  // same value in every lane
     B[k].px = cur.x; B[k].py = cur.y; B[k].pz = cur.z;
-    B[k].il = -1; B[k].bc = -1;
-#if OGJK_T2_CACHE
-    if (S[k].cc >= 0) {
-      T2Hit<T> h{dot3(S[k].cx, S[k].cy, S[k].cz, dx[k], dy[k], dz[k]), S[k].cx, S[k].cy, S[k].cz, S[k].co};
-      B[k].take(h, S[k].cc, true);
+    B[k].il = -1;
+    tkey[k] = 0;
+    tl[k] = 1u;
+    if (S[k].ntiles > 1) {
+      tkey[k] = t3_bound_key(t3_corner_dot(S[k].tlo, S[k].thi, dx[k], dy[k], dz[k]));
+      tl[k] = __ballot_sync(FULL, lane < S[k].ntiles && tkey[k] >= okey(B[k].bl));
     }
-#endif
   }
-  const int tiles = ((S[0].nc > S[1].nc ? S[0].nc : S[1].nc) + 31) >> 5;
-  for (int t = 0; t < tiles; ++t) {
-    T ub[2];
+  while (tl[0] | tl[1]) {
+    int t[2];
+    decltype(okey(T(0))) ukey[2];
     unsigned live[2];
+    T thr[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      T cx, cy, cz;
-      if (t == 0) {
-        cx = dx[k] >= (T)0 ? S[k].hi[0] : S[k].lo[0];
-        cy = dy[k] >= (T)0 ? S[k].hi[1] : S[k].lo[1];
-        cz = dz[k] >= (T)0 ? S[k].hi[2] : S[k].lo[2];
+      t[k] = -1;
+      if (tl[k]) {
+        t[k] = S[k].ntiles > 1 ? t3_argmax_lane(tl[k], lane, tkey[k]) : 0;  // most promising tile first
+        tl[k] &= ~(1u << t[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      T ub;
+      if (t[k] <= 0) {
+        ub = t3_corner_dot(S[k].lo, S[k].hi, dx[k], dy[k], dz[k]);
       } else {
-        const int c0 = (t * 32 < S[k].nc ? t : 0) * 32 + lane;  // a body with fewer tiles re-reads tile 0, masked off
-        cx = S[k].acc[(dx[k] >= (T)0 ? 3 : 0) * S[k].ncs + c0];
-        cy = S[k].acc[(dy[k] >= (T)0 ? 4 : 1) * S[k].ncs + c0];
-        cz = S[k].acc[(dz[k] >= (T)0 ? 5 : 2) * S[k].ncs + c0];
+        const T* bx = S[k].acc + t[k] * 32 + lane;
+        ub = dot3(bx[(dx[k] >= (T)0 ? 3 : 0) * S[k].ncs], bx[(dy[k] >= (T)0 ? 4 : 1) * S[k].ncs],
+                  bx[(dz[k] >= (T)0 ? 5 : 2) * S[k].ncs], dx[k], dy[k], dz[k]);
       }
-      ub[k] = dot3(cx, cy, cz, dx[k], dy[k], dz[k]);
+      ukey[k] = t3_bound_key(ub);
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      const bool has = t * 32 + lane < S[k].nc;
-      const T wb = unkey(group_max_key(FULL, okey(B[k].bl)));
-      live[k] = __ballot_sync(FULL, has && !(ub[k] < wb));
-#if OGJK_T2_CACHE
-      if ((S[k].cc >> 5) == t && S[k].cc >= 0) live[k] &= ~(1u << (S[k].cc & 31));  // already evaluated
-#endif
+      const bool has = t[k] >= 0 && t[k] * 32 + lane < S[k].nc;
+      const auto wkey = group_max_key(FULL, okey(B[k].bl));
+      thr[k] = unkey(wkey);
+      live[k] = __ballot_sync(FULL, has && ukey[k] >= wkey);
     }
-    bool first = true;
     while (live[0] | live[1]) {
-      int cl[2][K];
+      T x[2][VPL], y[2][VPL], z[2][VPL];
+      int o[2][VPL];
+      bool valid[2];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        int kmax = K;
-        if (first) {
-          // highest bound first: it most likely holds the winner and tightens the prune
-          const auto key = ((live[k] >> lane) & 1u) ? okey(ub[k]) : decltype(okey(ub[k]))(0);
-          const auto m = group_max_key(FULL, key);
-          const unsigned at = __ballot_sync(FULL, ((live[k] >> lane) & 1u) && key == m);
-          const int top = live[k] ? __ffs(at) - 1 : -1;
-          cl[k][0] = top < 0 ? -1 : t * 32 + top;
-          if (top >= 0) live[k] &= ~(1u << top);
-#if OGJK_T2_CACHE
-          if (S[k].cc < 0) kmax = 1;  // nothing is known yet about this body: do not speculate
-#else
-          kmax = 1;
-#endif
-        }
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-          if (first && j == 0) continue;
-          if (j < kmax && live[k]) {
-            cl[k][j] = t * 32 + __ffs(live[k]) - 1;
-            live[k] &= live[k] - 1;
-          } else {
-            cl[k][j] = -1;
-          }
-        }
-      }
-      T2Hit<T> h[2][K];
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-#pragma unroll
-        for (int j = 0; j < K; ++j) t2_fetch(S[k], cl[k][j] < 0 ? 0 : cl[k][j], lane, dx[k], dy[k], dz[k], h[k][j]);
+        const unsigned mine = live[k] & gmask;
+        valid[k] = mine != 0;
+        const unsigned took = __reduce_or_sync(FULL, mine & (0u - mine));
+        // idle groups re-read the lowest cluster taken this trip: its lines are in flight anyway
+        const int bit = __ffs(valid[k] ? mine : (took ? took : 1u)) - 1;
+        live[k] &= ~took;
+        const T* r = S[k].record((t[k] < 0 ? 0 : t[k]) * 32 + bit) + sub * VPL;
+        load_vec<VPL>(r, x[k]);
+        load_vec<VPL>(r + kAccelCluster, y[k]);
+        load_vec<VPL>(r + 2 * kAccelCluster, z[k]);
+        load_vec<VPL>(reinterpret_cast<const int*>(r - sub * VPL + 3 * kAccelCluster) + sub * VPL, o[k]);
       }
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
+        T sc[VPL];
 #pragma unroll
-        for (int j = 0; j < K; ++j) B[k].take(h[k][j], cl[k][j], cl[k][j] >= 0);
+        for (int j = 0; j < VPL; ++j) sc[j] = dot3(x[k][j], y[k][j], z[k][j], dx[k], dy[k], dz[k]);
+        T m = sc[0];
+#pragma unroll
+        for (int j = 1; j < VPL; ++j) m = fmax(m, sc[j]);
+        // only a vertex that reaches the best value seen by ANY lane so far can still win
+        if (valid[k] && m >= thr[k]) {
+#pragma unroll
+          for (int j = 0; j < VPL; ++j)
+            if (sc[j] > B[k].bl || (sc[j] == B[k].bl && o[k][j] < B[k].il)) {
+              B[k].bl = sc[j]; B[k].il = o[k][j]; B[k].px = x[k][j]; B[k].py = y[k][j]; B[k].pz = z[k][j];
+            }
+        }
       }
       if (live[0] | live[1]) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-          const T wb = unkey(group_max_key(FULL, okey(B[k].bl)));
-          live[k] &= __ballot_sync(FULL, !(ub[k] < wb));
+          const auto wkey = group_max_key(FULL, okey(B[k].bl));
+          thr[k] = unkey(wkey);
+          live[k] &= __ballot_sync(FULL, ukey[k] >= wkey);
         }
       }
-      first = false;
+    }
+    if (tl[0] | tl[1]) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const auto wkey = group_max_key(FULL, okey(B[k].bl));
+        tl[k] &= __ballot_sync(FULL, tkey[k] >= wkey);
+      }
     }
   }
 #pragma unroll
@@ -199,23 +220,14 @@ OGJK_DI void t2_support_both(T2Side<T> (&S)[2], int lane, const V3<T>& v, V3<T>&
     const int src = __ffs(__ballot_sync(FULL, cand && (unsigned)B[k].il == fi)) - 1;
     const V3<T> w{__shfl_sync(FULL, B[k].px, src), __shfl_sync(FULL, B[k].py, src), __shfl_sync(FULL, B[k].pz, src)};
     if (k == 0) { sa = w; ia = (int)fi; } else { sb = w; ib = (int)fi; }
-#if OGJK_T2_CACHE
-    const int wc = __shfl_sync(FULL, B[k].bc, src);
-    if (wc != S[k].cc) {  // issued now, first used at the top of the next iteration
-      const T* r = S[k].record(wc) + lane;
-      S[k].cx = r[0]; S[k].cy = r[kAccelCluster]; S[k].cz = r[2 * kAccelCluster];
-      S[k].co = reinterpret_cast<const int*>(r - lane + 3 * kAccelCluster)[lane];
-      S[k].cc = wc;
-    }
-#endif
   }
 }
 
-// The simplex (warp-uniform: 20 coordinates/indices + count + running max) is dead weight
-// during the support scans, which need their registers for the loads in flight; lane 0
-// parks it in the warp's shared-memory slot and every lane reads it back (broadcast).
-template <typename T> struct T2Park { T f[13]; int i[9]; };
-template <typename T> OGJK_DI void t2_park(T2Park<T>* slot, const GjkState<T>& st, int lane) {
+// The simplex (warp-uniform: 12 coordinates, 8 indices, count, running max) is dead weight
+// during the support scans, which want their registers for loads in flight; lane 0 parks it
+// in the warp's shared-memory slot and every lane reads it back (broadcast).
+template <typename T> struct T3Park { T f[13]; int i[9]; };
+template <typename T> OGJK_DI void t3_park(T3Park<T>* slot, const GjkState<T>& st, int lane) {
   if (lane == 0) {
     const Splx<T>& s = st.s;
     const T f[13] = {s.q0.x, s.q0.y, s.q0.z, s.q1.x, s.q1.y, s.q1.z, s.q2.x, s.q2.y, s.q2.z, s.q3.x, s.q3.y, s.q3.z, st.wmax2};
@@ -227,7 +239,7 @@ template <typename T> OGJK_DI void t2_park(T2Park<T>* slot, const GjkState<T>& s
   }
   __syncwarp();
 }
-template <typename T> OGJK_DI void t2_unpark(const T2Park<T>* slot, GjkState<T>& st) {
+template <typename T> OGJK_DI void t3_unpark(const T3Park<T>* slot, GjkState<T>& st) {
   const T* f = slot->f; const int* i = slot->i;
   st.s.n = i[0];
   st.s.q0 = MV<T>{f[0], f[1], f[2], i[1], i[2]};
@@ -238,115 +250,72 @@ template <typename T> OGJK_DI void t2_unpark(const T2Park<T>* slot, GjkState<T>&
   __syncwarp();
 }
 
-// Setup of one pair, produced by the lane-parallel pipeline below.
-struct T2Desc {
-  long long slot;  // position in the segment (>= end: no more work)
-  int p;           // pair id
-  int n1, n2;
-  long long boff1, boff2, aoff1, aoff2;
-};
-
-// The next pair's setup chain, one dependent load per step():
-//   0: queue grab   1: pair id   2: polytope index (even lanes body 1, odd lanes body 2)
-//   3: lane 0/1 vertex count, lane 2/3 block offset, lane 4/5 table offset    4: done
-template <typename T> struct T2Pipe {
-  int stage;
-  unsigned long long got;  // lane 0
-  long long slot;
-  int p;
-  long long h;
-  long long val;
-  OGJK_DI void start() { stage = 0; }
-  OGJK_DI void step(const StoreArgs<T>& a, const int* __restrict__ list, long long begin, long long end,
-                    unsigned long long* __restrict__ head, int lane) {
-    constexpr unsigned FULL = 0xffffffffu;
-    if (stage == 0) {
-      got = 0;
-      if (lane == 0) got = atomicAdd(head, 1ull);
-      stage = 1;
-    } else if (stage == 1) {
-      slot = begin + (long long)__shfl_sync(FULL, got, 0);
-      p = 0;
-      if (slot < end) { p = list ? list[slot] : (int)slot; stage = 2; } else { stage = 4; }
-    } else if (stage == 2) {
-      const int* idx = (lane & 1) ? a.idx2 : a.idx1;
-      h = idx ? (long long)idx[p] : (long long)p;
-      stage = 3;
-    } else if (stage == 3) {
-      const StoreView<T>& s = (lane & 1) ? a.s2 : a.s1;
-      val = 0;
-      if (lane < 2) val = s.cnt[h];
-      else if (lane < 4) val = s.boff[h];
-      else if (lane < 6) val = s.aoff[h];
-      stage = 4;
-    }
+// Safety net: a pair routed here without two tables takes the plain warp-wide scans.
+template <typename T>
+__device__ __noinline__ void t3_plain_pair(const StoreArgs<T>& a, long long p, long long h1, long long h2, int n1, int n2,
+                                           int lane) {
+  const GroupBody<T, 32> b1{a.s1.data + a.s1.boff[h1], n1, pad4(n1), lane, 0xffffffffu};
+  const GroupBody<T, 32> b2{a.s2.data + a.s2.boff[h2], n2, pad4(n2), lane, 0xffffffffu};
+  Splx<T> s;
+  V3<T> w1, w2;
+  const T d = gjk_query<T>(b1, b2, s, w1, w2);
+  if (lane == 0) {
+    a.distances[p] = d;
+    if (a.simplices) store_simplex(a.simplices + p, s, w1, w2);
   }
-  OGJK_DI T2Desc finish(const StoreArgs<T>& a, const int* __restrict__ list, long long begin, long long end,
-                        unsigned long long* __restrict__ head, int lane) {
-    constexpr unsigned FULL = 0xffffffffu;
-    while (stage < 4) step(a, list, begin, end, head, lane);
-    T2Desc d;
-    d.slot = slot; d.p = p;
-    d.n1 = d.n2 = 0; d.boff1 = d.boff2 = d.aoff1 = d.aoff2 = 0;
-    if (slot < end) {
-      d.n1 = (int)__shfl_sync(FULL, val, 0); d.n2 = (int)__shfl_sync(FULL, val, 1);
-      d.boff1 = __shfl_sync(FULL, val, 2); d.boff2 = __shfl_sync(FULL, val, 3);
-      d.aoff1 = __shfl_sync(FULL, val, 4); d.aoff2 = __shfl_sync(FULL, val, 5);
-    }
-    return d;
-  }
-};
+}
 
 template <typename T>
-__global__ void __launch_bounds__(128, (sizeof(T) == 8 ? OGJK_LB_TABLE2_F64 : OGJK_LB_TABLE2_F32))
-gjk_table2_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* __restrict__ seg_begin,
+__global__ void __launch_bounds__(128, (sizeof(T) == 8 ? OGJK_LB_TABLE3_F64 : OGJK_LB_TABLE3_F32))
+gjk_table3_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* __restrict__ seg_begin,
                   const unsigned* __restrict__ seg_end, unsigned long long* __restrict__ head) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const long long begin = seg_begin ? (long long)*seg_begin : 0;
   const long long end = seg_end ? (long long)*seg_end : a.npairs;
-#if OGJK_T2_PARK
-  __shared__ T2Park<T> park[4];
-  T2Park<T>* slot = &park[threadIdx.x >> 5];
+#if OGJK_T3_PARK
+  __shared__ T3Park<T> park[4];
+  T3Park<T>* pslot = &park[threadIdx.x >> 5];
 #endif
-  T2Pipe<T> pipe;
-  pipe.start();
-  T2Desc d = pipe.finish(a, list, begin, end, head, lane);
-  while (d.slot < end) {
-    pipe.start();
-#if OGJK_T2_PREFETCH
-    pipe.step(a, list, begin, end, head, lane);  // queue grab for the next pair
-#endif
-    const GroupBody<T, 32> b1{a.s1.data + d.boff1, d.n1, pad4(d.n1), lane, FULL};
-    const GroupBody<T, 32> b2{a.s2.data + d.boff2, d.n2, pad4(d.n2), lane, FULL};
-    T2Side<T> S[2];
-    S[0].open(a.s1.accel + d.aoff1, d.n1, lane);
-    S[1].open(a.s2.accel + d.aoff2, d.n2, lane);
+  for (;;) {
+    unsigned long long got = 0;
+    if (lane == 0) got = atomicAdd(head, 1ull);
+    got = __shfl_sync(FULL, got, 0);
+    const long long slot = begin + (long long)got;
+    if (slot >= end) break;
+    const long long p = list ? (long long)list[slot] : slot;
+    const long long h1 = a.idx1 ? (long long)a.idx1[p] : p;
+    const long long h2 = a.idx2 ? (long long)a.idx2[p] : p;
+    const int n1 = a.s1.cnt[h1], n2 = a.s2.cnt[h2];
+    const bool t1 = a.s1.accel && n1 >= a.s1.accel_min && n1 <= kAccelMaxVerts;
+    const bool t2 = a.s2.accel && n2 >= a.s2.accel_min && n2 <= kAccelMaxVerts;
+    if (!(t1 && t2)) { t3_plain_pair(a, p, h1, h2, n1, n2, lane); continue; }
+    const GroupBody<T, 32> b1{a.s1.data + a.s1.boff[h1], n1, pad4(n1), lane, FULL};
+    const GroupBody<T, 32> b2{a.s2.data + a.s2.boff[h2], n2, pad4(n2), lane, FULL};
+    T3Side<T> S[2];
+    S[0].open(a.s1.accel + a.s1.aoff[h1], n1, lane);
+    S[1].open(a.s2.accel + a.s2.aoff[h2], n2, lane);
     GjkState<T> st;
     gjk_init(b1, b2, st);
     bool done;
     do {
       st.k++;
-#if OGJK_T2_PARK
-      t2_park(slot, st, lane);
-      t2_support_both(S, lane, st.v, st.sa, st.ia, st.sb, st.ib);
-      t2_unpark(slot, st);
+#if OGJK_T3_PARK
+      t3_park(pslot, st, lane);
+      t3_support_both(S, lane, st.v, st.sa, st.ia, st.sb, st.ib);
+      t3_unpark(pslot, st);
 #else
-      t2_support_both(S, lane, st.v, st.sa, st.ia, st.sb, st.ib);
+      t3_support_both(S, lane, st.v, st.sa, st.ia, st.sb, st.ib);
 #endif
       done = gjk_step_tail(st);
-#if OGJK_T2_PREFETCH
-      pipe.step(a, list, begin, end, head, lane);
-#endif
     } while (!done);
     Splx<T> s = st.s;
     V3<T> w1, w2;
     gjk_witnesses(b1, b2, s, w1, w2);
     if (lane == 0) {
-      a.distances[d.p] = sqrt(nrm2(st.v.x, st.v.y, st.v.z));
-      if (a.simplices) store_simplex(a.simplices + d.p, s, w1, w2);
+      a.distances[p] = sqrt(nrm2(st.v.x, st.v.y, st.v.z));
+      if (a.simplices) store_simplex(a.simplices + p, s, w1, w2);
     }
-    d = pipe.finish(a, list, begin, end, head, lane);
   }
 }
 

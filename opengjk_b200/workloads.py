@@ -184,6 +184,40 @@ def tiny_bodies(npairs_per_shape=200, seed=7, scale=1.0, dtype=np.float64):
     return Workload(f"tiny_s{scale:g}", pts.astype(dtype), off, cnt, pa, pa + 1)
 
 
+def cap_stress(npairs, seed=11, dtype=np.float64, base=None):
+    """Pairs that end on the iteration cap (scalar/openGJK.c:1036-1042): rigid motions and tiny
+    perturbations of one cap-prone configuration (`base` = (a, b) vertex arrays; the tests pass
+    tests/golden/cap_pair.npz, a pair of the default bench workload).  Roughly 60-100 % of the
+    variants run all 25 iterations in either precision; the mix is rotate / translate /
+    jitter 1e-9 / jitter 1e-6 / slide body 2 by ~1e-3 / power-of-two scale, in equal parts."""
+    a, b = (np.asarray(x, dtype=np.float64) for x in base)
+    rng = np.random.default_rng(seed)
+    A, B = [], []
+    for i in range(npairs):
+        kind = i % 6
+        if kind == 0:
+            q = rng.normal(size=4)
+            q /= np.linalg.norm(q)
+            w_, x, y, z = q
+            r = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w_), 2 * (x * z + y * w_)],
+                          [2 * (x * y + z * w_), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w_)],
+                          [2 * (x * z - y * w_), 2 * (y * z + x * w_), 1 - 2 * (x * x + y * y)]])
+            A.append(a @ r.T); B.append(b @ r.T)
+        elif kind == 1:
+            t = rng.normal(size=3) * 3
+            A.append(a + t); B.append(b + t)
+        elif kind == 2:
+            A.append(a + rng.normal(size=a.shape) * 1e-9); B.append(b + rng.normal(size=b.shape) * 1e-9)
+        elif kind == 3:
+            A.append(a + rng.normal(size=a.shape) * 1e-6); B.append(b + rng.normal(size=b.shape) * 1e-6)
+        elif kind == 4:
+            A.append(a); B.append(b + rng.normal(size=3) * 1e-3)
+        else:
+            f = 2.0 ** int(rng.integers(-20, 21))
+            A.append(a * f); B.append(b * f)
+    return from_bodies(A, B, dtype, "cap_stress")
+
+
 def from_bodies(bodies_a, bodies_b, dtype=np.float64, name="explicit"):
     """Explicit list of (n_i,3) arrays for each side."""
     allb = []

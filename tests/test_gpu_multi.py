@@ -144,7 +144,7 @@ def test_multi_argument_errors():
     try:
         w = W.mixed_hulls(100, seed=96, dtype=np.float32)
         bad = w.off.copy()
-        bad[5] = 10**9
+        bad[4] = 10**9
         with pytest.raises(api.OpenGJKError):
             m.gjk_host_pools(w.coords, bad[w.pa], w.cnt[w.pa], w.coords, w.off[w.pb], w.cnt[w.pb])
     finally:

@@ -364,3 +364,50 @@ def test_scheduler_edge_cases(eng, prec, dt):
     _assert_same("all_classes", d, s, dref, sref, prec)
     d, s = eng.run_workload(w)
     _assert_same("all_classes_host", d, s, dref, sref, prec)
+
+
+@pytest.mark.parametrize("prec,dt", PRECS)
+def test_iteration_cap_exit_every_kernel_flavour(eng, eng_exp, prec, dt):
+    """>= 1000 pairs that end on the iteration cap (scalar/openGJK.c:1036-1042, k == mk:
+    witnesses of a non-converged simplex) through every kernel flavour, byte-equal to the
+    oracle and -- when oracle/_ref travelled -- to the unmodified reference library."""
+    from tests.test_oracle import _cap_workload
+    w = _cap_workload(dt, 6000, 12)
+    dref, sref, it = Oracle(prec).batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1, want_iters=True)
+    assert int((it >= 25).sum()) >= 1000
+    if Reference.available(prec):
+        saved = os.dup(1)
+        null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(null, 1)
+        try:
+            dr, sr = Reference(prec).batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(null)
+        _assert_same("cap/oracle-vs-reference", dref, sref, dr, sr, prec)
+    for mode in (api.MODE_AUTO, api.MODE_THREAD, api.MODE_WARP):
+        d, s = _gpu(eng, w, mode)
+        _assert_same(f"cap/mode{mode}", d, s, dref, sref, prec)
+    tables = [[(2048, g)] for g in (1, 2, 4, 8, 16, 32)]
+    exp_tables = [[(2048, 100 + 4)], [(2048, 200 + 2)], [(2048, 300 + 8)], [(2048, 500 + 4)]]
+    try:
+        for t in tables:
+            eng.set_classes(t)
+            d, s = _gpu(eng, w)
+            _assert_same(f"cap/classes{t}", d, s, dref, sref, prec)
+        for t in tables[:3] + exp_tables:
+            eng_exp.set_classes(t)
+            d, s = _gpu(eng_exp, w)
+            _assert_same(f"cap/exp classes{t}", d, s, dref, sref, prec)
+        eng_exp.set_classes([(2048, 2)])
+        eng_exp.set_passes(3, 4, 3)
+        d, s = _gpu(eng_exp, w)
+        _assert_same("cap/passes", d, s, dref, sref, prec)
+    finally:
+        eng.set_classes(DEFAULT_CLASSES)
+        eng_exp.set_classes(DEFAULT_CLASSES)
+        eng_exp.set_passes(1)
+    # host entry points (chunked and one-shot pipelines) and the packed store
+    d, s = eng.gjk_host_pools(*w.two_pools())
+    _assert_same("cap/host pools", d, s, dref, sref, prec)

@@ -231,3 +231,32 @@ def test_iteration_cap_never_hit_on_synthetic(o64):
     w = W.mixed_hulls(20000, seed=2)
     _, _, it = o64.batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=4, want_iters=True)
     assert it.max() < 25 and it.min() >= 1
+
+
+def _cap_workload(dt, n=3000, seed=11):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cap_pair.npz"))
+    return W.cap_stress(n, seed, dt, base=(g["a"], g["b"]))
+
+
+@pytest.mark.parametrize("prec,dt", [("f64", np.float64), ("f32", np.float32)])
+def test_iteration_cap_exit_restatement_equals_reference(prec, dt):
+    """The k == mk exit (scalar/openGJK.c:1036-1042: witnesses from a non-converged simplex):
+    >= 1000 pairs that run all 25 iterations, restatement byte-equal to the unmodified reference."""
+    w = _cap_workload(dt)
+    o = Oracle(prec)
+    d, s, it = o.batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1, want_iters=True)
+    assert int((it >= 25).sum()) >= 1000, int((it >= 25).sum())
+    if not Reference.available(prec):
+        pytest.skip("oracle/_ref not built")
+    import contextlib
+    with open(os.devnull, "w") as devnull:
+        saved = os.dup(1)
+        os.dup2(devnull.fileno(), 1)   # the reference prints a banner per cap hit
+        try:
+            dr, sr = Reference(prec).batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+    assert d.tobytes() == dr.tobytes()
+    for f in ("nvrtx", "vrtx", "vrtx_idx", "witnesses"):
+        assert np.ascontiguousarray(s[f]).tobytes() == np.ascontiguousarray(sr[f]).tobytes(), f
