@@ -183,6 +183,52 @@ class ClockSampler:
                 "reasons": [n for n, b in self.REASONS.items() if self.bits & b], "samples": len(sm)}
 
 
+ORIG_AFFINITY = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+
+
+@contextlib.contextmanager
+def all_host_cores():
+    """CPU baselines and the one-process multi-GPU run use every core the job was given, not just the
+    NUMA node a rank was bound to."""
+    cur = os.sched_getaffinity(0) if ORIG_AFFINITY is not None else None
+    if cur is not None and cur != ORIG_AFFINITY:
+        os.sched_setaffinity(0, ORIG_AFFINITY)
+    try:
+        yield
+    finally:
+        if cur is not None and cur != ORIG_AFFINITY:
+            os.sched_setaffinity(0, cur)
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, BEFORE any pinned host
+    buffer is allocated (first touch then places the pools next to the GPU's PCIe root).  Round 1
+    measured the host-buffer path at 0.48 / 0.37 of linear on 4 / 8 GPUs with unbound ranks.
+    Best effort: returns a short description or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:      # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"numa node {node} ({len(cpus)} cpus)"
+    except Exception:
+        return None
+
+
 def strided_sample(w, m):
     """m pairs of the workload taken at a fixed stride (keeps the mix of a workload built from slices)."""
     if w.npairs <= m:
@@ -223,7 +269,7 @@ def cpu_baseline(w, prec, budget_s=10.0, epa=False, sample_note=None):
     else:
         kind, o = "port", Oracle(prec)
         run = lambda nt: (lambda: o.batch(ws.coords, ws.off, ws.cnt, ws.pa, ws.pb, nthreads=nt))
-    with quiet_stdout():
+    with quiet_stdout(), all_host_cores():
         v_all, reps, dt = _timed_passes(run(cores), n, budget_s)
         # one thread: a 1/8 slice of the sample, a quarter of the budget
         m1 = max(1, n // 8)
@@ -346,6 +392,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -582,8 +629,11 @@ def main():
             # as run_store_batch routes: pairs whose two bodies both carry a table run the table kernel,
             # timed with the last class
             if store.table_bytes > 0 and dom == len(CLASS_TABLE) - 1 and min_cnt >= amin:
+                # default routing: pairs with a body above 1024 vertices -> tile kernel, the others -> first-generation kernel
                 tl = int(os.environ.get("OGJK_TABLE_LANES", 0))
-                kname = f"gjk_table3_kernel<{tname}>" if tl == 0 else f"gjk_table_kernel<{tname},{tl}>"
+                big = int(d_cnt.max().item()) > 1024
+                kname = (f"gjk_table3_kernel<{tname}>" if (tl == 3 or (tl == 0 and big))
+                         else f"gjk_table_kernel<{tname},{tl if tl in (8, 16, 32) else 32}>")
             else:
                 kname = f"gjk_small_kernel<{tname}>" if lanes == 0 else f"gjk_group_kernel<{tname},{lanes}>"
         traffic, traffic_src = traffic_for(name)
@@ -714,9 +764,13 @@ def main():
         dist.barrier(group=cpu_group)
         if rank == 0:
             try:
+                if ORIG_AFFINITY is not None:
+                    os.sched_setaffinity(0, ORIG_AFFINITY)  # this process now drives every GPU
                 prec = "f64" if dt == np.float64 else "f32"
                 sdt = api.SIMPLEX_F64 if prec == "f64" else api.SIMPLEX_F32
-                n = (args.pairs or default_pairs) * world
+                # the whole job of the main workload, capped at 2 M pairs (host generation + three host
+                # copies of an 8 x 1 M fp64 job would need > 40 GB and a minute of numpy time)
+                n = min((args.pairs or default_pairs) * world, 2_000_000)
                 w = maker(n, args.seed)
                 pools = [pin(x).numpy() for x in w.two_pools()]
                 o = (torch.empty(n, dtype=torch.float64 if prec == "f64" else torch.float32).pin_memory().numpy(),
@@ -771,6 +825,7 @@ def main():
                            + ("> 126 MB L2 (no flush needed)" if main_res["input_bytes_per_gpu"] > L2_BYTES
                               else "< L2: numbers are L2-warm")),
                     "resident_format": "packed polytope store (ogjk_store_create, outside the timed region)",
+                    "host_binding": numa or "unbound",
                     "scheduler_classes": [list(c) for c in CLASS_TABLE]},
             "roofline": main_res["roofline"], "e2e": main_res["e2e"], "gpu_launches": main_res["launches"],
             "from_raw_arrays": main_res["from_raw_arrays"], "store_build_ms": main_res["store_build_ms"],

@@ -147,10 +147,12 @@ OGJK_API int ogjk_ctx_set_accel_min(ogjk_ctx* ctx, int min_vertices);
  * and resumed densely packed in the next pass, so that warps do not idle on their slowest
  * pair.  passes = 1 is the one-pass kernel.  A tuning knob; results do not depend on it. */
 OGJK_API int ogjk_ctx_set_passes(ogjk_ctx* ctx, int passes, int iters1, int iters2);
-/* Kernel that uses the cluster tables: 0 (default) = the warp-per-pair kernel with
- * register-resident cluster boxes and cached support cluster (csrc/table_kernel.cuh);
- * 8, 16 or 32 = the first-generation kernel with that many lanes per pair.  A tuning
- * knob; results do not depend on it. */
+/* Kernels that use the cluster tables.  0 (default): pairs with a body above 1024 vertices run the
+ * tile kernel (csrc/table_kernel.cuh: register-resident cluster boxes, tile boxes, vector cluster
+ * fetches), pairs whose two bodies fit one 32-cluster tile the first-generation kernel with 32
+ * lanes per pair (the faster one at that size on B200).  3 = the tile kernel for every table pair;
+ * 8, 16 or 32 = the first-generation kernel with that many lanes per pair for every table pair.
+ * A tuning knob; results do not depend on it. */
 OGJK_API int ogjk_ctx_set_table_lanes(ogjk_ctx* ctx, int lanes);
 OGJK_API void ogjk_store_destroy(ogjk_store* store);
 OGJK_API int64_t ogjk_store_bytes(const ogjk_store* store);

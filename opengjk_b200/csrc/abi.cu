@@ -11,6 +11,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <new>
 #include <thread>
 #include <vector>
@@ -72,6 +77,93 @@ struct PinBuf {
 
 }  // namespace
 
+// Persistent host threads of a context (created on first use, joined with the context): the
+// struct-array entry points gather the callers' per-polytope vertex arrays with them while
+// earlier chunks are already on their way to the device.  Jobs [0, njobs) are handed out in
+// order through an atomic counter; every job raises its own flag when done, so the caller can
+// wait for a prefix of the job list (one chunk) while later jobs are still running.
+class HostPool {
+ public:
+  explicit HostPool(int nthreads) {
+    for (int t = 0; t < nthreads; ++t) th_.emplace_back([this] { loop(); });
+  }
+  ~HostPool() {
+    { std::lock_guard<std::mutex> lk(mu_); quit_ = true; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  int size() const { return (int)th_.size(); }
+  // Starts njobs calls fn(job) on the pool; returns at once.  One batch at a time.
+  void start(int njobs, std::function<void(int)> fn) {
+    wait_all();
+    auto b = std::make_shared<Batch>();
+    b->fn = std::move(fn);
+    b->njobs = njobs;
+    b->done.reset(new std::atomic<char>[(size_t)(njobs > 0 ? njobs : 1)]);
+    for (int j = 0; j < njobs; ++j) b->done[(size_t)j].store(0, std::memory_order_relaxed);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      cur_ = b;
+      ++epoch_;
+    }
+    cv_.notify_all();
+  }
+  // Blocks until jobs [0, upto) of the current batch are done.
+  void wait_prefix(int upto) {
+    std::shared_ptr<Batch> b;
+    { std::lock_guard<std::mutex> lk(mu_); b = cur_; }
+    if (!b) return;
+    for (int j = 0; j < upto && j < b->njobs; ++j)
+      while (!b->done[(size_t)j].load(std::memory_order_acquire)) std::this_thread::yield();
+  }
+  void wait_all() {
+    std::shared_ptr<Batch> b;
+    { std::lock_guard<std::mutex> lk(mu_); b = cur_; }
+    if (!b) return;
+    while (b->finished.load(std::memory_order_acquire) < b->njobs) std::this_thread::yield();
+  }
+  void run(int njobs, std::function<void(int)> fn) { start(njobs, std::move(fn)); wait_all(); }
+
+ private:
+  // Every batch owns its counters and flags, so a thread that is late leaving batch k can never
+  // touch batch k+1's state.
+  struct Batch {
+    std::function<void(int)> fn;
+    int njobs = 0;
+    std::atomic<int> next{0}, finished{0};
+    std::unique_ptr<std::atomic<char>[]> done;
+  };
+  void loop() {
+    unsigned long long seen = 0;
+    for (;;) {
+      std::shared_ptr<Batch> b;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return quit_ || epoch_ != seen; });
+        if (quit_) return;
+        seen = epoch_;
+        b = cur_;
+      }
+      for (;;) {
+        const int j = b->next.fetch_add(1);
+        if (j >= b->njobs) break;
+        b->fn(j);
+        b->done[(size_t)j].store(1, std::memory_order_release);
+        b->finished.fetch_add(1, std::memory_order_release);
+      }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::shared_ptr<Batch> cur_;
+  unsigned long long epoch_ = 0;
+  bool quit_ = false;
+};
+
+// "The host-side data of polytopes [0, upto) is complete" -- blocks until it is.
+using HostReady = std::function<void(int64_t upto)>;
+
 constexpr int kPhases = 8;   // timing slots: pack, sort, then up to six size classes
 constexpr int kMaxClasses = 6;
 
@@ -107,7 +199,7 @@ struct ogjk_ctx_ {
   int passes = 1;
   int pass_iters[2] = {4, 3};
   DevBuf pass_list[2], pass_f[2], pass_i[2];
-  int table_lanes = 0;   // 0: second-generation warp-per-pair table kernel (table_kernel.cuh); 8/16/32: the first one
+  int table_lanes = 0;   // 0: tile kernel (table_kernel.cuh) above 1024 vertices, first-generation kernel below; 3 / 8,16,32: force one
   bool timing = false;
   cudaEvent_t ev[2 * kPhases] = {};
   int timed_mask = 0;
@@ -126,6 +218,7 @@ struct ogjk_ctx_ {
   // staging for the host-buffer paths
   DevBuf d_coords1, d_coords2, d_off1, d_off2, d_cnt1, d_cnt2, d_idx1, d_idx2, d_simp, d_dist;
   PinBuf h_stage;
+  HostPool* pool = nullptr;  // host threads for the struct-array gathers (lazy)
 };
 
 namespace {
@@ -516,18 +609,33 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
     // sorted in front of everything else (store.cuh, kNumBinsAll) and run through the
     // pruned-scan kernel; timed with the last class.
     if (tables && c == last_run) {
-      const unsigned* tb = start + (kNumBinsAll - 1);  // = 0 pairs above the top bin
-      const unsigned* te = start + (kNumBins - 1);     // = pairs in the table bins
-      switch (ctx->table_lanes) {
-        case 8: launch_table<T, 8>(ctx, a, sorted, tb, te, counters + 6, st); break;
-        case 16: launch_table<T, 16>(ctx, a, sorted, tb, te, counters + 6, st); break;
-        case 32: launch_table<T, 32>(ctx, a, sorted, tb, te, counters + 6, st); break;
-        default: {
-          long long blocks = (a.npairs * 32 + 127) / 128, cap = (long long)ctx->sm_count * 16;
-          gjk_table3_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, sorted, tb, te, counters + 6);
-        } break;
+      // [0, *t_mid): pairs with a body above one tile (1024 vertices); [*t_mid, *t_end): both bodies within one
+      const unsigned* t_beg = start + (kNumBinsAll - 1);          // = 0 pairs above the top bin
+      const unsigned* t_mid = start + (kNumBins + kTableBins - 1);  // = pairs in the multi-tile bins
+      const unsigned* t_end = start + (kNumBins - 1);             // = pairs in all table bins
+      auto gen1 = [&](int lanes1, const unsigned* sb, const unsigned* se, unsigned long long* h) {
+        switch (lanes1) {
+          case 8: launch_table<T, 8>(ctx, a, sorted, sb, se, h, st); break;
+          case 16: launch_table<T, 16>(ctx, a, sorted, sb, se, h, st); break;
+          default: launch_table<T, 32>(ctx, a, sorted, sb, se, h, st); break;
+        }
+      };
+      auto gen3 = [&](const unsigned* sb, const unsigned* se, unsigned long long* h) {
+        long long blocks = (a.npairs * 32 + 127) / 128, cap = (long long)ctx->sm_count * 16;
+        gjk_table3_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, sorted, sb, se, h);
+      };
+      const int tl = ctx->table_lanes;
+      if (tl == 0) {          // default: the tile kernel above one tile, the first-generation kernel below
+        gen3(t_beg, t_mid, counters + 6);
+        gen1(32, t_mid, t_end, counters + 7);
+      } else if (tl == 3) {   // tuning: the tile kernel for everything
+        gen3(t_beg, t_mid, counters + 6);
+        gen3(t_mid, t_end, counters + 7);
+      } else {                // tuning: the first-generation kernel with 8 / 16 / 32 lanes per pair
+        gen1(tl, t_beg, t_mid, counters + 6);
+        gen1(tl, t_mid, t_end, counters + 7);
       }
-      ctx->launches += 1;
+      ctx->launches += 2;
     }
     switch (lanes) {
       case 0: {
@@ -662,7 +770,8 @@ int upload(ogjk_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
 template <typename T, typename S>
 int host_pipeline_chunked(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t* off1, const int* cnt1,
                           int64_t nverts1, const T* coords2, const int64_t* off2, const int* cnt2, int64_t nverts2,
-                          S* simplices, T* distances, T* w1, T* w2, T* normals, bool run_epa) {
+                          S* simplices, T* distances, T* w1, T* w2, T* normals, bool run_epa,
+                          const HostReady* ready = nullptr) {
   const int K = ctx->pipeline_chunks > 16 ? 16 : ctx->pipeline_chunks;
   if (K < 2 || npairs < 4096 * (int64_t)K) return 1;
   // chunk coordinate ranges; require monotone, gap-free-ish layouts
@@ -720,15 +829,23 @@ int host_pipeline_chunked(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const
     ctx->launches += 2;
   }
 
-  for (int c = 0; c < K; ++c) {
+  // H2D of chunk c is issued as soon as the caller says its host data is complete (struct-array
+  // entry points gather chunk c+1 on the context's host threads while chunk c is in flight)
+  auto h2d = [&](int c) -> int {
+    if (ready) (*ready)(r[c].hi);
     CU(cudaMemcpyAsync(static_cast<T*>(ctx->d_coords1.p) + 3 * r[c].a1, coords1 + 3 * r[c].a1,
                        (size_t)(r[c].b1 - r[c].a1) * 3 * sizeof(T), cudaMemcpyHostToDevice, si));
     CU(cudaMemcpyAsync(static_cast<T*>(ctx->d_coords2.p) + 3 * r[c].a2, coords2 + 3 * r[c].a2,
                        (size_t)(r[c].b2 - r[c].a2) * 3 * sizeof(T), cudaMemcpyHostToDevice, si));
     CU(cudaEventRecord(ctx->chunk_in[c], si));
-  }
+    return OGJK_OK;
+  };
+  if (!ready)
+    for (int c = 0; c < K; ++c)
+      if ((rc = h2d(c))) return rc;
   for (int c = 0; c < K; ++c) {
     const int64_t lo = r[c].lo, n = r[c].hi - r[c].lo;
+    if (ready && (rc = h2d(c))) return rc;
     CU(cudaStreamWaitEvent(sc, ctx->chunk_in[c], 0));
     if ((rc = store_pack_range<T>(ctx, &ctx->scratch1, lo, r[c].hi, dc1, do1, sc))) return rc;
     if ((rc = store_pack_range<T>(ctx, &ctx->scratch2, lo, r[c].hi, dc2, do2, sc))) return rc;
@@ -777,7 +894,7 @@ template <typename T, typename S>
 int host_pipeline(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t* off1, const int* cnt1, int64_t npoly1,
                   int64_t nverts1, const int* idx1, const T* coords2, const int64_t* off2, const int* cnt2, int64_t npoly2,
                   int64_t nverts2, const int* idx2, S* simplices, T* distances, T* w1, T* w2, T* normals, bool run_gjk,
-                  bool run_epa) {
+                  bool run_epa, const HostReady* ready = nullptr) {
   if (!ctx) return fail(OGJK_ERR_ARG, "ctx is NULL%s");
   if (npairs < 0 || npoly1 < 0 || npoly2 < 0 || nverts1 < 0 || nverts2 < 0) return fail(OGJK_ERR_ARG, "negative count%s");
   if (npairs == 0) return OGJK_OK;
@@ -791,9 +908,10 @@ int host_pipeline(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t
   const bool need_simp = simplices != nullptr || run_epa;
   if (run_gjk && !idx1 && !idx2 && !shared_pool && npoly1 >= npairs && npoly2 >= npairs) {
     const int rcc = host_pipeline_chunked<T, S>(ctx, npairs, coords1, off1, cnt1, nverts1, coords2, off2, cnt2, nverts2,
-                                                simplices, distances, w1, w2, normals, run_epa);
+                                                simplices, distances, w1, w2, normals, run_epa, ready);
     if (rcc <= 0) return rcc;  // done (0) or error (<0); 1 = layout not chunkable, use the one-shot path
   }
+  if (ready) (*ready)(npoly1 > npoly2 ? npoly1 : npoly2);  // one-shot path: everything must be in place
   int rc;
   if ((rc = upload(ctx, ctx->d_coords1, coords1, (size_t)nverts1 * 3 * sizeof(T)))) return rc;
   if ((rc = upload(ctx, ctx->d_off1, off1, (size_t)npoly1 * sizeof(int64_t)))) return rc;
@@ -866,54 +984,111 @@ int gjk_host(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t* off
                              idx2, simplices, distances, nullptr, nullptr, nullptr, true, false);
 }
 
-// Flatten an array of reference-shaped polytope structs (each with its own
-// host `coord` block) into one pinned pool: [coords | off | cnt].
-template <typename T, typename P>
-int flatten(ogjk_ctx* ctx, size_t base, int n, const P* bd, size_t* bytes_used, T** coords, int64_t** off, int** cnt,
-            int64_t* nverts) {
-  int64_t total = 0;
-  for (int i = 0; i < n; ++i) {
-    if (bd[i].numpoints < 1 || !bd[i].coord) return fail(OGJK_ERR_ARG, "polytope with no vertices%s");
-    total += bd[i].numpoints;
+HostPool* host_pool(ogjk_ctx* ctx) {
+  if (!ctx->pool) {
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt > 32 ? 32 : (nt < 2 ? 2 : nt);
+    ctx->pool = new (std::nothrow) HostPool((int)nt);
   }
-  size_t need = (size_t)total * 3 * sizeof(T) + (size_t)n * (sizeof(int64_t) + sizeof(int)) + 64;
-  char* p = static_cast<char*>(ctx->h_stage.p) + base;
-  (void)need;
-  T* c = reinterpret_cast<T*>(p);
-  size_t cbytes = ((size_t)total * 3 * sizeof(T) + 15) & ~(size_t)15;
-  int64_t* o = reinterpret_cast<int64_t*>(p + cbytes);
-  int* k = reinterpret_cast<int*>(p + cbytes + (size_t)n * sizeof(int64_t));
-  int64_t at = 0;
-  for (int i = 0; i < n; ++i) {
-    o[i] = at;
-    k[i] = bd[i].numpoints;
-    at += bd[i].numpoints;
-  }
-  // gather the per-polytope vertex arrays (the reference copies each one to the device with its own
-  // cudaMemcpy, gpu/opengjk_gpu.cu:3105-3166); many small host copies, spread over a few threads
-  auto gather = [&](int lo, int hi) {
-    for (int i = lo; i < hi; ++i) memcpy(c + 3 * o[i], bd[i].coord, (size_t)bd[i].numpoints * 3 * sizeof(T));
-  };
-  unsigned nt = std::thread::hardware_concurrency();
-  nt = nt > 16 ? 16 : (nt < 1 ? 1 : nt);
-  if (n < 4096 || nt == 1) {
-    gather(0, n);
-  } else {
-    std::vector<std::thread> pool;
-    pool.reserve(nt);
-    for (unsigned t = 0; t < nt; ++t)
-      pool.emplace_back(gather, (int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt));
-    for (auto& th : pool) th.join();
-  }
-  *coords = c; *off = o; *cnt = k; *nverts = total;
-  *bytes_used = ((cbytes + (size_t)n * (sizeof(int64_t) + sizeof(int))) + 63) & ~(size_t)63;
-  return OGJK_OK;
+  return ctx->pool;
 }
 
-template <typename P> size_t flat_bytes(int n, const P* bd, size_t tsize) {
-  size_t total = 0;
-  for (int i = 0; i < n; ++i) total += bd[i].numpoints > 0 ? (size_t)bd[i].numpoints : 0;
-  return ((((total * 3 * tsize + 15) & ~(size_t)15) + (size_t)n * 12 + 128) + 63) & ~(size_t)63;
+// An array of reference-shaped polytope structs (each with its own host `coord` block) laid
+// out as one pinned pool [coords | off | cnt] inside ctx->h_stage (the reference copies each
+// block to the device with its own cudaMemcpy, gpu/opengjk_gpu.cu:3105-3166).
+template <typename T> struct FlatSide { T* coords; int64_t* off; int* cnt; int64_t nverts; size_t bytes; };
+
+// Pass 1 (two short parallel sweeps over the structs): counts and offsets of every polytope --
+// the scheduler needs them for the whole batch before the first chunk leaves.  `sums` receives
+// one partial vertex total per job of kGatherJob polytopes; returns the vertex total or -1 when a
+// polytope has no vertices.
+constexpr int kGatherJob = 8192;
+template <typename P>
+int64_t struct_totals(ogjk_ctx* ctx, int n, const P* bd, std::vector<int64_t>& sums) {
+  const int njobs = (n + kGatherJob - 1) / kGatherJob;
+  sums.assign((size_t)njobs, 0);
+  std::atomic<int> bad{0};
+  auto job = [&](int j) {
+    const int lo = j * kGatherJob, hi = lo + kGatherJob < n ? lo + kGatherJob : n;
+    int64_t t = 0;
+    for (int i = lo; i < hi; ++i) {
+      if (bd[i].numpoints < 1 || !bd[i].coord) { bad.store(1); return; }
+      t += bd[i].numpoints;
+    }
+    sums[(size_t)j] = t;
+  };
+  HostPool* pool = host_pool(ctx);
+  if (pool && njobs >= 4) pool->run(njobs, job);
+  else for (int j = 0; j < njobs; ++j) job(j);
+  if (bad.load()) return -1;
+  int64_t total = 0;
+  for (int j = 0; j < njobs; ++j) { const int64_t t = sums[(size_t)j]; sums[(size_t)j] = total; total += t; }  // exclusive
+  return total;
+}
+inline size_t flat_bytes(int64_t total, int n, size_t tsize) {
+  return (((((size_t)total * 3 * tsize + 15) & ~(size_t)15) + (size_t)n * 12 + 128) + 63) & ~(size_t)63;
+}
+template <typename T, typename P>
+void flat_layout(ogjk_ctx* ctx, size_t base, int n, const P* bd, int64_t total, const std::vector<int64_t>& sums,
+                 FlatSide<T>* out) {
+  char* p = static_cast<char*>(ctx->h_stage.p) + base;
+  const size_t cbytes = ((size_t)total * 3 * sizeof(T) + 15) & ~(size_t)15;
+  out->coords = reinterpret_cast<T*>(p);
+  out->off = reinterpret_cast<int64_t*>(p + cbytes);
+  out->cnt = reinterpret_cast<int*>(p + cbytes + (size_t)n * sizeof(int64_t));
+  out->nverts = total;
+  out->bytes = ((cbytes + (size_t)n * (sizeof(int64_t) + sizeof(int))) + 63) & ~(size_t)63;
+  const int njobs = (n + kGatherJob - 1) / kGatherJob;
+  int64_t* off = out->off;
+  int* cnt = out->cnt;
+  auto job = [&, off, cnt](int j) {
+    const int lo = j * kGatherJob, hi = lo + kGatherJob < n ? lo + kGatherJob : n;
+    int64_t at = sums[(size_t)j];
+    for (int i = lo; i < hi; ++i) { off[i] = at; cnt[i] = bd[i].numpoints; at += bd[i].numpoints; }
+  };
+  HostPool* pool = host_pool(ctx);
+  if (pool && njobs >= 4) pool->run(njobs, job);
+  else for (int j = 0; j < njobs; ++j) job(j);
+}
+
+// Pass 2: the coordinate gather of up to two sides, cut into jobs of kGatherJob polytopes in
+// polytope order and started on the context's host threads.  Returns the HostReady callback
+// that waits for a prefix of the polytopes.
+template <typename T, typename P>
+HostReady start_gather(ogjk_ctx* ctx, int n, const P* bd1, const FlatSide<T>& f1, const P* bd2, const FlatSide<T>* f2) {
+  HostPool* pool = host_pool(ctx);
+  const int njobs = (n + kGatherJob - 1) / kGatherJob;
+  auto job = [=](int j) {
+    const int lo = j * kGatherJob, hi = lo + kGatherJob < n ? lo + kGatherJob : n;
+    for (int i = lo; i < hi; ++i) memcpy(f1.coords + 3 * f1.off[i], bd1[i].coord, (size_t)bd1[i].numpoints * 3 * sizeof(T));
+    if (f2)
+      for (int i = lo; i < hi; ++i) memcpy(f2->coords + 3 * f2->off[i], bd2[i].coord, (size_t)bd2[i].numpoints * 3 * sizeof(T));
+  };
+  if (!pool || n < 2 * kGatherJob) {  // small batch (or no threads): gather inline
+    for (int j = 0; j < njobs; ++j) job(j);
+    return HostReady([](int64_t) {});
+  }
+  pool->start(njobs, job);
+  return HostReady([pool](int64_t upto) { pool->wait_prefix((int)((upto + kGatherJob - 1) / kGatherJob)); });
+}
+
+// Lays both sides out in the pinned stage and starts the gather.  On success *ready waits for a
+// prefix of the polytopes; the caller MUST drain it (ready(n)) before returning.
+template <typename T, typename P>
+int stage_structs(ogjk_ctx* ctx, int n, const P* bd1, const P* bd2, size_t extra, FlatSide<T>* f1, FlatSide<T>* f2,
+                  HostReady* ready, size_t* extra_at) {
+  std::vector<int64_t> s1, s2;
+  const int64_t t1 = struct_totals(ctx, n, bd1, s1);
+  const int64_t t2 = bd2 ? struct_totals(ctx, n, bd2, s2) : 0;
+  if (t1 < 0 || t2 < 0) return fail(OGJK_ERR_ARG, "polytope with no vertices%s");
+  const size_t b1 = flat_bytes(t1, n, sizeof(T)), b2 = bd2 ? flat_bytes(t2, n, sizeof(T)) : 0;
+  int rc = ctx->h_stage.reserve(b1 + b2 + extra);
+  if (rc) return rc;
+  flat_layout<T, P>(ctx, 0, n, bd1, t1, s1, f1);
+  if (bd2) flat_layout<T, P>(ctx, b1, n, bd2, t2, s2, f2);
+  if (extra_at) *extra_at = b1 + b2;
+  *ready = start_gather<T, P>(ctx, n, bd1, *f1, bd2, bd2 ? f2 : nullptr);
+  return OGJK_OK;
 }
 
 template <typename T, typename P, typename S>
@@ -921,13 +1096,14 @@ int compute_min_dist(ogjk_ctx* ctx, int n, const P* bd1, const P* bd2, S* simpli
   if (n <= 0) return OGJK_OK;  // reference: silent return (gpu/opengjk_gpu.cu:2984)
   if (!ctx || !bd1 || !bd2 || !distances) return fail(OGJK_ERR_ARG, "NULL argument%s");
   CU(cudaSetDevice(ctx->device));
-  size_t b1 = flat_bytes(n, bd1, sizeof(T)), b2 = flat_bytes(n, bd2, sizeof(T));
-  int rc = ctx->h_stage.reserve(b1 + b2);
+  FlatSide<T> f1, f2;
+  HostReady ready;
+  int rc = stage_structs<T, P>(ctx, n, bd1, bd2, 0, &f1, &f2, &ready, nullptr);
   if (rc) return rc;
-  T *c1, *c2; int64_t *o1, *o2; int *k1, *k2; int64_t nv1, nv2; size_t used1, used2;
-  if ((rc = flatten<T, P>(ctx, 0, n, bd1, &used1, &c1, &o1, &k1, &nv1))) return rc;
-  if ((rc = flatten<T, P>(ctx, b1, n, bd2, &used2, &c2, &o2, &k2, &nv2))) return rc;
-  return gjk_host<T, S>(ctx, n, c1, o1, k1, n, nv1, nullptr, c2, o2, k2, n, nv2, nullptr, simplices, distances);
+  rc = host_pipeline<T, S>(ctx, n, f1.coords, f1.off, f1.cnt, n, f1.nverts, nullptr, f2.coords, f2.off, f2.cnt, n, f2.nverts,
+                           nullptr, simplices, distances, nullptr, nullptr, nullptr, true, false, &ready);
+  ready(n);  // never leave gather threads writing into the stage
+  return rc;
 }
 
 // compute_gjk_epa (gpu/opengjk_gpu.cu:3055-3099) and compute_epa (:3007-3053) over struct arrays.
@@ -937,14 +1113,14 @@ int compute_epa_structs(ogjk_ctx* ctx, int n, const P* bd1, const P* bd2, S* sim
   if (n <= 0) return OGJK_OK;
   if (!ctx || !bd1 || !bd2 || !simplices || !distances || !w1 || !w2) return fail(OGJK_ERR_ARG, "NULL argument%s");
   CU(cudaSetDevice(ctx->device));
-  size_t b1 = flat_bytes(n, bd1, sizeof(T)), b2 = flat_bytes(n, bd2, sizeof(T));
-  int rc = ctx->h_stage.reserve(b1 + b2);
+  FlatSide<T> f1, f2;
+  HostReady ready;
+  int rc = stage_structs<T, P>(ctx, n, bd1, bd2, 0, &f1, &f2, &ready, nullptr);
   if (rc) return rc;
-  T *c1, *c2; int64_t *o1, *o2; int *k1, *k2; int64_t nv1, nv2; size_t used1, used2;
-  if ((rc = flatten<T, P>(ctx, 0, n, bd1, &used1, &c1, &o1, &k1, &nv1))) return rc;
-  if ((rc = flatten<T, P>(ctx, b1, n, bd2, &used2, &c2, &o2, &k2, &nv2))) return rc;
-  return host_pipeline<T, S>(ctx, n, c1, o1, k1, n, nv1, nullptr, c2, o2, k2, n, nv2, nullptr, simplices, distances, w1, w2,
-                             normals, run_gjk, true);
+  rc = host_pipeline<T, S>(ctx, n, f1.coords, f1.off, f1.cnt, n, f1.nverts, nullptr, f2.coords, f2.off, f2.cnt, n, f2.nverts,
+                           nullptr, simplices, distances, w1, w2, normals, run_gjk, true, &ready);
+  ready(n);
+  return rc;
 }
 
 template <typename T, typename P, typename S>
@@ -953,21 +1129,26 @@ int compute_min_dist_indexed(ogjk_ctx* ctx, int npoly, int npairs, const P* poly
   if (npairs <= 0 || npoly <= 0) return OGJK_OK;  // reference: silent return (:3292)
   if (!ctx || !polys || !pairs || !distances) return fail(OGJK_ERR_ARG, "NULL argument%s");
   CU(cudaSetDevice(ctx->device));
-  size_t b1 = flat_bytes(npoly, polys, sizeof(T));
-  size_t ib = ((size_t)npairs * sizeof(int) + 63) & ~(size_t)63;
-  int rc = ctx->h_stage.reserve(b1 + 2 * ib);
+  const size_t ib = ((size_t)npairs * sizeof(int) + 63) & ~(size_t)63;
+  FlatSide<T> f, unused;
+  HostReady ready;
+  size_t at = 0;
+  int rc = stage_structs<T, P>(ctx, npoly, polys, static_cast<const P*>(nullptr), 2 * ib, &f, &unused, &ready, &at);
   if (rc) return rc;
-  T* c; int64_t* o; int* k; int64_t nv; size_t used;
-  if ((rc = flatten<T, P>(ctx, 0, npoly, polys, &used, &c, &o, &k, &nv))) return rc;
-  int* i1 = reinterpret_cast<int*>(static_cast<char*>(ctx->h_stage.p) + b1);
-  int* i2 = reinterpret_cast<int*>(static_cast<char*>(ctx->h_stage.p) + b1 + ib);
+  int* i1 = reinterpret_cast<int*>(static_cast<char*>(ctx->h_stage.p) + at);
+  int* i2 = reinterpret_cast<int*>(static_cast<char*>(ctx->h_stage.p) + at + ib);
   for (int p = 0; p < npairs; ++p) {
-    if (pairs[p].idx1 < 0 || pairs[p].idx1 >= npoly || pairs[p].idx2 < 0 || pairs[p].idx2 >= npoly)
+    if (pairs[p].idx1 < 0 || pairs[p].idx1 >= npoly || pairs[p].idx2 < 0 || pairs[p].idx2 >= npoly) {
+      ready(npoly);
       return fail(OGJK_ERR_ARG, "pair index out of range%s");
+    }
     i1[p] = pairs[p].idx1;
     i2[p] = pairs[p].idx2;
   }
-  return gjk_host<T, S>(ctx, npairs, c, o, k, npoly, nv, i1, c, o, k, npoly, nv, i2, simplices, distances);
+  rc = host_pipeline<T, S>(ctx, npairs, f.coords, f.off, f.cnt, npoly, f.nverts, i1, f.coords, f.off, f.cnt, npoly, f.nverts, i2,
+                           simplices, distances, nullptr, nullptr, nullptr, true, false, &ready);
+  ready(npoly);
+  return rc;
 }
 
 template <typename T, typename S>
@@ -1290,6 +1471,7 @@ void ogjk_ctx_destroy(ogjk_ctx* c) {
                     &c->d_cnt1,   &c->d_cnt2,     &c->d_idx1,     &c->d_idx2,    &c->d_simp,    &c->d_dist};
   for (DevBuf* b : bufs) b->release();
   c->h_stage.release();
+  delete c->pool;
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->in_stream) cudaStreamDestroy(c->in_stream);
   if (c->out_stream) cudaStreamDestroy(c->out_stream);
@@ -1554,7 +1736,8 @@ int ogjk_ctx_set_passes(ogjk_ctx* c, int passes, int iters1, int iters2) {
 }
 
 int ogjk_ctx_set_table_lanes(ogjk_ctx* c, int lanes) {
-  if (!c || (lanes != 0 && lanes != 8 && lanes != 16 && lanes != 32)) return fail(OGJK_ERR_ARG, "table lanes must be 0, 8, 16 or 32%s");
+  if (!c || (lanes != 0 && lanes != 3 && lanes != 8 && lanes != 16 && lanes != 32))
+    return fail(OGJK_ERR_ARG, "table lanes must be 0 (default), 3, 8, 16 or 32%s");
   c->table_lanes = lanes;
   return OGJK_OK;
 }

@@ -37,8 +37,10 @@ template <> struct BoxChunk<double> {
 #ifndef OGJK_AABB_LANES
 #define OGJK_AABB_LANES 8  // lanes per polytope (tools/aabb_ab.sh: 8 / 4 / 2 lanes = 87 / 73 / 45 % of HBM peak on 1000-vertex bodies, 47-50 % on 8-64-vertex ones)
 #endif
+// 8 resident blocks per SM for fp32 (32 registers); fp64 needs 12 running extrema of two
+// registers each plus the loads in flight and spilled 172 bytes at that cap, so it runs at 4.
 template <typename T>
-__global__ void __launch_bounds__(256, 8)
+__global__ void __launch_bounds__(256, (sizeof(T) == 8 ? 4 : 8))
 aabb_kernel(StoreView<T> s, long long npoly, T* __restrict__ out) {
   constexpr int CV = BoxChunk<T>::kVerts;
   constexpr int L = OGJK_AABB_LANES;

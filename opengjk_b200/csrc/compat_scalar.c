@@ -3,6 +3,7 @@
  * (the reference function is re-entrant, so concurrent callers are serialised here). */
 #include <math.h>
 #include <pthread.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "openGJK/openGJK.h"
@@ -21,8 +22,16 @@ typedef ogjk_simplex_f64 simplex_t;
 static ogjk_ctx* g_ctx;
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 
+/* Called with g_lock held (every entry point takes it first), so creation happens once. */
 static ogjk_ctx* context(void) {
-  if (!g_ctx && ogjk_ctx_create(0, &g_ctx) != OGJK_OK) g_ctx = 0;
+  static int tried;
+  if (!tried) {
+    tried = 1;
+    if (ogjk_ctx_create(0, &g_ctx) != OGJK_OK) {
+      g_ctx = 0;
+      fprintf(stderr, "opengjk_ce (opengjk_b200): %s\n", ogjk_last_error());
+    }
+  }
   return g_ctx;
 }
 

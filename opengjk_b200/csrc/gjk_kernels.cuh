@@ -320,6 +320,15 @@ template <> struct Chunk<double> {
   }
 };
 
+// Group-wide maximum of a floating-point value.  fp32: sm_100a reduces floats on the redux unit
+// (CREDUX.MAX.F32; NaN inputs are ignored unless every lane holds one, +0 > -0), one instruction
+// instead of key conversion + integer reduction + conversion back; fp64 goes through the keys.
+OGJK_DI float group_fmax(unsigned gm, float x) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "r"(gm));
+  return r;
+}
+
 // G cooperating lanes (a power of two, 1..32) scan one polytope block:
 // lane g takes chunks g, g+G, ... (ascending vertex index within the lane), then
 // the group reduces with a (value, lowest index) butterfly.  Every lane of the
@@ -377,13 +386,25 @@ template <typename T, int G> struct GroupBody {
         if (sc > best) { best = sc; better = CV * c + t; }
       }
     }
+    return group_argmax(mask, best, better);
+  }
+  // (largest value, lowest index among the lanes holding it) across the G lanes of the group.
+  // fp32 with 4 or more lanes: two redux instructions (CREDUX.MAX.F32 + REDUX.MIN on the indices of the
+  // lanes that hold the maximum) instead of log2(G) shuffle rounds.  A lane without a candidate carries
+  // the carried point's dot and index 0x7fffffff, which can only win when nobody beat the carried point.
+  static OGJK_DI int group_argmax(unsigned mask, T best, int better) {
+    if constexpr (sizeof(T) == 4 && G >= 4) {
+      const T m = group_fmax(mask, best);
+      return (int)__reduce_min_sync(mask, best == m ? (unsigned)better : 0x7fffffffu);
+    } else {
 #pragma unroll
-    for (int m = G / 2; m > 0; m >>= 1) {
-      const T ob = __shfl_xor_sync(mask, best, m);
-      const int oi = __shfl_xor_sync(mask, better, m);
-      if (ob > best || (ob == best && oi < better)) { best = ob; better = oi; }
+      for (int m = G / 2; m > 0; m >>= 1) {
+        const T ob = __shfl_xor_sync(mask, best, m);
+        const int oi = __shfl_xor_sync(mask, better, m);
+        if (ob > best || (ob == best && oi < better)) { best = ob; better = oi; }
+      }
+      return better;
     }
-    return better;
   }
 };
 
@@ -432,6 +453,9 @@ OGJK_DI unsigned long long group_max_key(unsigned gm, unsigned long long k) {
   const unsigned ml = __reduce_max_sync(gm, hi == mh ? (unsigned)k : 0u);
   return ((unsigned long long)mh << 32) | ml;
 }
+
+OGJK_DI double group_fmax(unsigned gm, double x) { return unkey(group_max_key(gm, okey(x))); }
+
 
 // G-lane body (G = 8, 16, 32) with the polytope's cluster table; acc == null when it has none.
 template <typename T, int G> struct AccelBody {
@@ -487,7 +511,7 @@ template <typename T, int G> struct ScanSide {
         bl = h.sc[j]; il = h.o[j]; px = h.x[j]; py = h.y[j]; pz = h.z[j];
       }
   }
-  OGJK_DI T group_best(unsigned gm) const { return unkey(group_max_key(gm, okey(bl))); }
+  OGJK_DI T group_best(unsigned gm) const { return group_fmax(gm, bl); }
 };
 
 #ifndef OGJK_ACCEL_K
@@ -538,15 +562,15 @@ OGJK_DI void support_both(const AccelBody<T, G>& b1, const AccelBody<T, G>& b2, 
     if (t == 0) {
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        auto mk = okey((T)-INFINITY);
+        T mv = (T)-INFINITY;  // NaN bounds are skipped here (they stay live below: a NaN bound never prunes)
 #pragma unroll
         for (int j = 0; j < VPL; ++j)
-          if (((has[k] >> j) & 1u) && okey(ub[k][j]) > mk) mk = okey(ub[k][j]);
-        const auto m = group_max_key(gm, mk);
+          if (((has[k] >> j) & 1u) && ub[k][j] > mv) mv = ub[k][j];
+        const T m = group_fmax(gm, mv);
         unsigned mine = 0xffffffffu;
 #pragma unroll
         for (int j = VPL - 1; j >= 0; --j)
-          if (((has[k] >> j) & 1u) && okey(ub[k][j]) == m) mine = (unsigned)(g * VPL + j);
+          if (((has[k] >> j) & 1u) && ub[k][j] == m) mine = (unsigned)(g * VPL + j);
         const unsigned first = __reduce_min_sync(gm, mine);
         top[k] = first == 0xffffffffu ? 0 : (int)first;
       }
@@ -605,8 +629,7 @@ OGJK_DI void support_both(const AccelBody<T, G>& b1, const AccelBody<T, G>& b2, 
   }
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
-    const auto key = okey(s[k].bl);
-    const bool cand = key == group_max_key(gm, key);
+    const bool cand = s[k].bl == group_fmax(gm, s[k].bl);  // all-NaN: no candidate, the carried point stays
     const unsigned fi = __reduce_min_sync(gm, cand ? (unsigned)s[k].il : 0xffffffffu);
     if (fi == 0xffffffffu) continue;  // nothing beats the carried point
     const int src = __ffs(__ballot_sync(gm, cand && (unsigned)s[k].il == fi)) - 1;

@@ -20,6 +20,8 @@
 //     library has no link-time dependency on it.
 #pragma once
 #include <dlfcn.h>
+#include <pthread.h>
+#include <sched.h>
 
 #include <condition_variable>
 #include <functional>
@@ -98,8 +100,44 @@ struct ogjk_multi_store_ {
 
 namespace {
 
+// Best effort: run the device's host thread on the CPUs of the NUMA node its PCIe root hangs off
+// (its staging allocations and its cudaMemcpyAsync submissions then stay local to the link).
+void bind_thread_to_device_node(int device) {
+  char bus[32] = "";
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return; }
+  for (char* c = bus; *c; ++c) if (*c >= 'A' && *c <= 'F') *c = (char)(*c - 'A' + 'a');
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return;
+  int node = -1;
+  const int got = fscanf(f, "%d", &node);
+  fclose(f);
+  if (got != 1 || node < 0) return;
+  snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+  f = fopen(path, "r");
+  if (!f) return;
+  cpu_set_t want, have;
+  CPU_ZERO(&want);
+  int lo = 0, hi = 0;
+  for (;;) {
+    if (fscanf(f, "%d", &lo) != 1) break;
+    hi = lo;
+    int ch = fgetc(f);
+    if (ch == '-') { if (fscanf(f, "%d", &hi) != 1) break; ch = fgetc(f); }
+    for (int c = lo; c <= hi && c < CPU_SETSIZE; ++c) CPU_SET(c, &want);
+    if (ch != ',') break;
+  }
+  fclose(f);
+  if (pthread_getaffinity_np(pthread_self(), sizeof(have), &have) != 0) return;
+  cpu_set_t both;
+  CPU_AND(&both, &want, &have);
+  if (CPU_COUNT(&both) > 0) pthread_setaffinity_np(pthread_self(), sizeof(both), &both);
+}
+
 void multi_worker_main(MultiWorker* w) {
   cudaSetDevice(w->device);
+  if (!getenv("OGJK_NO_NUMA_BIND")) bind_thread_to_device_node(w->device);
   std::unique_lock<std::mutex> lk(w->mu);
   for (;;) {
     w->cv.wait(lk, [&] { return w->has_job || w->quit; });
@@ -407,9 +445,11 @@ void ogjk_multi_destroy(ogjk_multi* m) {
       { std::lock_guard<std::mutex> lk(w->mu); w->quit = true; w->cv.notify_all(); }
       w->th.join();
     }
-    cudaSetDevice(w->device);
-    w->d_idx1.release(); w->d_idx2.release(); w->r_dist.release(); w->r_simp.release();
-    if (w->ctx) ogjk_ctx_destroy(w->ctx);
+    if (w->ctx) {  // a slot whose context was never created has nothing on a device (and maybe no valid ordinal)
+      cudaSetDevice(w->device);
+      w->d_idx1.release(); w->d_idx2.release(); w->r_dist.release(); w->r_simp.release();
+      ogjk_ctx_destroy(w->ctx);
+    }
     delete w;
   }
   delete m;

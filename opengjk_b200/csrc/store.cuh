@@ -47,11 +47,34 @@ template <typename T> struct StoreView {
 // Block layout in T elements, nc = ceil(n/32), ncs = nc rounded up to 32:
 //   lox[ncs] loy[ncs] loz[ncs] hix[ncs] hiy[ncs] hiz[ncs]       cluster boxes
 //   6 x kAccelMaxTiles tile boxes (same order)                   box of each run of 32 clusters
+//   ox oy oz slack | nx[ncs] ny[ncs] nz[ncs] ct[ncs] A[ncs] B[ncs] R[ncs]   cluster cones (below; OGJK_T3_CONE builds only)
 //   nc cluster records = x[32] y[32] z[32] | int orig[32]        (kAccelRecord<T> elements each)
 // (slots past n in the last cluster repeat that cluster's first vertex; table entries
 // past nc are zero and never used).  The k-d order makes 32 consecutive clusters a compact
 // region, so a tile box prunes 1024 vertices with one dot product (bodies above 1024
 // vertices; same monotone-rounding argument as for the cluster boxes).
+//
+// Cluster cones (experimental, -DOGJK_T3_CONE=1; off by default: on B200 the extra per-iteration
+// arithmetic cost more than the saved fetches, profiles/r2g_table_cone_rank_ab.jsonl).
+// A box bounds a patch of a curved hull loosely (on 1000-vertex sphere hulls 5-6
+// of 32 boxes survive a search direction where the exact per-cluster support would keep 1-2),
+// so every cluster also gets a cone seen from a point o inside the body (the centre of its
+// bounding box): all its vertices lie within distance R of o and within angle theta of the unit
+// axis n.  Then, with phi the angle between n and d,
+//     p.d  <=  o.d + R |d| max(0, cos(max(0, phi - theta)))
+// and the kernel takes min(box bound, cone bound).  The cone bound is evaluated in floating point
+// with explicit margins instead of a rounding argument: ct = cos(theta) is lowered by 1e-4 at
+// build time (absorbs the build's own rounding and |n| != 1), sin(theta) and R are rounded up,
+// and `slack` * |d| = 2^-15 (|o|_1 + max R) |d| is added -- three orders of magnitude above the
+// worst-case rounding error of both the bound and the vertices' dot products, five below the
+// spread of the bounds.  Degenerate clusters (non-finite data, all vertices at o) get ct = -2,
+// i.e. the ball bound o.d + R|d|; the kernel falls back to the box bound whenever |d|^2 is
+// outside [1e-30, 1e30] or the cone bound is not finite.
+// A = R * ct and B = R * sin(theta) are stored premultiplied: outside the cone the bound is
+// o.d + max(0, A (n.d) + B sqrt(|d|^2 - (n.d)^2)) + slack |d|.
+#ifndef OGJK_T3_CONE
+#define OGJK_T3_CONE 0  // cluster cones in the tables (measured on B200: exact, fewer clusters fetched, slower: DESIGN.md section 4)
+#endif
 constexpr int kAccelCluster = 32;
 constexpr int kAccelMaxVerts = 16384;
 constexpr int kAccelMaxClusters = kAccelMaxVerts / kAccelCluster;
@@ -59,12 +82,16 @@ constexpr int kAccelMaxTiles = kAccelMaxClusters / 32;  // 16
 template <typename T> constexpr int kAccelRecord = 3 * kAccelCluster + kAccelCluster * (int)sizeof(int) / (int)sizeof(T);
 
 __host__ __device__ __forceinline__ int accel_table_stride(int nc) { return (nc + 31) & ~31; }
+// Element offsets inside a polytope's table: cone header (ox oy oz slack) + cone arrays (only in
+// -DOGJK_T3_CONE=1 builds), cluster records.
+__host__ __device__ __forceinline__ int accel_cone_at(int ncs) { return 6 * ncs + 6 * (16384 / 32 / 32); }
+__host__ __device__ __forceinline__ int accel_records_at(int ncs) {
+  return OGJK_T3_CONE ? 13 * ncs + 6 * (16384 / 32 / 32) + 4 : 6 * ncs + 6 * (16384 / 32 / 32);
+}
 template <typename T> __host__ __device__ __forceinline__ long long accel_elems(int n) {
   const int nc = (n + kAccelCluster - 1) / kAccelCluster;
-  return 6ll * accel_table_stride(nc) + 6 * kAccelMaxTiles + (long long)nc * kAccelRecord<T>;
+  return (long long)accel_records_at(accel_table_stride(nc)) + (long long)nc * kAccelRecord<T>;
 }
-// Element offset of the cluster records inside a polytope's table.
-__host__ __device__ __forceinline__ int accel_records_at(int ncs) { return 6 * ncs + 6 * kAccelMaxTiles; }
 
 // Per-polytope element counts the three scan kernels below accumulate.
 struct BlockElems {
@@ -274,6 +301,8 @@ accel_build_kernel(StoreView<T> s, long long npoly, T* __restrict__ accel, int p
   extern __shared__ unsigned long long accel_keys[];
   __shared__ unsigned seg_lo[3][kAccelMaxClusters], seg_hi[3][kAccelMaxClusters];
   __shared__ unsigned char seg_axis[kAccelMaxClusters];
+  __shared__ T cone_o[3];
+  __shared__ unsigned cone_rmax;  // ordered fp32 key of the largest cluster radius
   const int tid = threadIdx.x, nth = blockDim.x;
   for (long long h = blockIdx.x; h < npoly; h += gridDim.x) {
     const int n = s.cnt[h];
@@ -389,6 +418,76 @@ accel_build_kernel(StoreView<T> s, long long npoly, T* __restrict__ accel, int p
       }
     }
     __syncthreads();
+#if OGJK_T3_CONE
+    // cluster cones about the centre of the body's box (see the layout comment above)
+    if (tid < 32) {
+      if (tid == 0) cone_rmax = 0u;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        T l = (T)INFINITY, hh = (T)-INFINITY;
+        for (int t = tid; t < kAccelMaxTiles && t * 32 < nc; t += 32) {
+          l = fmin(l, tb[a * kAccelMaxTiles + t]);
+          hh = fmax(hh, tb[(3 + a) * kAccelMaxTiles + t]);
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+          l = fmin(l, __shfl_xor_sync(0xffffffffu, l, m));
+          hh = fmax(hh, __shfl_xor_sync(0xffffffffu, hh, m));
+        }
+        if (tid == 0) cone_o[a] = l * (T)0.5 + hh * (T)0.5;
+      }
+    }
+    __syncthreads();
+    T* cone = out + accel_cone_at(ncs);
+    T* carr = cone + 4;
+    const T ox = cone_o[0], oy = cone_o[1], oz = cone_o[2];
+    for (int c = tid >> 5; c < ncs; c += nth >> 5) {
+      const int lane = tid & 31;
+      if (c >= nc) {  // padding: never used
+        if (lane < 7) carr[lane * ncs + c] = (T)0;
+        continue;
+      }
+      const T* r = rec + (long long)c * kAccelRecord<T>;
+      const T qx = r[lane] - ox, qy = r[kAccelCluster + lane] - oy, qz = r[2 * kAccelCluster + lane] - oz;
+      const T rr = sqrt(qx * qx + qy * qy + qz * qz);
+      const bool at_o = !(rr > (T)0);  // vertex at o (or NaN): contributes no direction
+      T ux = at_o ? (T)0 : qx / rr, uy = at_o ? (T)0 : qy / rr, uz = at_o ? (T)0 : qz / rr;
+      T sx = ux, sy = uy, sz = uz, rmax = rr;
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, m);
+        sy += __shfl_xor_sync(0xffffffffu, sy, m);
+        sz += __shfl_xor_sync(0xffffffffu, sz, m);
+        rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, m));
+      }
+      const T sn = sqrt(sx * sx + sy * sy + sz * sz);
+      const bool has_axis = sn > (T)1e-6;
+      const T nx = has_axis ? sx / sn : (T)0, ny = has_axis ? sy / sn : (T)0, nz = has_axis ? sz / sn : (T)0;
+      T cmin = at_o ? (T)1 : ux * nx + uy * ny + uz * nz;
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) cmin = fmin(cmin, __shfl_xor_sync(0xffffffffu, cmin, m));
+      const unsigned finite = __ballot_sync(0xffffffffu, rr == rr && rr < (T)INFINITY);
+      T ct = cmin - (T)1e-4, R = rmax * (T)(1.0 + 1e-6);
+      if (!has_axis || finite != 0xffffffffu || !(ct == ct)) { ct = (T)-2; R = (finite == 0xffffffffu) ? R : (T)INFINITY; }
+      const T ctc = ct < (T)-1 ? (T)-1 : (ct > (T)1 ? (T)1 : ct);
+      const T st = sqrt(fmax((T)0, (T)1 - ctc * ctc)) * (T)(1.0 + 1e-5) + (T)1e-7;
+      if (lane == 0) {
+        carr[0 * ncs + c] = nx; carr[1 * ncs + c] = ny; carr[2 * ncs + c] = nz;
+        carr[3 * ncs + c] = ct;
+        carr[4 * ncs + c] = R * ctc;
+        carr[5 * ncs + c] = R * st;
+        carr[6 * ncs + c] = R;
+        atomicMax(&cone_rmax, accel_ord((float)fmin(R, (T)3.0e38)));
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const T rm = (T)accel_unord(cone_rmax) * (T)(1.0 + 1e-6);
+      cone[0] = ox; cone[1] = oy; cone[2] = oz;
+      cone[3] = (fabs(ox) + fabs(oy) + fabs(oz) + rm) * (T)(1.0 / 32768.0);
+    }
+    __syncthreads();
+#endif
   }
 }
 
@@ -451,9 +550,14 @@ __host__ __device__ __forceinline__ int bin_upper(int tk) {
   return tk <= kFineKeys ? tk * kFineSub + kFineSub - 1 : kFineKeys * kFineSub + kFineSub - 1 + (tk - kFineKeys);
 }
 // Pairs whose two bodies both carry a cluster table (persistent stores) are sorted into
-// kMaxKey + 1 extra bins ABOVE the plain ones (one per size key), so they come first in the
-// sorted list and run as one segment through the pruned-scan kernel.
-constexpr int kNumBinsAll = kNumBins + kMaxKey + 1;
+// 2 x (kMaxKey + 1) extra bins ABOVE the plain ones, so they come first in the sorted list and
+// run as two segments through the table kernels: first the pairs with a body above
+// kAccelOneTile vertices (several 32-cluster tiles: table_kernel.cuh), then the pairs whose two
+// bodies fit one tile (first-generation table kernel, still the faster one there).  Inside a
+// segment the bin is the first body's index (see pair_key).
+constexpr int kAccelOneTile = 32 * kAccelCluster;  // 1024 vertices
+constexpr int kTableBins = kMaxKey + 1;
+constexpr int kNumBinsAll = kNumBins + 2 * kTableBins;
 constexpr int kSortBlock = 256;
 constexpr int kSortItems = 8;  // pairs per thread
 
@@ -465,15 +569,13 @@ __device__ __forceinline__ int pair_key(const StoreView<T>& s1, const StoreView<
   const int n1 = s1.cnt[h1], n2 = s2.cnt[h2];
   const int np1 = pad4(n1), np2 = pad4(n2);
   int k = (np1 + np2) >> 2;
-  if (s1.accel && s2.accel && n1 >= s1.accel_min && n1 <= kAccelMaxVerts && n2 >= s2.accel_min && n2 <= kAccelMaxVerts)
-#ifdef OGJK_TABLE_ORDER_BY_SIZE
-    return kNumBins + (k > kMaxKey ? kMaxKey : k);
-#else
-    // The table kernel runs one pair per warp, so equal sizes inside a warp do not matter;
-    // ordering the segment by the first body's index instead keeps the bodies a pair list
+  if (s1.accel && s2.accel && n1 >= s1.accel_min && n1 <= kAccelMaxVerts && n2 >= s2.accel_min && n2 <= kAccelMaxVerts) {
+    // The table kernels run one pair per warp, so equal sizes inside a warp do not matter;
+    // ordering a segment by the first body's index instead keeps the bodies a pair list
     // reuses (indexed batches) hot in L2.
-    return kNumBins + (int)(h1 * (long long)(kMaxKey + 1) / (s1.npoly > 0 ? s1.npoly : 1));
-#endif
+    const int large = (n1 > kAccelOneTile || n2 > kAccelOneTile) ? kTableBins : 0;
+    return kNumBins + large + (int)(h1 * (long long)kTableBins / (s1.npoly > 0 ? s1.npoly : 1));
+  }
   // keys 2..4 are reserved for pairs whose two polytopes both fit 8 register slots
   if ((np1 > 8 || np2 > 8) && k < kSmallKeyMax + 1) k = kSmallKeyMax + 1;
   if (k > kMaxKey) k = kMaxKey;

@@ -41,8 +41,12 @@ namespace ogjk {
 #define OGJK_T3_VPL_F64 2
 #endif
 #ifndef OGJK_T3_PARK
-#define OGJK_T3_PARK 0  // park the simplex in shared memory while the support scans run
+#define OGJK_T3_PARK 1  // park the simplex in shared memory while the support scans run
 #endif
+#ifndef OGJK_T3_TOPFIRST
+#define OGJK_T3_TOPFIRST 1  // crowded tile: the highest bound goes with the first trip
+#endif
+// OGJK_T3_CONE (store.cuh, default 0): min(box bound, cone bound) per cluster
 #ifndef OGJK_LB_TABLE3_F32
 #define OGJK_LB_TABLE3_F32 4
 #endif
@@ -52,12 +56,23 @@ namespace ogjk {
 
 template <typename T> struct T3Vpl { static constexpr int value = sizeof(T) == 4 ? OGJK_T3_VPL_F32 : OGJK_T3_VPL_F64; };
 
+// Square root for the cone bound: only an upper estimate within ~1e-6 relative is needed
+// (fp32: the 1-instruction approximation, scaled up; fp64: the correctly rounded one).
+OGJK_DI float t3_sqrt_up(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * 1.000001f;
+}
+OGJK_DI double t3_sqrt_up(double x) { return sqrt(x) * 1.000000001; }
+
 // Per-body state of one query.
 template <typename T> struct T3Side {
   const T* acc;      // table base (cluster boxes | tile boxes | records)
   int nc, ncs, ntiles;
   T lo[3], hi[3];    // lane c: box of cluster c (tile 0)
-  T tlo[3], thi[3];  // lane t: box of tile t (bodies with more than one tile)
+#if OGJK_T3_CONE
+  T ox, oy, oz, slack;  // cone apex (centre of the body's box) and the bound's safety term per unit |d|
+#endif
   OGJK_DI const T* record(int c) const { return acc + accel_records_at(ncs) + (long long)c * kAccelRecord<T>; }
   OGJK_DI void open(const T* table, int n, int lane) {
     acc = table;
@@ -66,14 +81,25 @@ template <typename T> struct T3Side {
     ntiles = (nc + 31) >> 5;
 #pragma unroll
     for (int a = 0; a < 3; ++a) { lo[a] = acc[a * ncs + lane]; hi[a] = acc[(3 + a) * ncs + lane]; }
-#pragma unroll
-    for (int a = 0; a < 3; ++a) { tlo[a] = (T)0; thi[a] = (T)0; }
-    if (ntiles > 1) {
-      const T* tb = acc + 6 * ncs + (lane & (kAccelMaxTiles - 1));
-#pragma unroll
-      for (int a = 0; a < 3; ++a) { tlo[a] = tb[a * kAccelMaxTiles]; thi[a] = tb[(3 + a) * kAccelMaxTiles]; }
-    }
+#if OGJK_T3_CONE
+    const T* ch = acc + accel_cone_at(ncs);
+    ox = ch[0]; oy = ch[1]; oz = ch[2]; slack = ch[3];
+#endif
   }
+#if OGJK_T3_CONE
+  // Cone bound of cluster c (this lane's cluster of the current tile) for direction d; od = o.d,
+  // dd = |d|^2, dn = |d| (rounded, see store.cuh for the margins).  Returns +inf when unusable.
+  OGJK_DI T cone_bound(int c, T dx, T dy, T dz, T od, T dd, T dn) const {
+    const T* ca = acc + accel_cone_at(ncs) + 4 + c;
+    const T nx = ca[0], ny = ca[ncs], nz = ca[2 * ncs], ct = ca[3 * ncs], A = ca[4 * ncs], B = ca[5 * ncs], R = ca[6 * ncs];
+    const T nd = dot3(nx, ny, nz, dx, dy, dz);
+    const T t = dd - nd * nd;
+    const T st = t3_sqrt_up(t > (T)0 ? t : (T)0);
+    const T off = A * nd + B * st;
+    const T cone = nd >= ct * dn ? R * dn : (off > (T)0 ? off : (T)0);
+    return od + cone + slack * dn;
+  }
+#endif
 };
 
 // Running best of one lane: value, original index (-1 = the carried point), vertex.
@@ -84,24 +110,30 @@ OGJK_DI T t3_corner_dot(const T (&lo)[3], const T (&hi)[3], T dx, T dy, T dz) {
   return dot3(dx >= (T)0 ? hi[0] : lo[0], dy >= (T)0 ? hi[1] : lo[1], dz >= (T)0 ? hi[2] : lo[2], dx, dy, dz);
 }
 
-// Lowest set lane of `bits` among those holding the largest key.
-template <typename K> OGJK_DI int t3_argmax_lane(unsigned bits, int lane, K key) {
+// Warp-wide maximum.  fp32: one CREDUX.MAX.F32 (sm_100a has the float reduction; NaN inputs are
+// ignored unless every lane holds one); fp64: the order-preserving key pair on the integer unit.
+OGJK_DI float t3_wmax(float x) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(x));
+  return r;
+}
+OGJK_DI double t3_wmax(double x) { return unkey(group_max_key(0xffffffffu, okey(x))); }
+
+// Lowest set lane of `bits` among those holding the largest bound (bounds are never NaN).
+template <typename T> OGJK_DI int t3_argmax_lane(unsigned bits, int lane, T ub) {
   const bool mine = (bits >> lane) & 1u;
-  const K k = mine ? key : K(0);
-  const K m = group_max_key(0xffffffffu, k);
-  return __ffs(__ballot_sync(0xffffffffu, mine && k == m)) - 1;
+  const T m = t3_wmax(mine ? ub : (T)-INFINITY);
+  return __ffs(__ballot_sync(0xffffffffu, mine && ub == m)) - 1;
 }
 
-// Key of a bound for pruning in key space: NaN bounds (of either sign) must never prune.
-OGJK_DI unsigned t3_bound_key(float ub) { return ub != ub ? 0xffffffffu : okey(ub); }
-OGJK_DI unsigned long long t3_bound_key(double ub) { return ub != ub ? ~0ull : okey(ub); }
+// A NaN bound (of either sign) must never prune: it becomes +inf.
+template <typename T> OGJK_DI T t3_bound(T ub) { return ub != ub ? (T)INFINITY : ub; }
 
 // Both support calls of one iteration (openGJK.c:992-993) in lockstep.
 //
-// Cluster selection is lane-parallel: the 32/VPL-lane group q owns the clusters c of the
-// current tile with c % VPL == q and takes its lowest live one each trip (the k-d order makes
-// the live set a few runs of neighbouring indices, so the residue classes stay balanced);
-// one REDUX.OR clears what the groups took.  No serial "next cluster" chain per slot.
+// Cluster selection is lane-parallel: each trip the 32/VPL-lane group q takes the q-th lowest
+// live cluster of the current tile (a few bit operations per lane; no serial "next cluster"
+// chain per slot).
 template <typename T>
 OGJK_DI void t3_support_both(const T3Side<T> (&S)[2], int lane, const V3<T>& v, V3<T>& sa, int& ia, V3<T>& sb, int& ib) {
   constexpr int VPL = T3Vpl<T>::value;
@@ -109,10 +141,16 @@ OGJK_DI void t3_support_both(const T3Side<T> (&S)[2], int lane, const V3<T>& v, 
   constexpr int NG = VPL;        // clusters per fetch
   constexpr unsigned FULL = 0xffffffffu;
   const int q = lane / LPC, sub = lane % LPC;
-  const unsigned gmask = (NG == 4 ? 0x11111111u : NG == 2 ? 0x55555555u : 0xffffffffu) << q;
   const T dx[2] = {-v.x, v.x}, dy[2] = {-v.y, v.y}, dz[2] = {-v.z, v.z};
   T3Best<T> B[2];
-  decltype(okey(T(0))) tkey[2];  // key of this lane's tile bound
+#if OGJK_T3_CONE
+  const T dd = v.x * v.x + v.y * v.y + v.z * v.z;
+  const T dn = t3_sqrt_up(dd);
+  const bool dd_ok = dd > (T)1e-30 && dd < (T)1e30;  // outside: under/overflow territory, box bounds only
+  const T od[2] = {dot3(S[0].ox, S[0].oy, S[0].oz, dx[0], dy[0], dz[0]), dot3(S[1].ox, S[1].oy, S[1].oz, dx[1], dy[1], dz[1])};
+  const bool cone_ok[2] = {dd_ok && S[0].slack < (T)INFINITY, dd_ok && S[1].slack < (T)INFINITY};
+#endif
+  T tub[2];        // this lane's tile bound
   unsigned tl[2];                // tiles still to visit
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
@@ -120,23 +158,26 @@ OGJK_DI void t3_support_both(const T3Side<T> (&S)[2], int lane, const V3<T>& v, 
     B[k].bl = dot3(cur.x, cur.y, cur.z, dx[k], dy[k], dz[k]);  // same value in every lane
     B[k].px = cur.x; B[k].py = cur.y; B[k].pz = cur.z;
     B[k].il = -1;
-    tkey[k] = 0;
+    tub[k] = (T)0;
     tl[k] = 1u;
     if (S[k].ntiles > 1) {
-      tkey[k] = t3_bound_key(t3_corner_dot(S[k].tlo, S[k].thi, dx[k], dy[k], dz[k]));
-      tl[k] = __ballot_sync(FULL, lane < S[k].ntiles && tkey[k] >= okey(B[k].bl));
+      // tile boxes (one per 32 clusters) are read per iteration: bodies above 1024 vertices only
+      const T* tb = S[k].acc + 6 * S[k].ncs + (lane & (kAccelMaxTiles - 1));
+      tub[k] = t3_bound(dot3(tb[(dx[k] >= (T)0 ? 3 : 0) * kAccelMaxTiles], tb[(dy[k] >= (T)0 ? 4 : 1) * kAccelMaxTiles],
+                             tb[(dz[k] >= (T)0 ? 5 : 2) * kAccelMaxTiles], dx[k], dy[k], dz[k]));
+      tl[k] = __ballot_sync(FULL, lane < S[k].ntiles && !(tub[k] < B[k].bl));
     }
   }
   while (tl[0] | tl[1]) {
     int t[2];
-    decltype(okey(T(0))) ukey[2];
+    T ukey[2];  // this lane's cluster bound (NaN-free)
     unsigned live[2];
     T thr[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       t[k] = -1;
       if (tl[k]) {
-        t[k] = S[k].ntiles > 1 ? t3_argmax_lane(tl[k], lane, tkey[k]) : 0;  // most promising tile first
+        t[k] = S[k].ntiles > 1 ? t3_argmax_lane(tl[k], lane, tub[k]) : 0;  // most promising tile first
         tl[k] &= ~(1u << t[k]);
       }
     }
@@ -150,27 +191,52 @@ OGJK_DI void t3_support_both(const T3Side<T> (&S)[2], int lane, const V3<T>& v, 
         ub = dot3(bx[(dx[k] >= (T)0 ? 3 : 0) * S[k].ncs], bx[(dy[k] >= (T)0 ? 4 : 1) * S[k].ncs],
                   bx[(dz[k] >= (T)0 ? 5 : 2) * S[k].ncs], dx[k], dy[k], dz[k]);
       }
-      ukey[k] = t3_bound_key(ub);
+#if OGJK_T3_CONE
+      if (t[k] >= 0 && cone_ok[k]) {
+        const T ubc = S[k].cone_bound(t[k] * 32 + lane, dx[k], dy[k], dz[k], od[k], dd, dn);
+        ub = ubc < ub ? ubc : ub;  // a NaN cone bound leaves the box bound
+      }
+#endif
+      ukey[k] = t3_bound(ub);
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const bool has = t[k] >= 0 && t[k] * 32 + lane < S[k].nc;
-      const auto wkey = group_max_key(FULL, okey(B[k].bl));
-      thr[k] = unkey(wkey);
-      live[k] = __ballot_sync(FULL, has && ukey[k] >= wkey);
+      thr[k] = t3_wmax(B[k].bl);
+      live[k] = __ballot_sync(FULL, has && !(ukey[k] < thr[k]));
     }
+    bool first = true;
     while (live[0] | live[1]) {
       T x[2][VPL], y[2][VPL], z[2][VPL];
       int o[2][VPL];
       bool valid[2];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const unsigned mine = live[k] & gmask;
-        valid[k] = mine != 0;
-        const unsigned took = __reduce_or_sync(FULL, mine & (0u - mine));
+        // group q takes the q-th lowest live cluster (rank, not residue class: neighbouring clusters
+        // of the k-d order differ by powers of two, so residue classes would pile up on one group)
+        unsigned pool = live[k];
+        int forced = -1, rank = q, take = NG;
+#if OGJK_T3_TOPFIRST
+        if (first && __popc(pool) > NG) {
+          // more live clusters than one trip moves (typically the first iteration, when the carried
+          // point bounds nothing): the highest bound most likely holds the winner and prunes the rest
+          forced = t3_argmax_lane(pool, lane, ukey[k]);
+          pool &= ~(1u << forced);
+          rank = q - 1;
+          take = NG - 1;
+        }
+#endif
+        unsigned rest = pool;
+#pragma unroll
+        for (int g = 1; g < NG; ++g) rest = rank >= g ? rest & (rest - 1) : rest;  // drop the `rank` lowest bits
+        const bool top = forced >= 0 && q == 0;
+        valid[k] = top || rest != 0;
+        unsigned left = pool;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) left = g < take ? left & (left - 1) : left;   // what remains after this trip
         // idle groups re-read the lowest cluster taken this trip: its lines are in flight anyway
-        const int bit = __ffs(valid[k] ? mine : (took ? took : 1u)) - 1;
-        live[k] &= ~took;
+        const int bit = top ? forced : __ffs(rest ? rest : (live[k] ? live[k] : 1u)) - 1;
+        live[k] = left;
         const T* r = S[k].record((t[k] < 0 ? 0 : t[k]) * 32 + bit) + sub * VPL;
         load_vec<VPL>(r, x[k]);
         load_vec<VPL>(r + kAccelCluster, y[k]);
@@ -197,24 +263,23 @@ OGJK_DI void t3_support_both(const T3Side<T> (&S)[2], int lane, const V3<T>& v, 
       if (live[0] | live[1]) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-          const auto wkey = group_max_key(FULL, okey(B[k].bl));
-          thr[k] = unkey(wkey);
-          live[k] &= __ballot_sync(FULL, ukey[k] >= wkey);
+          thr[k] = t3_wmax(B[k].bl);
+          live[k] &= __ballot_sync(FULL, !(ukey[k] < thr[k]));
         }
       }
+      first = false;
     }
     if (tl[0] | tl[1]) {
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const auto wkey = group_max_key(FULL, okey(B[k].bl));
-        tl[k] &= __ballot_sync(FULL, tkey[k] >= wkey);
+        const T wb = t3_wmax(B[k].bl);
+        tl[k] &= __ballot_sync(FULL, !(tub[k] < wb));
       }
     }
   }
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
-    const auto key = okey(B[k].bl);
-    const bool cand = key == group_max_key(FULL, key);
+    const bool cand = B[k].bl == t3_wmax(B[k].bl);  // +0 == -0; all-NaN leaves no candidate and the carried point stays
     const unsigned fi = __reduce_min_sync(FULL, cand ? (unsigned)B[k].il : 0xffffffffu);
     if (fi == 0xffffffffu) continue;  // nothing beats the carried point
     const int src = __ffs(__ballot_sync(FULL, cand && (unsigned)B[k].il == fi)) - 1;
@@ -267,7 +332,7 @@ __device__ __noinline__ void t3_plain_pair(const StoreArgs<T>& a, long long p, l
 
 template <typename T>
 __global__ void __launch_bounds__(128, (sizeof(T) == 8 ? OGJK_LB_TABLE3_F64 : OGJK_LB_TABLE3_F32))
-gjk_table3_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* __restrict__ seg_begin,
+gjk_table3_kernel(const __grid_constant__ StoreArgs<T> a, const int* __restrict__ list, const unsigned* __restrict__ seg_begin,
                   const unsigned* __restrict__ seg_end, unsigned long long* __restrict__ head) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;

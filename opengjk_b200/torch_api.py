@@ -89,9 +89,17 @@ def _outputs(n, like):
     return simp, dist, f64
 
 
-def _pairs(pairs, device):
+def _pairs(pairs, device, npoly=None, validate=False):
+    """(N, 2) integer pair list -> two contiguous int32 index tensors.  With validate=True the
+    indices are range-checked against the pool (one device reduction + a host read, i.e. a
+    synchronisation; off by default on the zero-copy path -- out-of-range indices are undefined
+    behaviour there exactly as in the reference's indexed kernel, gpu/opengjk_gpu.cu:1445-1631)."""
     torch = _torch()
     p = torch.as_tensor(pairs, device=device).to(torch.int32).reshape(-1, 2)
+    if validate and npoly is not None and p.numel():
+        lo, hi = int(p.min().item()), int(p.max().item())
+        if lo < 0 or hi >= npoly:
+            raise ValueError(f"pair index out of range: [{lo}, {hi}] vs {npoly} polytopes")
     return p[:, 0].contiguous(), p[:, 1].contiguous()
 
 
@@ -112,13 +120,14 @@ def compute_minimum_distance(bodies1, bodies2, counts1=None, counts2=None, engin
     return _soa(simp, dist, n, f64)
 
 
-def compute_minimum_distance_indexed(polytopes, pairs, counts=None, engine=None):
+def compute_minimum_distance_indexed(polytopes, pairs, counts=None, engine=None, validate=False):
     """Indexed batch over one device pool (reference: compute_minimum_distance_indexed,
-    gpu/include/openGJK_GPU.h:331-366): polytopes (P, V, 3), pairs (N, 2) integer tensor."""
+    gpu/include/openGJK_GPU.h:331-366): polytopes (P, V, 3), pairs (N, 2) integer tensor.
+    validate=True range-checks the pair indices first (synchronises)."""
     torch = _torch()
     b = _as_bodies(polytopes)
     eng = engine or api.default_engine(b.device.index or 0)
-    pa, pb = _pairs(pairs, b.device)
+    pa, pb = _pairs(pairs, b.device, b.shape[0], validate)
     n = int(pa.numel())
     c, o, k = _layout(b, counts)
     simp, dist, f64 = _outputs(n, b)
@@ -140,9 +149,9 @@ class TensorStore:
         c, o, k = _layout(b, counts)
         self.store = self.engine.store_create(c, o, k, torch.cuda.current_stream(b.device).cuda_stream)
 
-    def query(self, pairs, epa=False):
+    def query(self, pairs, epa=False, validate=False):
         torch = _torch()
-        pa, pb = _pairs(pairs, self.device)
+        pa, pb = _pairs(pairs, self.device, self.store.num_polytopes, validate)
         n = int(pa.numel())
         simp, dist, f64 = _outputs(n, torch.empty(0, dtype=self.dtype, device=self.device))
         st = torch.cuda.current_stream(self.device).cuda_stream

@@ -98,3 +98,47 @@ def test_gjk_epa_and_mid_level_api(prec, dt):
     assert w1b.tobytes() == ref["witness1"].tobytes() and nrb.tobytes() == ref["normals"].tobytes()
     lib.free_device_arrays(*d)
     lib.free_epa_device_arrays(*e)
+
+
+@pytest.mark.gpu
+def test_eight_concurrent_callers_on_the_batched_flavour():
+    """The flavour library's single context is created once (std::call_once) and calls are
+    serialised: 8 threads calling compute_minimum_distance at the same time (the first call of
+    the process included) all get the oracle's bytes."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, os, sys, threading
+import numpy as np
+sys.path.insert(0, %r)
+from opengjk_b200 import workloads as W
+from oracle.pyoracle import Oracle, polytope_dtype, simplex_dtype
+lib = C.CDLL(%r)
+prec, dt = "f32", np.float32
+ws = [W.mixed_hulls(3000, seed=200 + t, dtype=dt) for t in range(8)]
+refs = [Oracle(prec).batch(w.coords, w.off, w.cnt, w.pa, w.pb) for w in ws]
+out = [None] * 8
+def body(w, which):
+    arr = np.zeros(which.shape[0], dtype=polytope_dtype(prec))
+    arr["numpoints"] = w.cnt[which]
+    arr["coord"] = w.coords.ctypes.data + w.off[which].astype(np.uint64) * np.uint64(3 * w.coords.itemsize)
+    return arr
+start = threading.Barrier(8)
+def work(t):
+    w = ws[t]
+    b1, b2 = body(w, w.pa), body(w, w.pb)
+    simp = np.zeros(w.npairs, dtype=simplex_dtype(prec)); dist = np.zeros(w.npairs, dtype=dt)
+    start.wait()
+    for _ in range(5):
+        lib.compute_minimum_distance(C.c_int(w.npairs), b1.ctypes.data_as(C.c_void_p), b2.ctypes.data_as(C.c_void_p),
+                                     simp.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p))
+    out[t] = (dist, simp)
+th = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+[x.start() for x in th]; [x.join() for x in th]
+for t in range(8):
+    assert out[t][0].tobytes() == refs[t][0].tobytes(), t
+    assert np.ascontiguousarray(out[t][1]["vrtx_idx"]).tobytes() == np.ascontiguousarray(refs[t][1]["vrtx_idx"]).tobytes(), t
+print("CONCURRENT_OK")
+''' % (ROOT, LIBS["f32"])
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert "CONCURRENT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

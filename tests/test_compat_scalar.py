@@ -126,3 +126,40 @@ def test_device_subsolver_matches_oracle_bitwise():
                 assert vo.tobytes() == vd.tobytes()
                 for f in ("nvrtx", "vrtx", "vrtx_idx"):
                     assert so[f].tobytes() == sd[f].tobytes(), f
+
+
+@pytest.mark.gpu
+def test_eight_concurrent_callers_on_the_scalar_flavour():
+    """The reference's compute_minimum_distance is re-entrant; the drop-in serialises callers on
+    a mutex around its lazily created context.  8 threads (racing on the first call of the
+    process) must all get the reference's answers."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, threading
+import numpy as np
+sys.path.insert(0, %r)
+from ctypes import c_double
+from tests.test_compat_scalar import binding, LIB64
+from opengjk_b200 import workloads as W
+from oracle.pyoracle import Oracle
+_, q = binding(LIB64, c_double)
+w = W.mixed_hulls(160, seed=300, dtype=np.float64)
+dref, sref = Oracle("f64").batch(w.coords, w.off, w.cnt, w.pa, w.pb)
+got = np.zeros(w.npairs)
+idx = np.zeros((w.npairs, 4, 2), dtype=np.int32)
+start = threading.Barrier(8)
+def work(t):
+    start.wait()
+    for p in range(t, w.npairs, 8):
+        d, s = q(w.polytope(w.pa[p]), w.polytope(w.pb[p]))
+        got[p] = d
+        idx[p] = np.array([[s.vrtx_idx[i][0], s.vrtx_idx[i][1]] for i in range(4)])
+th = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+[x.start() for x in th]; [x.join() for x in th]
+assert got.tobytes() == dref.tobytes()
+assert idx.tobytes() == np.ascontiguousarray(sref["vrtx_idx"]).tobytes()
+print("CONCURRENT_OK")
+''' % (ROOT,)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert "CONCURRENT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

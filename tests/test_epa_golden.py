@@ -18,8 +18,16 @@ from tests.golden.make_epa_golden import checksum, epa_workloads
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 PRECS = [("f64", np.float64, 1e-10, np.uint64), ("f32", np.float32, 1e-5, np.uint32)]
-# f64 hulls_mixed: 1 of 1500 pairs differs in the last bits (within 1e-10); everything else is exact
-MIN_BIT_EQUAL = 0.998
+# EPA outputs (penetrating pairs) are bit-equal on EVERY pair.  For SEPARATED pairs EPA only copies the
+# GJK result, and the golden files hold the reference's CUDA GJK there, whose support reduction
+# (gpu/opengjk_gpu.cu:1229-1241: __shfl_down tree over lane chunks, "other > mine" strict) resolves an exact
+# tie between two vertices of non-adjacent chunks towards whatever the tree leaves in lane 0 -- not the lowest
+# index the scalar reference takes (scalar/openGJK.c:617-622).  Root-caused on f64 hulls_mixed pair 306
+# (iteration 5: vertices 3 and 14 of body 1 have the identical dot 0x1.e04ed492d452ap-3; scalar -> 3,
+# CUDA -> 14; traced with instrumented copies of both reference sources) and pair 1442.  This repo's GJK
+# follows the scalar reference (the north-star contract), so those pairs differ from the CUDA golden in the
+# last bits; at most 0.5 % of the separated pairs (2 of 512 here) may do so, all within the tolerance.
+MIN_BIT_EQUAL_SEPARATED = 0.995
 
 
 def _bits(a, it):
@@ -40,7 +48,11 @@ def _compare(name, prec, tol, it, g, dist, w1, w2):
         if variant == "_nofma":
             deq = _bits(d, it) == _bits(dist, it)
             weq = (_bits(r1, it) == _bits(w1, it)).all(1) & (_bits(r2, it) == _bits(w2, it)).all(1)
-            assert deq.mean() >= MIN_BIT_EQUAL and weq.mean() >= MIN_BIT_EQUAL, (k, deq.mean(), weq.mean())
+            pen = d < 0
+            assert deq[pen].all() and weq[pen].all(), (k, "EPA outputs", deq[pen].mean(), weq[pen].mean())
+            if (~pen).any():
+                assert deq[~pen].mean() >= MIN_BIT_EQUAL_SEPARATED and weq[~pen].mean() >= MIN_BIT_EQUAL_SEPARATED, \
+                    (k, "separated pairs (reference CUDA GJK tie rule)", deq[~pen].mean(), weq[~pen].mean())
             assert np.isclose(r1, w1, rtol=tol, atol=tol).all() and np.isclose(r2, w2, rtol=tol, atol=tol).all(), k
 
 

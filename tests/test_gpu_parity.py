@@ -411,3 +411,26 @@ def test_iteration_cap_exit_every_kernel_flavour(eng, eng_exp, prec, dt):
     # host entry points (chunked and one-shot pipelines) and the packed store
     d, s = eng.gjk_host_pools(*w.two_pools())
     _assert_same("cap/host pools", d, s, dref, sref, prec)
+
+
+@pytest.mark.parametrize("prec,dt", PRECS)
+def test_struct_array_entry_points_with_pipelined_gather(eng, prec, dt):
+    """Arrays of gkPolytope large enough for the host-thread gather (csrc/abi.cu: stage_structs,
+    HostPool) to run chunk-pipelined against the uploads: plain, indexed and GJK+EPA forms,
+    repeated calls on one context, all byte-equal to the oracle."""
+    w = W.mixed_hulls(40000, seed=81, dtype=dt)
+    o = Oracle(prec)
+    dref, sref = o.batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1)
+    A = [w.polytope(h) for h in w.pa]
+    B = [w.polytope(h) for h in w.pb]
+    for _ in range(2):
+        d, s = api.compute_minimum_distance_structs(A, B, dt, eng)
+        _assert_same("structs", d, s, dref, sref, prec)
+    pool = [w.polytope(h) for h in range(w.npoly)]
+    d, s = api.compute_minimum_distance_indexed_structs(pool, np.stack([w.pa, w.pb], 1), dt, eng)
+    _assert_same("structs/indexed", d, s, dref, sref, prec)
+    we = W.random_hulls(20000, 8, 64, 82, 1.0, dt, 0.5)
+    ref = o.gjk_epa_batch(we.coords, we.off, we.cnt, we.pa, we.pb, nthreads=os.cpu_count() or 1)
+    d, s, w1, w2 = api.compute_gjk_epa_structs([we.polytope(h) for h in we.pa], [we.polytope(h) for h in we.pb], dt, eng)
+    assert d.tobytes() == ref["distances"].tobytes()
+    assert w1.tobytes() == ref["witness1"].tobytes() and w2.tobytes() == ref["witness2"].tobytes()
