@@ -200,9 +200,10 @@ class Engine:
     def set_pipeline_chunks(self, chunks):
         self._ck(self._L.ogjk_ctx_set_pipeline_chunks(self._h, int(chunks)))
 
-    def gjk_host_pools(self, c1, o1, k1, c2, o2, k2, out=None, epa=False):
+    def gjk_host_pools(self, c1, o1, k1, c2, o2, k2, out=None, epa=False, epa_out=None):
         """Un-indexed form over two pools (pair p = polytope p of each pool), the shape of
-        the reference's bd1[] / bd2[] arrays; large batches are chunk-pipelined over PCIe."""
+        the reference's bd1[] / bd2[] arrays; large batches are chunk-pipelined over PCIe.
+        out = (distances, simplices), epa_out = (witness1, witness2, normals): caller-owned outputs."""
         c1 = np.ascontiguousarray(c1); c2 = np.ascontiguousarray(c2)
         if c1.dtype != c2.dtype:
             raise ValueError(f"pools differ in precision: {c1.dtype} vs {c2.dtype}")
@@ -220,7 +221,10 @@ class Engine:
         args = [self._h, n, _p(c1), _p(o1), _p(k1), n, c1.size // 3, None, _p(c2), _p(o2), _p(k2), n, c2.size // 3, None,
                 _p(simp), _p(dist)]
         if epa:
-            w1 = np.zeros((n, 3), dtype=c1.dtype); w2 = np.zeros((n, 3), dtype=c1.dtype); nr = np.zeros((n, 3), dtype=c1.dtype)
+            if epa_out is None:
+                w1 = np.zeros((n, 3), dtype=c1.dtype); w2 = np.zeros((n, 3), dtype=c1.dtype); nr = np.zeros((n, 3), dtype=c1.dtype)
+            else:
+                w1, w2, nr = epa_out  # caller-owned (e.g. pinned) output arrays
             self._ck(getattr(self._L, f"ogjk_gjk_epa_host_{prec}")(*args, _p(w1), _p(w2), _p(nr)))
             return {"distances": dist, "simplices": simp, "witness1": w1, "witness2": w2, "normals": nr}
         self._ck(getattr(self._L, f"ogjk_gjk_host_{prec}")(*args))

@@ -624,8 +624,18 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
         long long blocks = (a.npairs * 32 + 127) / 128, cap = (long long)ctx->sm_count * 16;
         gjk_table3_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, sorted, sb, se, h);
       };
+      auto batch = [&](const unsigned* sb, const unsigned* se, unsigned long long* h) {
+        long long blocks = (a.npairs + 127) / 128, cap = (long long)ctx->sm_count * 16;
+        gjk_tablebatch_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, sorted, sb, se, h);
+      };
       const int tl = ctx->table_lanes;
-      if (tl == 0) {          // default: the tile kernel above one tile, the first-generation kernel below
+      if (tl == 1) {          // tuning: the pair-batched kernel (32 pairs per warp) for everything
+        batch(t_beg, t_mid, counters + 6);
+        batch(t_mid, t_end, counters + 7);
+      } else if (tl == 2) {   // tuning: tile kernel above one tile, pair-batched kernel below
+        gen3(t_beg, t_mid, counters + 6);
+        batch(t_mid, t_end, counters + 7);
+      } else if (tl == 0) {   // default: the tile kernel above one tile, the first-generation kernel below
         gen3(t_beg, t_mid, counters + 6);
         gen1(32, t_mid, t_end, counters + 7);
       } else if (tl == 3) {   // tuning: the tile kernel for everything
@@ -1736,8 +1746,8 @@ int ogjk_ctx_set_passes(ogjk_ctx* c, int passes, int iters1, int iters2) {
 }
 
 int ogjk_ctx_set_table_lanes(ogjk_ctx* c, int lanes) {
-  if (!c || (lanes != 0 && lanes != 3 && lanes != 8 && lanes != 16 && lanes != 32))
-    return fail(OGJK_ERR_ARG, "table lanes must be 0 (default), 3, 8, 16 or 32%s");
+  if (!c || (lanes != 0 && lanes != 1 && lanes != 2 && lanes != 3 && lanes != 8 && lanes != 16 && lanes != 32))
+    return fail(OGJK_ERR_ARG, "table lanes must be 0 (default), 1, 2, 3, 8, 16 or 32%s");
   c->table_lanes = lanes;
   return OGJK_OK;
 }

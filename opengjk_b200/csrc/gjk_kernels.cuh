@@ -389,11 +389,16 @@ template <typename T, int G> struct GroupBody {
     return group_argmax(mask, best, better);
   }
   // (largest value, lowest index among the lanes holding it) across the G lanes of the group.
-  // fp32 with 4 or more lanes: two redux instructions (CREDUX.MAX.F32 + REDUX.MIN on the indices of the
-  // lanes that hold the maximum) instead of log2(G) shuffle rounds.  A lane without a candidate carries
-  // the carried point's dot and index 0x7fffffff, which can only win when nobody beat the carried point.
+  // fp32, full warp: two redux instructions (CREDUX.MAX.F32 + REDUX.MIN on the indices of the lanes that
+  // hold the maximum) instead of five shuffle rounds (+4.7 % on 1000-vertex hulls).  With partial member
+  // masks the redux path LOSES to the shuffles (G = 2/4/8: -17/-16/-9 %, profiles/r2j_redux_argmax_ab.jsonl),
+  // so smaller groups keep the butterfly.  A lane without a candidate carries the carried point's dot and
+  // index 0x7fffffff, which can only win when nobody beat the carried point.
   static OGJK_DI int group_argmax(unsigned mask, T best, int better) {
-    if constexpr (sizeof(T) == 4 && G >= 4) {
+#ifndef OGJK_REDUX_ARGMAX_MIN_G
+#define OGJK_REDUX_ARGMAX_MIN_G 32
+#endif
+    if constexpr (sizeof(T) == 4 && G >= OGJK_REDUX_ARGMAX_MIN_G) {
       const T m = group_fmax(mask, best);
       return (int)__reduce_min_sync(mask, best == m ? (unsigned)better : 0x7fffffffu);
     } else {

@@ -188,16 +188,25 @@ void shard_bounds(int64_t npairs, int ndev, int i, int64_t* lo, int64_t* hi) {
 }
 
 // Coordinate range [lo_v, hi_v) the polytopes [lo, hi) of a pool touch, and their offsets rebased to it.
+// One pass for pools stored in pair order (the common case: the first polytope starts the range);
+// a pool that is not gets a second pass.
 int slice_pool(const int64_t* off, const int* cnt, int64_t lo, int64_t hi, int64_t nverts, std::vector<int64_t>& reb,
                int64_t* lo_v, int64_t* nv) {
-  int64_t a = INT64_MAX, b = 0;
-  for (int64_t p = lo; p < hi; ++p) {
-    if (cnt[p] < 1 || off[p] < 0 || off[p] + cnt[p] > nverts) return fail(OGJK_ERR_ARG, "polytope range outside the pool%s");
-    if (off[p] < a) a = off[p];
-    if (off[p] + cnt[p] > b) b = off[p] + cnt[p];
+  const int64_t n = hi - lo;
+  reb.resize((size_t)n);
+  const int64_t first = off[lo];
+  int64_t a = first, b = 0;
+  bool bad = false;
+  for (int64_t p = 0; p < n; ++p) {
+    const int64_t o = off[lo + p], e = o + cnt[lo + p];
+    bad |= cnt[lo + p] < 1 || o < 0 || e > nverts;
+    a = o < a ? o : a;
+    b = e > b ? e : b;
+    reb[(size_t)p] = o - first;
   }
-  reb.resize((size_t)(hi - lo));
-  for (int64_t p = lo; p < hi; ++p) reb[(size_t)(p - lo)] = off[p] - a;
+  if (bad) return fail(OGJK_ERR_ARG, "polytope range outside the pool%s");
+  if (a != first)
+    for (int64_t p = 0; p < n; ++p) reb[(size_t)p] += first - a;
   *lo_v = a;
   *nv = b - a;
   return OGJK_OK;

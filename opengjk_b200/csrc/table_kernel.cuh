@@ -384,4 +384,99 @@ gjk_table3_kernel(const __grid_constant__ StoreArgs<T> a, const int* __restrict_
   }
 }
 
+// =============================================================================
+// Pair-batched table kernel: 32 pairs per warp, supports one pair at a time
+// =============================================================================
+// ncu on both warp-per-pair table kernels (profiles/r2h_*): ~40 % of the ~4.2 k warp
+// instructions per pair are the sub-solver, the termination tests and the witnesses --
+// scalar work that all 32 lanes of the warp repeat for the ONE pair they share.  Here a
+// warp owns 32 pairs: every lane keeps the GJK state of its own pair, so that part runs
+// thread-per-pair (one pass serves 32 pairs), while the support scans -- the part that
+// needs the lanes -- still run with the whole warp, one pair after the other: the pair's
+// owner lane broadcasts its direction, carried support points and table pointers, all 32
+// lanes run the pruned scan of the first-generation kernel (support_both<T,32>), and the
+// owner keeps the result.  The pair setup (queue, list, indices, counts, offsets) becomes
+// coalesced per-lane loads, amortised over 32 pairs.  Lanes whose pair has terminated cost
+// nothing in the support phase; the warp leaves when its slowest pair is done.
+// Every pair executes exactly the operation sequence of the warp-per-pair kernels, so the
+// results are the same bytes.
+#ifndef OGJK_LB_TABLEB_F32
+#define OGJK_LB_TABLEB_F32 4
+#endif
+#ifndef OGJK_LB_TABLEB_F64
+#define OGJK_LB_TABLEB_F64 2
+#endif
+
+template <typename T> OGJK_DI const T* t3_bcast_ptr(const T* p, int src) {
+  return reinterpret_cast<const T*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(p), src));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128, (sizeof(T) == 8 ? OGJK_LB_TABLEB_F64 : OGJK_LB_TABLEB_F32))
+gjk_tablebatch_kernel(const __grid_constant__ StoreArgs<T> a, const int* __restrict__ list,
+                      const unsigned* __restrict__ seg_begin, const unsigned* __restrict__ seg_end,
+                      unsigned long long* __restrict__ head) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const long long begin = seg_begin ? (long long)*seg_begin : 0;
+  const long long end = seg_end ? (long long)*seg_end : a.npairs;
+  for (;;) {
+    unsigned long long got = 0;
+    if (lane == 0) got = atomicAdd(head, 32ull);
+    got = __shfl_sync(FULL, got, 0);
+    const long long base = begin + (long long)got;
+    if (base >= end) break;
+    const long long slot = base + lane;
+    bool active = slot < end;
+    // this lane's pair
+    long long p = 0;
+    int n1 = 1, n2 = 1;
+    const T *blk1 = a.s1.data, *blk2 = a.s2.data, *acc1 = nullptr, *acc2 = nullptr;
+    if (active) {
+      p = list ? (long long)list[slot] : slot;
+      const long long h1 = a.idx1 ? (long long)a.idx1[p] : p;
+      const long long h2 = a.idx2 ? (long long)a.idx2[p] : p;
+      n1 = a.s1.cnt[h1]; n2 = a.s2.cnt[h2];
+      blk1 = a.s1.data + a.s1.boff[h1];
+      blk2 = a.s2.data + a.s2.boff[h2];
+      const bool t1 = a.s1.accel && n1 >= a.s1.accel_min && n1 <= kAccelMaxVerts;
+      const bool t2 = a.s2.accel && n2 >= a.s2.accel_min && n2 <= kAccelMaxVerts;
+      acc1 = t1 ? a.s1.accel + a.s1.aoff[h1] : nullptr;  // without two tables support_both takes the plain scans
+      acc2 = t2 ? a.s2.accel + a.s2.aoff[h2] : nullptr;
+    }
+    const GroupBody<T, 1> own1{blk1, n1, pad4(n1), 0, 0u}, own2{blk2, n2, pad4(n2), 0, 0u};
+    GjkState<T> st;
+    gjk_init(own1, own2, st);  // idle lanes initialise from block 0 (valid memory) and never run
+    for (;;) {
+      const unsigned live = __ballot_sync(FULL, active);
+      if (!live) break;
+#pragma unroll 1
+      for (unsigned m = live; m; m &= m - 1) {
+        const int j = __ffs(m) - 1;
+        // the owner lane hands its pair to the warp
+        const int m1 = __shfl_sync(FULL, n1, j), m2 = __shfl_sync(FULL, n2, j);
+        const AccelBody<T, 32> b1{{t3_bcast_ptr(blk1, j), m1, pad4(m1), lane, FULL}, t3_bcast_ptr(acc1, j)};
+        const AccelBody<T, 32> b2{{t3_bcast_ptr(blk2, j), m2, pad4(m2), lane, FULL}, t3_bcast_ptr(acc2, j)};
+        const V3<T> v{__shfl_sync(FULL, st.v.x, j), __shfl_sync(FULL, st.v.y, j), __shfl_sync(FULL, st.v.z, j)};
+        V3<T> sa{__shfl_sync(FULL, st.sa.x, j), __shfl_sync(FULL, st.sa.y, j), __shfl_sync(FULL, st.sa.z, j)};
+        V3<T> sb{__shfl_sync(FULL, st.sb.x, j), __shfl_sync(FULL, st.sb.y, j), __shfl_sync(FULL, st.sb.z, j)};
+        int ia = __shfl_sync(FULL, st.ia, j), ib = __shfl_sync(FULL, st.ib, j);
+        support_both(b1, b2, v, sa, ia, sb, ib);
+        if (lane == j) { st.sa = sa; st.ia = ia; st.sb = sb; st.ib = ib; }
+      }
+      if (active) {
+        st.k++;
+        if (gjk_step_tail(st)) {
+          Splx<T> s = st.s;
+          V3<T> w1, w2;
+          gjk_witnesses(own1, own2, s, w1, w2);
+          a.distances[p] = sqrt(nrm2(st.v.x, st.v.y, st.v.z));
+          if (a.simplices) store_simplex(a.simplices + p, s, w1, w2);
+          active = false;
+        }
+      }
+    }
+  }
+}
+
 }  // namespace ogjk

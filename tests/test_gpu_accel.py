@@ -48,9 +48,10 @@ def _check(eng, w, prec, expect_tables=True):
     dref, sref = o.batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1)
     d0, s0, plain_bytes = _store_run(eng, w, 0)
     _assert_same(w.name + "/plain", d0, s0, dref, sref, prec)
-    # 0: default routing (tile kernel above 1024 vertices, first-generation kernel below); 3: tile kernel for
-    # every table pair; 8/16/32: first-generation kernel with that many lanes per pair
-    for lanes in (0, 3, 8, 16, 32):
+    # 0: default routing; 1: pair-batched kernel (32 pairs per warp) for every table pair; 2: tile kernel above
+    # 1024 vertices + pair-batched kernel below; 3: tile kernel for every table pair; 8/16/32: first-generation
+    # kernel with that many lanes per pair
+    for lanes in (0, 1, 2, 3, 8, 16, 32):
         d1, s1, table_bytes = _store_run(eng, w, 256, lanes)
         _assert_same(f"{w.name}/tables/lanes{lanes}", d1, s1, dref, sref, prec)
         assert (table_bytes > plain_bytes) == expect_tables, (plain_bytes, table_bytes)

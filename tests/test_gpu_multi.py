@@ -72,6 +72,35 @@ def test_multi_host_entry_points_match_the_oracle(prec, dt):
 
 
 @pytest.mark.parametrize("prec,dt", PRECS)
+def test_multi_host_chunk_pipelined_slices(prec, dt):
+    """Slices large enough for every device to take the chunk-pipelined host path (>= 8 x 4096 pairs per
+    device) concurrently from its own host thread, pinned and pageable outputs."""
+    import torch
+    o = Oracle(prec)
+    for devs in _devsets():
+        n = 40000 * len(devs) + 7
+        w = W.mixed_hulls(n, seed=97, dtype=dt)
+        dref, sref = o.batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1)
+        pools = w.two_pools()
+        sdt = api.SIMPLEX_F64 if prec == "f64" else api.SIMPLEX_F32
+        m = api.MultiEngine(devs)
+        try:
+            for pinned in (False, True):
+                if pinned:
+                    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+                    args = [pin(x) for x in pools]
+                    out = (torch.empty(n, dtype=torch.float64 if prec == "f64" else torch.float32).pin_memory().numpy(),
+                           torch.empty(n * sdt.itemsize, dtype=torch.uint8).pin_memory().numpy().view(sdt))
+                else:
+                    args, out = list(pools), None
+                for _ in range(2):
+                    d, s = m.gjk_host_pools(*args, out=out)
+                    _same(f"chunked{devs}/pinned{pinned}", d, s, dref, sref)
+        finally:
+            m.close()
+
+
+@pytest.mark.parametrize("prec,dt", PRECS)
 def test_multi_epa_and_replicated_stores(prec, dt):
     o = Oracle(prec)
     w = W.random_hulls(20001, 8, 64, 93, 1.0, dt, 0.5)

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--classes", default="")
     ap.add_argument("--out", default="")
+    ap.add_argument("--accel-min", type=int, default=-1, help="cluster-table threshold (0 = no tables)")
     args = ap.parse_args()
     import torch
     import bench
@@ -51,6 +52,8 @@ def main():
             eng.set_classes([tuple(int(x) for x in c.split(":")) for c in args.classes.split(",")])
         if lanes:
             eng.set_table_lanes(int(lanes))
+        if args.accel_min >= 0:
+            eng.set_accel_min(args.accel_min)
         store = eng.store_create(d_coords, d_off, d_cnt, stream)
         d_dist = torch.zeros(n, dtype=d_coords.dtype, device=dev)
         d_simp = torch.zeros(n * sdt.itemsize, dtype=torch.uint8, device=dev)
