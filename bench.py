@@ -10,7 +10,7 @@ fp64, per GPU (weak scaling: every rank owns its own contiguous slice of the job
 data-path collective).  By default the other north-star configurations are measured in
 the same run and reported under `other_workloads`:
   boxes100m_f32        config 3: ONE 100 M-pair oriented-box batch split over the N GPUs (strong)
-  hulls1k_f32          config 4a: 1000-vertex hulls (the ">= 70 % of HBM" target)
+  hulls1k_f32          config 4a: 1 M indexed pairs over 32768 1000-vertex hulls (the ">= 70 % of HBM" target)
   hulls1k10k_full_f32  config 4: 1 M indexed pairs over 8192 hulls with 1 k-10 k vertices
   epa10m_f32           config 5: 10 M intersecting pairs, GJK + EPA
 
@@ -55,10 +55,10 @@ WORKLOADS = {
                   lambda n, seed: W.boxes(n, True, seed, dtype=np.float32), 8_000_000),
     "boxes_aligned_f32": ("config3a: axis-aligned unit cubes (tie stress), fp32", np.float32,
                           lambda n, seed: W.boxes(n, False, seed, dtype=np.float32), 8_000_000),
-    "hulls1k_f32": ("config4a: indexed pairs of 1000-vertex hulls, fp32", np.float32,
-                    lambda n, seed: W.large_hull_pool(n, 32768, 1000, 1000, seed, dtype=np.float32), 200_000),
+    "hulls1k_f32": ("config4a: 1 M indexed pairs over a pool of 32768 1000-vertex hulls (393 MB), fp32", np.float32,
+                    lambda n, seed: W.large_hull_pool(n, 32768, 1000, 1000, seed, dtype=np.float32), 1_000_000),
     "hulls1k_f64": ("config4a in fp64: indexed pairs of 1000-vertex hulls", np.float64,
-                    lambda n, seed: W.large_hull_pool(n, 16384, 1000, 1000, seed, dtype=np.float64), 100_000),
+                    lambda n, seed: W.large_hull_pool(n, 16384, 1000, 1000, seed, dtype=np.float64), 500_000),
     "hulls1k10k_f32": ("config4 (small pool): indexed pairs of 1k-10k-vertex hulls, fp32", np.float32,
                        lambda n, seed: W.large_hull_pool(n, 2048, 1000, 10000, seed, dtype=np.float32), 50_000),
     "hulls1k10k_full_f32": ("config4: 1 M indexed pairs over a pool of 8192 hulls with 1k-10k vertices (540 MB), fp32",
@@ -629,10 +629,13 @@ def main():
             # as run_store_batch routes: pairs whose two bodies both carry a table run the table kernel,
             # timed with the last class
             if store.table_bytes > 0 and dom == len(CLASS_TABLE) - 1 and min_cnt >= amin:
-                # default routing: pairs with a body above 1024 vertices -> tile kernel, the others -> first-generation kernel
+                # default routing: pairs with a body above 1024 vertices -> tile kernel; the others -> pair-batched
+                # kernel in batches of >= 131072 pairs, first-generation kernel below
                 tl = int(os.environ.get("OGJK_TABLE_LANES", 0))
                 big = int(d_cnt.max().item()) > 1024
-                kname = (f"gjk_table3_kernel<{tname}>" if (tl == 3 or (tl == 0 and big))
+                batched = tl == 1 or (not big and (tl == 2 or (tl == 0 and n >= 131072)))  # kBatchKernelMinPairs, abi.cu
+                kname = (f"gjk_table3_kernel<{tname}>" if (tl == 3 or (tl in (0, 2) and big))
+                         else f"gjk_tablebatch_kernel<{tname}>" if batched
                          else f"gjk_table_kernel<{tname},{tl if tl in (8, 16, 32) else 32}>")
             else:
                 kname = f"gjk_small_kernel<{tname}>" if lanes == 0 else f"gjk_group_kernel<{tname},{lanes}>"

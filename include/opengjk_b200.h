@@ -149,10 +149,13 @@ OGJK_API int ogjk_ctx_set_accel_min(ogjk_ctx* ctx, int min_vertices);
 OGJK_API int ogjk_ctx_set_passes(ogjk_ctx* ctx, int passes, int iters1, int iters2);
 /* Kernels that use the cluster tables.  0 (default): pairs with a body above 1024 vertices run the
  * tile kernel (csrc/table_kernel.cuh: register-resident cluster boxes, tile boxes, vector cluster
- * fetches), pairs whose two bodies fit one 32-cluster tile the first-generation kernel with 32
- * lanes per pair (the faster one at that size on B200).  3 = the tile kernel for every table pair;
+ * fetches); pairs whose two bodies fit one 32-cluster tile run the pair-batched kernel (a warp
+ * owns up to 32 pairs: per-lane sub-solver, warp-wide support scans one pair at a time) when the
+ * batch has at least 131072 pairs, and the first-generation warp-per-pair kernel below that.
+ * Tuning values: 1 = the pair-batched kernel for every table pair; 2 = tile kernel above one tile,
+ * pair-batched kernel below, whatever the batch size; 3 = the tile kernel for every table pair;
  * 8, 16 or 32 = the first-generation kernel with that many lanes per pair for every table pair.
- * A tuning knob; results do not depend on it. */
+ * Results do not depend on the choice. */
 OGJK_API int ogjk_ctx_set_table_lanes(ogjk_ctx* ctx, int lanes);
 OGJK_API void ogjk_store_destroy(ogjk_store* store);
 OGJK_API int64_t ogjk_store_bytes(const ogjk_store* store);

@@ -182,6 +182,11 @@ struct ogjk_store_ {
   }
 };
 
+// Batches at least this long send their one-tile table pairs to gjk_tablebatch_kernel: with fewer
+// pairs than about 30 per resident warp the warp-per-pair kernel finishes sooner (measured
+// cross-over on B200 between 60 k and 200 k pairs, profiles/r2p_table_batch_ab.jsonl).
+static constexpr long long kBatchKernelMinPairs = 131072;
+
 struct ogjk_ctx_ {
   int device = 0;
   int sm_count = 148;
@@ -199,13 +204,15 @@ struct ogjk_ctx_ {
   int passes = 1;
   int pass_iters[2] = {4, 3};
   DevBuf pass_list[2], pass_f[2], pass_i[2];
+  int batch_blocks[2] = {0, 0};  // resident CTAs of gjk_tablebatch_kernel<float|double> on this device
   int table_lanes = 0;   // 0: tile kernel (table_kernel.cuh) above 1024 vertices, first-generation kernel below; 3 / 8,16,32: force one
   bool timing = false;
   cudaEvent_t ev[2 * kPhases] = {};
   int timed_mask = 0;
   cudaStream_t own_stream = nullptr;  // used by the host-buffer entry points
   cudaStream_t in_stream = nullptr, out_stream = nullptr;  // H2D / D2H legs of the chunked host pipeline
-  cudaEvent_t chunk_in[16] = {}, chunk_done[16] = {};
+  cudaEvent_t chunk_in[16] = {}, chunk_done[16] = {}, chunk_out[16] = {};
+  PinBuf h_out;                       // pinned landing zone for results whose destination is pageable memory
   int pipeline_chunks = 8;            // 0/1 disables chunking
   DevBuf counters;                    // kCounterSlots x u64: work-queue heads (the first kQueueSlots are reset per batch)
   DevBuf sort_tmp;                    // hist | start | cursor (u32 each, kMaxKey+2)
@@ -625,7 +632,11 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
         gjk_table3_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, sorted, sb, se, h);
       };
       auto batch = [&](const unsigned* sb, const unsigned* se, unsigned long long* h) {
-        long long blocks = (a.npairs + 127) / 128, cap = (long long)ctx->sm_count * 16;
+        // one resident wave: the kernel sizes its batches from the number of warps in the grid
+        int& per_sm = ctx->batch_blocks[sizeof(T) == 8];
+        if (!per_sm && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk_tablebatch_kernel<T>, 128, 0) != cudaSuccess)
+          per_sm = 4;
+        long long blocks = (a.npairs + 15) / 16, cap = (long long)ctx->sm_count * per_sm;
         gjk_tablebatch_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, sorted, sb, se, h);
       };
       const int tl = ctx->table_lanes;
@@ -635,9 +646,10 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
       } else if (tl == 2) {   // tuning: tile kernel above one tile, pair-batched kernel below
         gen3(t_beg, t_mid, counters + 6);
         batch(t_mid, t_end, counters + 7);
-      } else if (tl == 0) {   // default: the tile kernel above one tile, the first-generation kernel below
-        gen3(t_beg, t_mid, counters + 6);
-        gen1(32, t_mid, t_end, counters + 7);
+      } else if (tl == 0) {   // default: the tile kernel above one tile; below, the pair-batched kernel for
+        gen3(t_beg, t_mid, counters + 6);  // long batches and the first-generation kernel for short ones
+        if (a.npairs >= kBatchKernelMinPairs) batch(t_mid, t_end, counters + 7);
+        else gen1(32, t_mid, t_end, counters + 7);
       } else if (tl == 3) {   // tuning: the tile kernel for everything
         gen3(t_beg, t_mid, counters + 6);
         gen3(t_mid, t_end, counters + 7);
@@ -771,6 +783,17 @@ int upload(ogjk_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
   return OGJK_OK;
 }
 
+HostPool* host_pool(ogjk_ctx* ctx);
+
+// Pinned (page-locked or registered) host memory?  Device-to-host copies into pageable memory are
+// staged by the driver through small bounce buffers and block the issuing thread: ~4x slower than
+// the link, and they serialise the pipeline.
+bool host_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
 // Chunked variant of the host pipeline for the un-indexed form (pair p uses polytope p
 // of each pool -- the reference's bd1[] / bd2[] arrays): the pair range is cut into
 // chunks whose coordinate ranges are contiguous, and H2D of chunk c+1, the kernels
@@ -823,6 +846,22 @@ int host_pipeline_chunked(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const
   const int64_t* do2 = static_cast<const int64_t*>(ctx->d_off2.p);
   const int* dk1 = static_cast<const int*>(ctx->d_cnt1.p);
   const int* dk2 = static_cast<const int*>(ctx->d_cnt2.p);
+  // results go straight to the caller's arrays when those are pinned, through the pinned landing zone otherwise
+  const bool stage_out = !(host_pinned(distances) && (!simplices || host_pinned(simplices)) &&
+                           (!run_epa || (host_pinned(w1) && host_pinned(w2) && (!normals || host_pinned(normals)))));
+  T *o_dist = distances, *o_w1 = w1, *o_w2 = w2, *o_nrm = normals;
+  S* o_simp = simplices;
+  if (stage_out) {
+    const size_t bs = ((size_t)npairs * sizeof(S) + 255) & ~(size_t)255, bd = ((size_t)npairs * sizeof(T) + 255) & ~(size_t)255;
+    const size_t bw = ((size_t)npairs * 3 * sizeof(T) + 255) & ~(size_t)255;
+    if ((rc = ctx->h_out.reserve(bs + bd + 3 * bw))) return rc;
+    char* z = static_cast<char*>(ctx->h_out.p);
+    o_simp = simplices ? reinterpret_cast<S*>(z) : nullptr;
+    o_dist = reinterpret_cast<T*>(z + bs);
+    o_w1 = reinterpret_cast<T*>(z + bs + bd);
+    o_w2 = reinterpret_cast<T*>(z + bs + bd + bw);
+    o_nrm = normals ? reinterpret_cast<T*>(z + bs + bd + 2 * bw) : nullptr;
+  }
   ctx->timed_mask = 0;
   if ((rc = store_build<T>(ctx, &ctx->scratch1, npairs, nverts1, dc1, do1, dk1, false, sc, false, host_sum(cnt1, npairs)))) return rc;
   if ((rc = store_build<T>(ctx, &ctx->scratch2, npairs, nverts2, dc2, do2, dk2, false, sc, false, host_sum(cnt2, npairs)))) return rc;
@@ -879,14 +918,38 @@ int host_pipeline_chunked(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const
     }
     CU(cudaEventRecord(ctx->chunk_done[c], sc));
     CU(cudaStreamWaitEvent(so, ctx->chunk_done[c], 0));
-    CU(cudaMemcpyAsync(distances + lo, static_cast<T*>(ctx->d_dist.p) + lo, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, so));
+    CU(cudaMemcpyAsync(o_dist + lo, static_cast<T*>(ctx->d_dist.p) + lo, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, so));
     if (simplices)
-      CU(cudaMemcpyAsync(simplices + lo, static_cast<S*>(ctx->d_simp.p) + lo, (size_t)n * sizeof(S), cudaMemcpyDeviceToHost, so));
+      CU(cudaMemcpyAsync(o_simp + lo, static_cast<S*>(ctx->d_simp.p) + lo, (size_t)n * sizeof(S), cudaMemcpyDeviceToHost, so));
     if (run_epa) {
-      CU(cudaMemcpyAsync(w1 + 3 * lo, static_cast<T*>(ctx->d_w1.p) + 3 * lo, (size_t)n * 3 * sizeof(T), cudaMemcpyDeviceToHost, so));
-      CU(cudaMemcpyAsync(w2 + 3 * lo, static_cast<T*>(ctx->d_w2.p) + 3 * lo, (size_t)n * 3 * sizeof(T), cudaMemcpyDeviceToHost, so));
+      CU(cudaMemcpyAsync(o_w1 + 3 * lo, static_cast<T*>(ctx->d_w1.p) + 3 * lo, (size_t)n * 3 * sizeof(T), cudaMemcpyDeviceToHost, so));
+      CU(cudaMemcpyAsync(o_w2 + 3 * lo, static_cast<T*>(ctx->d_w2.p) + 3 * lo, (size_t)n * 3 * sizeof(T), cudaMemcpyDeviceToHost, so));
       if (normals)
-        CU(cudaMemcpyAsync(normals + 3 * lo, static_cast<T*>(ctx->d_nrm.p) + 3 * lo, (size_t)n * 3 * sizeof(T), cudaMemcpyDeviceToHost, so));
+        CU(cudaMemcpyAsync(o_nrm + 3 * lo, static_cast<T*>(ctx->d_nrm.p) + 3 * lo, (size_t)n * 3 * sizeof(T), cudaMemcpyDeviceToHost, so));
+    }
+    if (stage_out) CU(cudaEventRecord(ctx->chunk_out[c], so));
+  }
+  if (stage_out) {
+    // results landed in the pinned zone: hand every chunk to the caller's (pageable) arrays as soon as its
+    // copy has finished, with the context's host threads, while later chunks are still in flight
+    HostPool* pool = host_pool(ctx);
+    for (int c = 0; c < K; ++c) {
+      CU(cudaEventSynchronize(ctx->chunk_out[c]));
+      const int64_t lo = r[c].lo, n = r[c].hi - r[c].lo;
+      constexpr int64_t kPart = 16384;  // pairs per copy job
+      const int parts = (int)((n + kPart - 1) / kPart);
+      auto job = [&](int j) {
+        const int64_t a0 = lo + (int64_t)j * kPart, m = (a0 + kPart < lo + n ? a0 + kPart : lo + n) - a0;
+        memcpy(distances + a0, o_dist + a0, (size_t)m * sizeof(T));
+        if (simplices) memcpy(simplices + a0, o_simp + a0, (size_t)m * sizeof(S));
+        if (run_epa) {
+          memcpy(w1 + 3 * a0, o_w1 + 3 * a0, (size_t)m * 3 * sizeof(T));
+          memcpy(w2 + 3 * a0, o_w2 + 3 * a0, (size_t)m * 3 * sizeof(T));
+          if (normals) memcpy(normals + 3 * a0, o_nrm + 3 * a0, (size_t)m * 3 * sizeof(T));
+        }
+      };
+      if (pool && parts > 1) pool->run(parts, job);
+      else for (int j = 0; j < parts; ++j) job(j);
     }
   }
   int bad = 0;
@@ -1456,6 +1519,7 @@ int ogjk_ctx_create(int device, ogjk_ctx** out) {
   for (int i = 0; i < 16 && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&c->chunk_in[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->chunk_done[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->chunk_out[i], cudaEventDisableTiming);
   }
   if (e == cudaSuccess && c->counters.reserve(kCounterSlots * sizeof(unsigned long long)) != OGJK_OK) e = cudaErrorMemoryAllocation;
   if (e == cudaSuccess) e = cudaMemset(c->counters.p, 0, kCounterSlots * sizeof(unsigned long long));
@@ -1481,6 +1545,7 @@ void ogjk_ctx_destroy(ogjk_ctx* c) {
                     &c->d_cnt1,   &c->d_cnt2,     &c->d_idx1,     &c->d_idx2,    &c->d_simp,    &c->d_dist};
   for (DevBuf* b : bufs) b->release();
   c->h_stage.release();
+  c->h_out.release();
   delete c->pool;
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->in_stream) cudaStreamDestroy(c->in_stream);
@@ -1488,6 +1553,7 @@ void ogjk_ctx_destroy(ogjk_ctx* c) {
   for (int i = 0; i < 16; ++i) {
     if (c->chunk_in[i]) cudaEventDestroy(c->chunk_in[i]);
     if (c->chunk_done[i]) cudaEventDestroy(c->chunk_done[i]);
+    if (c->chunk_out[i]) cudaEventDestroy(c->chunk_out[i]);
   }
   for (int i = 0; i < 2 * kPhases; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   delete c;

@@ -172,7 +172,7 @@ int multi_run(ogjk_multi_* m, const std::function<int(int)>& fn) {
     w->cv.wait(lk, [&] { return w->done; });
     if (w->rc && !rc) {
       rc = w->rc;
-      snprintf(g_err, sizeof(g_err), "device %d: %s", w->device, w->err);
+      snprintf(g_err, sizeof(g_err), "device %d: %.400s", w->device, w->err);
     }
   }
   return rc;

@@ -85,8 +85,11 @@ __host__ __device__ __forceinline__ int accel_table_stride(int nc) { return (nc 
 // Element offsets inside a polytope's table: cone header (ox oy oz slack) + cone arrays (only in
 // -DOGJK_T3_CONE=1 builds), cluster records.
 __host__ __device__ __forceinline__ int accel_cone_at(int ncs) { return 6 * ncs + 6 * (16384 / 32 / 32); }
+#ifndef OGJK_TABLE_PAD
+#define OGJK_TABLE_PAD 0  // tuning: extra elements between the box arrays and the records
+#endif
 __host__ __device__ __forceinline__ int accel_records_at(int ncs) {
-  return OGJK_T3_CONE ? 13 * ncs + 6 * (16384 / 32 / 32) + 4 : 6 * ncs + 6 * (16384 / 32 / 32);
+  return (OGJK_T3_CONE ? 13 * ncs + 6 * (16384 / 32 / 32) + 4 : 6 * ncs + 6 * (16384 / 32 / 32)) + OGJK_TABLE_PAD;
 }
 template <typename T> __host__ __device__ __forceinline__ long long accel_elems(int n) {
   const int nc = (n + kAccelCluster - 1) / kAccelCluster;
@@ -301,8 +304,10 @@ accel_build_kernel(StoreView<T> s, long long npoly, T* __restrict__ accel, int p
   extern __shared__ unsigned long long accel_keys[];
   __shared__ unsigned seg_lo[3][kAccelMaxClusters], seg_hi[3][kAccelMaxClusters];
   __shared__ unsigned char seg_axis[kAccelMaxClusters];
+#if OGJK_T3_CONE
   __shared__ T cone_o[3];
   __shared__ unsigned cone_rmax;  // ordered fp32 key of the largest cluster radius
+#endif
   const int tid = threadIdx.x, nth = blockDim.x;
   for (long long h = blockIdx.x; h < npoly; h += gridDim.x) {
     const int n = s.cnt[h];

@@ -48,10 +48,10 @@ namespace ogjk {
 #endif
 // OGJK_T3_CONE (store.cuh, default 0): min(box bound, cone bound) per cluster
 #ifndef OGJK_LB_TABLE3_F32
-#define OGJK_LB_TABLE3_F32 4
+#define OGJK_LB_TABLE3_F32 7
 #endif
 #ifndef OGJK_LB_TABLE3_F64
-#define OGJK_LB_TABLE3_F64 3
+#define OGJK_LB_TABLE3_F64 4
 #endif
 
 template <typename T> struct T3Vpl { static constexpr int value = sizeof(T) == 4 ? OGJK_T3_VPL_F32 : OGJK_T3_VPL_F64; };
@@ -401,10 +401,10 @@ gjk_table3_kernel(const __grid_constant__ StoreArgs<T> a, const int* __restrict_
 // Every pair executes exactly the operation sequence of the warp-per-pair kernels, so the
 // results are the same bytes.
 #ifndef OGJK_LB_TABLEB_F32
-#define OGJK_LB_TABLEB_F32 4
+#define OGJK_LB_TABLEB_F32 8
 #endif
 #ifndef OGJK_LB_TABLEB_F64
-#define OGJK_LB_TABLEB_F64 2
+#define OGJK_LB_TABLEB_F64 3
 #endif
 
 template <typename T> OGJK_DI const T* t3_bcast_ptr(const T* p, int src) {
@@ -420,14 +420,24 @@ gjk_tablebatch_kernel(const __grid_constant__ StoreArgs<T> a, const int* __restr
   const int lane = threadIdx.x & 31;
   const long long begin = seg_begin ? (long long)*seg_begin : 0;
   const long long end = seg_end ? (long long)*seg_end : a.npairs;
+  // Guided batch sizes: a warp takes 32 pairs while the queue is long and fewer as it drains
+  // (remaining / (2 x warps in the grid), down to single pairs), so the last wave of warps ends
+  // together and a short queue still spreads over every warp.
+  const long long nwarps2 = 2ll * gridDim.x * (blockDim.x >> 5);
   for (;;) {
     unsigned long long got = 0;
-    if (lane == 0) got = atomicAdd(head, 32ull);
+    int take = 32;
+    if (lane == 0) {
+      const long long left = end - begin - (long long)*(volatile unsigned long long*)head;
+      take = (int)max(1ll, min(32ll, left / nwarps2));
+      got = atomicAdd(head, (unsigned long long)take);
+    }
     got = __shfl_sync(FULL, got, 0);
+    take = __shfl_sync(FULL, take, 0);
     const long long base = begin + (long long)got;
     if (base >= end) break;
     const long long slot = base + lane;
-    bool active = slot < end;
+    bool active = lane < take && slot < end;
     // this lane's pair
     long long p = 0;
     int n1 = 1, n2 = 1;
