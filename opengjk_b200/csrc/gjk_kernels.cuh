@@ -533,7 +533,7 @@ template <typename T, int G> struct ScanSide {
 // maximum, so the result is the full scan's: the largest dot if it strictly exceeds the
 // carried point's, lowest original index among equals.  The winner's coordinates travel by
 // shuffle.  Without two tables both bodies take the plain scan.
-template <typename T, int G>
+template <int KO = 0, typename T, int G>
 OGJK_DI void support_both(const AccelBody<T, G>& b1, const AccelBody<T, G>& b2, const V3<T>& v, V3<T>& sa, int& ia,
                           V3<T>& sb, int& ib) {
   if (!(b1.acc && b2.acc)) {
@@ -542,7 +542,7 @@ OGJK_DI void support_both(const AccelBody<T, G>& b1, const AccelBody<T, G>& b2, 
     return;
   }
   constexpr int VPL = 32 / G;
-  constexpr int K = OGJK_ACCEL_K ? OGJK_ACCEL_K : (G == 8 ? 1 : G == 16 ? 2 : 3);
+  constexpr int K = KO ? KO : OGJK_ACCEL_K ? OGJK_ACCEL_K : (G == 8 ? 1 : G == 16 ? 2 : 3);  // KO: the caller's choice
   using Side = ScanSide<T, G>;
   using Hit = typename Side::Hit;
   const int g = b1.base.g;

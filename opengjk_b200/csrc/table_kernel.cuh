@@ -406,6 +406,9 @@ gjk_table3_kernel(const __grid_constant__ StoreArgs<T> a, const int* __restrict_
 #ifndef OGJK_LB_TABLEB_F64
 #define OGJK_LB_TABLEB_F64 3
 #endif
+#ifndef OGJK_TB_K
+#define OGJK_TB_K 2  // clusters per body per trip of the scan (the warp-per-pair kernel takes 3 with its 128 registers)
+#endif
 
 template <typename T> OGJK_DI const T* t3_bcast_ptr(const T* p, int src) {
   return reinterpret_cast<const T*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(p), src));
@@ -471,7 +474,7 @@ gjk_tablebatch_kernel(const __grid_constant__ StoreArgs<T> a, const int* __restr
         V3<T> sa{__shfl_sync(FULL, st.sa.x, j), __shfl_sync(FULL, st.sa.y, j), __shfl_sync(FULL, st.sa.z, j)};
         V3<T> sb{__shfl_sync(FULL, st.sb.x, j), __shfl_sync(FULL, st.sb.y, j), __shfl_sync(FULL, st.sb.z, j)};
         int ia = __shfl_sync(FULL, st.ia, j), ib = __shfl_sync(FULL, st.ib, j);
-        support_both(b1, b2, v, sa, ia, sb, ib);
+        support_both<OGJK_TB_K>(b1, b2, v, sa, ia, sb, ib);
         if (lane == j) { st.sa = sa; st.ia = ia; st.sb = sb; st.ib = ib; }
       }
       if (active) {
