@@ -384,12 +384,13 @@ int store_build_accel(ogjk_ctx* ctx, ogjk_store_* s, cudaStream_t st) {
   const long long nblocks = (npoly + kScanBlock - 1) / kScanBlock;
   int rc;
   if ((rc = s->aoff.reserve((size_t)npoly * sizeof(long long)))) return rc;
-  if ((rc = s->scan_tmp.reserve((size_t)(nblocks + 2) * sizeof(long long)))) return rc;
+  if ((rc = s->scan_tmp.reserve((size_t)(nblocks + 2 + 8) * sizeof(long long)))) return rc;
   const int* cnt = static_cast<const int*>(s->cnt.p);
   auto* sums = static_cast<long long*>(s->scan_tmp.p);
   auto* aoff = static_cast<long long*>(s->aoff.p);
   int* d_max = reinterpret_cast<int*>(sums + nblocks + 1);
-  CU(cudaMemsetAsync(d_max, 0, sizeof(long long), st));
+  auto* build_next = reinterpret_cast<unsigned long long*>(sums + nblocks + 2);  // one work counter per build launch
+  CU(cudaMemsetAsync(d_max, 0, 9 * sizeof(long long), st));
   const AccelElems<T> f{amin};
   scan_block_sums_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(cnt, npoly, sums, f);
   scan_spine_kernel<<<1, 1024, 0, st>>>(sums, nblocks, sums + nblocks);
@@ -406,19 +407,25 @@ int store_build_accel(ogjk_ctx* ctx, ogjk_store_* s, cudaStream_t st) {
   const int maxn = (int)(tail[1] & 0xffffffffll);
   if (total <= 0 || maxn <= 0) return OGJK_OK;
   if ((rc = s->accel.reserve((size_t)total * sizeof(T)))) return rc;
-  int pcap = 32;
-  while (pcap < maxn) pcap <<= 1;
-  const size_t smem = (size_t)pcap * sizeof(unsigned long long);
-  CU(cudaFuncSetAttribute(accel_build_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   StoreView<T> v{static_cast<const T*>(s->data.p), static_cast<const long long*>(s->boff.p), cnt};
   v.accel = static_cast<const T*>(s->accel.p);
   v.aoff = aoff;
   v.accel_min = amin;
-  // small polytopes: narrow CTAs, many per SM (the per-level sorts are barrier-latency bound)
-  const int threads = pcap <= 2048 ? 256 : 1024;
-  const long long cap = (long long)ctx->sm_count * (pcap <= 2048 ? 8 : pcap <= 4096 ? 2 : 1);
-  accel_build_kernel<T><<<(unsigned)(npoly < cap ? npoly : cap), threads, smem, st>>>(v, npoly, static_cast<T*>(s->accel.p), pcap);
-  ctx->launches += 1;
+  // One launch per power-of-two size range, so that small polytopes get narrow CTAs, many per SM
+  // (the per-level sorts are barrier-latency bound), and only the largest ones a whole SM.
+  int pmax = 2048;
+  while (pmax < maxn) pmax <<= 1;
+  CU(cudaFuncSetAttribute(accel_build_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)((size_t)pmax * sizeof(unsigned long long))));
+  int launch = 0;
+  for (int pcap = 2048, nlo = 0; nlo < maxn; nlo = pcap, pcap <<= 1, ++launch) {
+    const int threads = pcap <= 2048 ? 256 : pcap <= 4096 ? 512 : 1024;
+    const int per_sm = pcap <= 2048 ? 8 : pcap <= 4096 ? 4 : pcap <= 8192 ? 2 : 1;
+    const long long cap = (long long)ctx->sm_count * per_sm;
+    accel_build_kernel<T><<<(unsigned)(npoly < cap ? npoly : cap), threads, (size_t)pcap * sizeof(unsigned long long), st>>>(
+        v, npoly, static_cast<T*>(s->accel.p), nlo, pcap, build_next + launch);
+    ctx->launches += 1;
+  }
   CU(cudaGetLastError());
   s->accel_min = amin;
   s->accel_elems = total;

@@ -37,8 +37,8 @@ template <typename T> struct StoreView {
 
 // ---- cluster tables: exact pruning of the support scan for large polytopes --------
 //   A polytope with many vertices gets, next to its block, a
-// copy of its vertices grouped into spatially compact clusters of 32 (k-d median
-// splits), the original index of every copied vertex, and each cluster's bounding box.
+// copy of its vertices grouped into spatially compact clusters of 32 (left-balanced k-d
+// splits along the widest axis), the original index of every copied vertex, and each cluster's bounding box.
 // For a search direction d the box corner picked by the signs of d gives
 //   ub = (cx*dx + cy*dy) + cz*dz  >=  (x*dx + y*dy) + z*dz   for every vertex of the cluster,
 // and the inequality holds for the ROUNDED values too (same operation order, IEEE
@@ -270,14 +270,85 @@ __device__ __forceinline__ unsigned accel_ord(float f) {  // order-preserving fl
 __device__ __forceinline__ float accel_unord(unsigned u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
-// Segment of clusters [c0, c1) that position `i` belongs to after `level` median splits
-// of the cluster range [0, nc): a segment of m clusters splits into ceil(m/2) and the rest.
+// Segment of clusters [c0, c1) that position `i` belongs to after `level` splits of the
+// cluster range [0, nc).  A segment of m clusters splits into the largest power of two below
+// m and the rest (a left-balanced k-d tree), so every segment starts at a multiple of its
+// size rounded up to a power of two: after `level` splits no segment has more than
+// 2^(K - level) clusters (2^K >= nc) or crosses a boundary of that size, and the level's sort
+// can run inside aligned blocks instead of over the whole polytope.
 __device__ __forceinline__ void accel_segment(int i, int level, int nc, int& c0, int& c1) {
   c0 = 0; c1 = nc;
   const int c = i / kAccelCluster;
   for (int l = 0; l < level && c1 - c0 > 1; ++l) {
-    const int mid = c0 + (c1 - c0 + 1) / 2;
+    const int mid = c0 + (1 << (31 - __clz(c1 - c0 - 1)));
     if (c < mid) c1 = mid; else c0 = mid;
+  }
+}
+
+// Bitonic sort of every aligned block of `sortw` keys (a power of two >= 64) of keys[0, P) in
+// shared memory, ascending.  The network's steps are grouped so that the keys make few round
+// trips through shared memory (the sort is bound by its bandwidth): the steps with a partner
+// distance below 32 run on one key per lane with shuffles, the others up to three at a time on
+// 8 keys per thread.  Every lane of the CTA calls this (CTA widths are multiples of 32).
+__device__ __forceinline__ unsigned long long accel_cx_lane(unsigned long long a, int j, bool asc) {
+  const unsigned long long b = __shfl_xor_sync(0xffffffffu, a, j);
+  const bool keep_min = ((threadIdx.x & j) == 0) == asc;
+  return keep_min ? (a < b ? a : b) : (a > b ? a : b);
+}
+template <int R>
+__device__ __forceinline__ void accel_sort_group(unsigned long long* keys, int P, int sortw, int k, int j, int tid, int nth) {
+  constexpr int E = 1 << R;
+  const int q = j >> (R - 1);  // smallest partner distance of the group
+  const int qs = 31 - __clz(q);
+  for (int t = tid; t < (P >> R); t += nth) {
+    const int base = ((t >> qs) << (qs + R)) | (t & (q - 1));
+    const bool asc = (base & k) == 0 || k == sortw;
+    unsigned long long x[E];
+#pragma unroll
+    for (int m = 0; m < E; ++m) x[m] = keys[base + m * q];
+#pragma unroll
+    for (int r = R - 1; r >= 0; --r) {
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        if (m & (1 << r)) continue;
+        const unsigned long long a = x[m], b = x[m | (1 << r)];
+        if ((a > b) == asc) { x[m] = b; x[m | (1 << r)] = a; }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < E; ++m) keys[base + m * q] = x[m];
+  }
+}
+__device__ __forceinline__ void accel_sort_blocks(unsigned long long* keys, int P, int sortw, int tid, int nth) {
+  // k = 2 .. 32: whole sub-networks inside 32 consecutive keys
+  for (int i = tid; i < P; i += nth) {
+    unsigned long long a = keys[i];
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+      const bool asc = (i & k) == 0;  // sortw >= 64: never the final merge
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) a = accel_cx_lane(a, j, asc);
+    }
+    keys[i] = a;
+  }
+  __syncthreads();
+  for (int k = 64; k <= sortw; k <<= 1) {
+    int j = k >> 1;
+    while (j >= 32) {
+      const int left = 31 - __clz(j) - 4;  // steps with a partner distance >= 32 still to do
+      if (left >= 3) { accel_sort_group<3>(keys, P, sortw, k, j, tid, nth); j >>= 3; }
+      else if (left == 2) { accel_sort_group<2>(keys, P, sortw, k, j, tid, nth); j >>= 2; }
+      else { accel_sort_group<1>(keys, P, sortw, k, j, tid, nth); j >>= 1; }
+      __syncthreads();
+    }
+    for (int i = tid; i < P; i += nth) {
+      unsigned long long a = keys[i];
+      const bool asc = (i & k) == 0 || k == sortw;
+#pragma unroll
+      for (int jj = 16; jj > 0; jj >>= 1) a = accel_cx_lane(a, jj, asc);
+      keys[i] = a;
+    }
+    __syncthreads();
   }
 }
 
@@ -296,11 +367,14 @@ max_count_kernel(const int* __restrict__ cnt, long long n, int amin, int* __rest
 
 // Sort keys live in dynamic shared memory: (segment's first cluster) << 46 | ordered
 // fp32 coordinate along the segment's widest axis << 14 | vertex index; one bitonic sort
-// per k-d level.  The partition is a heuristic (any partition gives exact queries), so
-// the split coordinate is compared in fp32 even for fp64 stores.
+// per k-d level, inside the aligned blocks that hold the level's segments.  The partition is a
+// heuristic (any partition gives exact queries), so the split coordinate is compared in fp32
+// even for fp64 stores.  One launch handles the polytopes with nlo < n <= pcap vertices
+// (the host launches one per power-of-two size range, each with its own CTA shape).
 template <typename T>
 __global__ void __launch_bounds__(1024)
-accel_build_kernel(StoreView<T> s, long long npoly, T* __restrict__ accel, int pcap) {
+accel_build_kernel(StoreView<T> s, long long npoly, T* __restrict__ accel, int nlo, int pcap,
+                   unsigned long long* __restrict__ next) {
   extern __shared__ unsigned long long accel_keys[];
   __shared__ unsigned seg_lo[3][kAccelMaxClusters], seg_hi[3][kAccelMaxClusters];
   __shared__ unsigned char seg_axis[kAccelMaxClusters];
@@ -308,16 +382,23 @@ accel_build_kernel(StoreView<T> s, long long npoly, T* __restrict__ accel, int p
   __shared__ T cone_o[3];
   __shared__ unsigned cone_rmax;  // ordered fp32 key of the largest cluster radius
 #endif
+  __shared__ long long next_h;
   const int tid = threadIdx.x, nth = blockDim.x;
-  for (long long h = blockIdx.x; h < npoly; h += gridDim.x) {
+  for (;;) {
+    // polytopes are handed out one at a time (build times differ by an order of magnitude
+    // inside a launch's size range and most polytopes of a mixed pool are out of it)
+    __syncthreads();
+    if (tid == 0) next_h = (long long)atomicAdd(next, 1ull);
+    __syncthreads();
+    const long long h = next_h;
+    if (h >= npoly) break;
     const int n = s.cnt[h];
-    if (n < s.accel_min || n > kAccelMaxVerts) continue;
+    if (n < s.accel_min || n > kAccelMaxVerts || n <= nlo || n > pcap) continue;
     const int np = pad4(n);
     const T* blk = s.data + s.boff[h];
     const int nc = (n + kAccelCluster - 1) / kAccelCluster;
     int P = 32;
     while (P < n) P <<= 1;
-    if (P > pcap) continue;  // cannot happen: pcap is sized from the largest eligible polytope
     for (int i = tid; i < P; i += nth) accel_keys[i] = i < n ? (unsigned long long)i : ~0ull;
     int levels = 0;
     while ((1 << levels) < nc) ++levels;
@@ -328,16 +409,22 @@ accel_build_kernel(StoreView<T> s, long long npoly, T* __restrict__ accel, int p
         seg_hi[0][c] = seg_hi[1][c] = seg_hi[2][c] = 0u;
       }
       __syncthreads();
-      for (int i = tid; i < n; i += nth) {
+      // a warp covers one cluster (CTA widths are multiples of 32), i.e. one segment: its extent
+      // is reduced on the redux unit and one lane per warp touches the segment's shared counters
+      for (int i = tid; i < nc * kAccelCluster; i += nth) {
         int c0, c1;
         accel_segment(i, level, nc, c0, c1);
-        if (c1 - c0 > 1) {
-          const int v = (int)(accel_keys[i] & 0x3fffu);
+        if (c1 - c0 > 1) {  // warp-uniform
+          const int v = (int)(accel_keys[i < n ? i : 0] & 0x3fffu);
 #pragma unroll
           for (int a = 0; a < 3; ++a) {
             const unsigned f = accel_ord((float)blk[a * np + v]);
-            atomicMin(&seg_lo[a][c0], f);
-            atomicMax(&seg_hi[a][c0], f);
+            const unsigned lo = __reduce_min_sync(0xffffffffu, i < n ? f : 0xffffffffu);
+            const unsigned hi = __reduce_max_sync(0xffffffffu, i < n ? f : 0u);
+            if ((tid & 31) == 0) {
+              atomicMin(&seg_lo[a][c0], lo);
+              atomicMax(&seg_hi[a][c0], hi);
+            }
           }
         }
       }
@@ -361,17 +448,8 @@ accel_build_kernel(StoreView<T> s, long long npoly, T* __restrict__ accel, int p
         accel_keys[i] = ((unsigned long long)c0 << 46) | ((unsigned long long)f << 14) | v;
       }
       __syncthreads();
-      for (int k = 2; k <= P; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int t = tid; t < (P >> 1); t += nth) {
-            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-            const int l = i | j;
-            const unsigned long long a = accel_keys[i], b = accel_keys[l];
-            if ((a > b) == ((i & k) == 0)) { accel_keys[i] = b; accel_keys[l] = a; }
-          }
-          __syncthreads();
-        }
-      }
+      const int sortw = max(P >> level, 2 * kAccelCluster);  // aligned block that holds any segment of this level
+      accel_sort_blocks(accel_keys, P, sortw, tid, nth);
     }
     // cluster records + original indices; a warp per cluster reduces its bounding box
     const int ncs = accel_table_stride(nc);
