@@ -19,6 +19,9 @@
 #include <new>
 #include <thread>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "../../include/opengjk_b200.h"
 #include "gjk_kernels.cuh"
@@ -801,6 +804,75 @@ bool host_pinned(const void* p) {
   return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
 }
 
+// Sequential writer for the gather: collects the small per-polytope blocks in a cache-resident
+// buffer and writes whole lines to the pinned stage with streaming stores, so that the stage is
+// written once instead of read (for ownership) and written -- the gather runs beside the H2D
+// copy and both are bound by host memory bandwidth.
+class StreamOut {
+ public:
+  explicit StreamOut(void* dst) : dst_(static_cast<char*>(dst)) {}
+  void put(const void* src, size_t n) {
+    const char* s = static_cast<const char*>(src);
+    while (n) {
+      if (!fill_ && (reinterpret_cast<uintptr_t>(dst_) & 63)) {  // head: up to the next line
+        size_t h = 64 - (reinterpret_cast<uintptr_t>(dst_) & 63);
+        if (h > n) h = n;
+        memcpy(dst_, s, h);
+        dst_ += h; s += h; n -= h;
+        continue;
+      }
+      size_t take = sizeof(buf_) - fill_;
+      if (take > n) take = n;
+      memcpy(buf_ + fill_, s, take);
+      fill_ += take; s += take; n -= take;
+      if (fill_ == sizeof(buf_)) { lines(fill_); fill_ = 0; }
+    }
+  }
+  void finish() {
+    const size_t whole = fill_ & ~(size_t)63;
+    lines(whole);
+    if (fill_ > whole) memcpy(dst_, buf_ + whole, fill_ - whole);
+    dst_ += fill_ - whole;
+    fill_ = 0;
+#if defined(__SSE2__)
+    _mm_sfence();
+#endif
+  }
+
+ private:
+  void lines(size_t bytes) {  // dst_ is 64-byte aligned here
+#if defined(__SSE2__)
+    for (size_t i = 0; i < bytes; i += 16)
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst_ + i), _mm_load_si128(reinterpret_cast<const __m128i*>(buf_ + i)));
+#else
+    memcpy(dst_, buf_, bytes);
+#endif
+    dst_ += bytes;
+  }
+  char* dst_;
+  size_t fill_ = 0;
+  alignas(64) char buf_[4096];
+};
+
+// One large block through the same streaming stores (pageable -> pinned staging and back).
+inline void stream_copy(void* dst, const void* src, size_t n) {
+#if defined(__SSE2__)
+  char* d = static_cast<char*>(dst);
+  const char* s = static_cast<const char*>(src);
+  size_t head = (64 - (reinterpret_cast<uintptr_t>(d) & 63)) & 63;
+  if (head > n) head = n;
+  memcpy(d, s, head);
+  d += head; s += head; n -= head;
+  const size_t body = n & ~(size_t)63;
+  for (size_t i = 0; i < body; i += 16)
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + i), _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i)));
+  memcpy(d + body, s + body, n - body);
+  _mm_sfence();
+#else
+  memcpy(dst, src, n);
+#endif
+}
+
 // Chunked variant of the host pipeline for the un-indexed form (pair p uses polytope p
 // of each pool -- the reference's bd1[] / bd2[] arrays): the pair range is cut into
 // chunks whose coordinate ranges are contiguous, and H2D of chunk c+1, the kernels
@@ -947,12 +1019,12 @@ int host_pipeline_chunked(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const
       const int parts = (int)((n + kPart - 1) / kPart);
       auto job = [&](int j) {
         const int64_t a0 = lo + (int64_t)j * kPart, m = (a0 + kPart < lo + n ? a0 + kPart : lo + n) - a0;
-        memcpy(distances + a0, o_dist + a0, (size_t)m * sizeof(T));
-        if (simplices) memcpy(simplices + a0, o_simp + a0, (size_t)m * sizeof(S));
+        stream_copy(distances + a0, o_dist + a0, (size_t)m * sizeof(T));
+        if (simplices) stream_copy(simplices + a0, o_simp + a0, (size_t)m * sizeof(S));
         if (run_epa) {
-          memcpy(w1 + 3 * a0, o_w1 + 3 * a0, (size_t)m * 3 * sizeof(T));
-          memcpy(w2 + 3 * a0, o_w2 + 3 * a0, (size_t)m * 3 * sizeof(T));
-          if (normals) memcpy(normals + 3 * a0, o_nrm + 3 * a0, (size_t)m * 3 * sizeof(T));
+          stream_copy(w1 + 3 * a0, o_w1 + 3 * a0, (size_t)m * 3 * sizeof(T));
+          stream_copy(w2 + 3 * a0, o_w2 + 3 * a0, (size_t)m * 3 * sizeof(T));
+          if (normals) stream_copy(normals + 3 * a0, o_nrm + 3 * a0, (size_t)m * 3 * sizeof(T));
         }
       };
       if (pool && parts > 1) pool->run(parts, job);
@@ -965,6 +1037,52 @@ int host_pipeline_chunked(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const
   CU(cudaStreamSynchronize(si));
   if ((rc = pool_verdict(ctx, sc))) return rc;
   return bad ? 1 : OGJK_OK;  // 1: polytopes not in pair order -> caller reruns the one-shot path
+}
+
+// Pageable coordinate pools in the un-indexed form: a host-to-device copy from pageable memory
+// goes through the driver's small bounce buffers and blocks the issuing thread, so the pools are
+// copied into the pinned stage by the context's host threads, chunk by chunk in pipeline order,
+// and the chunked pipeline uploads from there (`ready` gates each chunk).  Returns false when
+// the layout is not chunkable or there are no host threads (the caller passes the arrays as is).
+template <typename T>
+bool stage_flat_inputs(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t* off1, const int* cnt1, int64_t nverts1,
+                       const T* coords2, const int64_t* off2, const int* cnt2, int64_t nverts2, const T** s1, const T** s2,
+                       HostReady* ready) {
+  const int K = ctx->pipeline_chunks > 16 ? 16 : ctx->pipeline_chunks;
+  if (K < 2 || npairs < 4096 * (int64_t)K) return false;
+  HostPool* pool = host_pool(ctx);
+  if (!pool) return false;
+  const size_t b1 = (((size_t)nverts1 * 3 * sizeof(T)) + 255) & ~(size_t)255, b2 = (size_t)nverts2 * 3 * sizeof(T);
+  if (ctx->h_stage.reserve(b1 + b2)) { cudaGetLastError(); return false; }
+  char* z = static_cast<char*>(ctx->h_stage.p);
+  struct Piece { char* dst; const char* src; size_t bytes; };
+  auto pieces = std::make_shared<std::vector<Piece>>();
+  auto ends = std::make_shared<std::vector<std::pair<int64_t, int>>>();  // (pairs up to, jobs up to)
+  constexpr size_t kPiece = (size_t)1 << 20;
+  int64_t pa1 = 0, pa2 = 0;
+  for (int c = 0; c < K; ++c) {
+    const int64_t lo = npairs * c / K, hi = npairs * (c + 1) / K, last = hi - 1;
+    const int64_t a1 = off1[lo], e1 = off1[last] + cnt1[last], a2 = off2[lo], e2 = off2[last] + cnt2[last];
+    if (a1 < pa1 || a2 < pa2 || e1 < a1 || e2 < a2 || e1 > nverts1 || e2 > nverts2) return false;  // not chunkable
+    pa1 = e1; pa2 = e2;
+    const size_t o1 = (size_t)a1 * 3 * sizeof(T), n1 = (size_t)(e1 - a1) * 3 * sizeof(T);
+    const size_t o2 = (size_t)a2 * 3 * sizeof(T), n2 = (size_t)(e2 - a2) * 3 * sizeof(T);
+    for (size_t at = 0; at < n1; at += kPiece)
+      pieces->push_back({z + o1 + at, reinterpret_cast<const char*>(coords1) + o1 + at, n1 - at < kPiece ? n1 - at : kPiece});
+    for (size_t at = 0; at < n2; at += kPiece)
+      pieces->push_back({z + b1 + o2 + at, reinterpret_cast<const char*>(coords2) + o2 + at, n2 - at < kPiece ? n2 - at : kPiece});
+    ends->push_back({hi, (int)pieces->size()});
+  }
+  pool->start((int)pieces->size(), [pieces](int j) { const Piece& p = (*pieces)[(size_t)j]; stream_copy(p.dst, p.src, p.bytes); });
+  *s1 = reinterpret_cast<const T*>(z);
+  *s2 = reinterpret_cast<const T*>(z + b1);
+  *ready = HostReady([pool, ends](int64_t upto) {
+    int jobs = ends->empty() ? 0 : ends->back().second;
+    for (const auto& e : *ends)
+      if (e.first >= upto) { jobs = e.second; break; }
+    pool->wait_prefix(jobs);
+  });
+  return true;
 }
 
 // Host-buffer pipeline shared by every host entry point: upload the pools, repack
@@ -987,8 +1105,14 @@ int host_pipeline(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t
   const bool shared_pool = (coords1 == coords2 && off1 == off2 && cnt1 == cnt2);
   const bool need_simp = simplices != nullptr || run_epa;
   if (run_gjk && !idx1 && !idx2 && !shared_pool && npoly1 >= npairs && npoly2 >= npairs) {
-    const int rcc = host_pipeline_chunked<T, S>(ctx, npairs, coords1, off1, cnt1, nverts1, coords2, off2, cnt2, nverts2,
-                                                simplices, distances, w1, w2, normals, run_epa, ready);
+    const T *c1 = coords1, *c2 = coords2;
+    HostReady staged_ready;
+    const bool staged = !ready && !(host_pinned(coords1) && host_pinned(coords2)) &&
+                        stage_flat_inputs<T>(ctx, npairs, coords1, off1, cnt1, nverts1, coords2, off2, cnt2, nverts2, &c1, &c2,
+                                             &staged_ready);
+    const int rcc = host_pipeline_chunked<T, S>(ctx, npairs, c1, off1, cnt1, nverts1, c2, off2, cnt2, nverts2, simplices,
+                                                distances, w1, w2, normals, run_epa, staged ? &staged_ready : ready);
+    if (staged) staged_ready(npairs);  // the copy jobs read the caller's arrays: drained before returning
     if (rcc <= 0) return rcc;  // done (0) or error (<0); 1 = layout not chunkable, use the one-shot path
   }
   if (ready) (*ready)(npoly1 > npoly2 ? npoly1 : npoly2);  // one-shot path: everything must be in place
@@ -1140,9 +1264,15 @@ HostReady start_gather(ogjk_ctx* ctx, int n, const P* bd1, const FlatSide<T>& f1
   const int njobs = (n + kGatherJob - 1) / kGatherJob;
   auto job = [=](int j) {
     const int lo = j * kGatherJob, hi = lo + kGatherJob < n ? lo + kGatherJob : n;
-    for (int i = lo; i < hi; ++i) memcpy(f1.coords + 3 * f1.off[i], bd1[i].coord, (size_t)bd1[i].numpoints * 3 * sizeof(T));
-    if (f2)
-      for (int i = lo; i < hi; ++i) memcpy(f2->coords + 3 * f2->off[i], bd2[i].coord, (size_t)bd2[i].numpoints * 3 * sizeof(T));
+    // a job's polytopes are consecutive in the stage (off[i + 1] = off[i] + cnt[i])
+    StreamOut o1(f1.coords + 3 * f1.off[lo]);
+    for (int i = lo; i < hi; ++i) o1.put(bd1[i].coord, (size_t)bd1[i].numpoints * 3 * sizeof(T));
+    o1.finish();
+    if (f2) {
+      StreamOut o2(f2->coords + 3 * f2->off[lo]);
+      for (int i = lo; i < hi; ++i) o2.put(bd2[i].coord, (size_t)bd2[i].numpoints * 3 * sizeof(T));
+      o2.finish();
+    }
   };
   if (!pool || n < 2 * kGatherJob) {  // small batch (or no threads): gather inline
     for (int j = 0; j < njobs; ++j) job(j);

@@ -39,7 +39,21 @@ for name, maker, n in (("hulls 8-64 v", lambda n, dt: W.mixed_hulls(n, dtype=dt)
                 lib.compute_minimum_distance(C.c_int(n), p(b1), p(b2), p(simp), p(dist))
             res[who] = n * reps / (time.perf_counter() - t0)
             res[who + "_checksum"] = float(np.nansum(dist))
+        if "skipped" in name:
+            # the flat-pool entry point with plain (pageable) numpy arrays, as a ctypes binding passes them
+            from opengjk_b200 import api
+            eng = api.Engine(0)
+            pools = w.two_pools()
+            got = eng.gjk_host_pools(*pools)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                got = eng.gjk_host_pools(*pools)
+            res["ours_flat_pageable"] = n * 3 / (time.perf_counter() - t0)
+            res["ours_flat_pageable_checksum"] = float(np.nansum(got[0] if isinstance(got, tuple) else got["distances"]))
+            del eng
         out = {"workload": name, "prec": prec, "pairs": n, "pairs_per_s": {k: v for k, v in res.items() if not k.endswith("checksum")}}
+        if "ours_flat_pageable" in res:
+            out["distance_sums"] = [res["ours_checksum"], res["ours_flat_pageable_checksum"]]
         if "ours" in res and "reference" in res:
             out["speedup"] = res["ours"] / res["reference"]
             out["distance_sums"] = [res["ours_checksum"], res["reference_checksum"]]
