@@ -157,6 +157,13 @@ OGJK_API int ogjk_ctx_set_passes(ogjk_ctx* ctx, int passes, int iters1, int iter
  * 8, 16 or 32 = the first-generation kernel with that many lanes per pair for every table pair.
  * Results do not depend on the choice. */
 OGJK_API int ogjk_ctx_set_table_lanes(ogjk_ctx* ctx, int lanes);
+/* In-CTA regrouping of the 2-lane size classes (csrc/regroup_kernel.cuh): a CTA takes 128 pairs, runs
+ * them iteration-synchronously and packs the pairs still iterating after `iters1` (and `iters2`) GJK
+ * iterations into the lowest lanes through shared memory, so that whole warps fall idle instead of
+ * lanes.  Bit-exact but measured 25 % slower than the plain group kernel on B200,
+ * so it is compiled into libopengjk_b200_exp.so only: the product library accepts 0 (off) and rejects
+ * anything else.  iters2 = 0 means one regroup point. */
+OGJK_API int ogjk_ctx_set_regroup(ogjk_ctx* ctx, int iters1, int iters2);
 OGJK_API void ogjk_store_destroy(ogjk_store* store);
 OGJK_API int64_t ogjk_store_bytes(const ogjk_store* store);
 OGJK_API int64_t ogjk_store_num_polytopes(const ogjk_store* store);

@@ -35,7 +35,7 @@ assert SIMPLEX_F32.itemsize == 108 and SIMPLEX_F64.itemsize == 184
 EXPORTS = [
     "ogjk_last_error", "ogjk_version", "ogjk_ctx_create", "ogjk_ctx_destroy", "ogjk_ctx_device",
     "ogjk_ctx_launch_count", "ogjk_ctx_pool_status", "ogjk_ctx_set_warp_threshold", "ogjk_ctx_set_timing", "ogjk_ctx_last_timing",
-    "ogjk_ctx_set_classes", "ogjk_ctx_set_pipeline_chunks", "ogjk_ctx_set_accel_min", "ogjk_ctx_set_table_lanes", "ogjk_ctx_set_passes", "ogjk_store_create_f32", "ogjk_store_create_f64", "ogjk_store_destroy", "ogjk_store_bytes",
+    "ogjk_ctx_set_classes", "ogjk_ctx_set_pipeline_chunks", "ogjk_ctx_set_accel_min", "ogjk_ctx_set_table_lanes", "ogjk_ctx_set_regroup", "ogjk_ctx_set_passes", "ogjk_store_create_f32", "ogjk_store_create_f64", "ogjk_store_destroy", "ogjk_store_bytes",
     "ogjk_store_num_polytopes", "ogjk_store_table_bytes", "ogjk_store_aabbs_f32", "ogjk_store_aabbs_f64", "ogjk_pairs_cull_f32",
     "ogjk_pairs_cull_f64", "ogjk_pairs_all_f32", "ogjk_pairs_all_f64", "ogjk_intersect_flags_f32", "ogjk_intersect_flags_f64", "ogjk_store_gjk_f32", "ogjk_store_gjk_f64",
     "ogjk_store_epa_f32", "ogjk_store_epa_f64", "ogjk_store_gjk_epa_f32", "ogjk_store_gjk_epa_f64",
@@ -100,6 +100,7 @@ def lib(path=None):
     L.ogjk_ctx_set_pipeline_chunks.argtypes = [C.c_void_p, C.c_int]
     L.ogjk_ctx_set_accel_min.argtypes = [C.c_void_p, C.c_int]
     L.ogjk_ctx_set_table_lanes.argtypes = [C.c_void_p, C.c_int]
+    L.ogjk_ctx_set_regroup.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ogjk_ctx_set_passes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.ogjk_store_destroy.argtypes = [C.c_void_p]
     L.ogjk_store_destroy.restype = None

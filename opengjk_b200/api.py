@@ -194,8 +194,12 @@ class Engine:
         self._ck(self._L.ogjk_ctx_set_passes(self._h, int(passes), int(iters1), int(iters2)))
 
     def set_table_lanes(self, lanes):
-        """Lanes per pair (8, 16, 32) of the kernel that uses the cluster tables."""
+        """Kernel choice for the cluster-table pairs (0 default routing, 1/2/3 or 8/16/32: see the header)."""
         self._ck(self._L.ogjk_ctx_set_table_lanes(self._h, int(lanes)))
+
+    def set_regroup(self, iters1, iters2=0):
+        """In-CTA regrouping of the 2-lane classes after iters1 (and iters2) iterations; 0 = off."""
+        self._ck(self._L.ogjk_ctx_set_regroup(self._h, int(iters1), int(iters2)))
 
     def set_pipeline_chunks(self, chunks):
         self._ck(self._L.ogjk_ctx_set_pipeline_chunks(self._h, int(chunks)))

@@ -28,6 +28,7 @@
 #include "table_kernel.cuh"
 #ifdef OGJK_EXPERIMENTAL
 #include "gjk_experimental.cuh"
+#include "regroup_kernel.cuh"
 #endif
 #include "epa_kernels.cuh"
 #include "broadphase.cuh"
@@ -207,6 +208,7 @@ struct ogjk_ctx_ {
   int passes = 1;
   int pass_iters[2] = {4, 3};
   DevBuf pass_list[2], pass_f[2], pass_i[2];
+  int regroup[2] = {0, 0};       // > 0: the 2-lane classes regroup in the CTA after that many iterations (tuning)
   int batch_blocks[2] = {0, 0};  // resident CTAs of gjk_tablebatch_kernel<float|double> on this device
   int table_lanes = 0;   // 0: tile kernel (table_kernel.cuh) above 1024 vertices, first-generation kernel below; 3 / 8,16,32: force one
   bool timing = false;
@@ -453,6 +455,17 @@ void launch_group(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const u
   const char* cap_env = getenv("OGJK_GRID_CAP");  // tuning hook (blocks per SM), read per call
   const int cap_per_sm = cap_env ? atoi(cap_env) : 16;
   long long blocks = (a.npairs * G + 127) / 128, cap = (long long)ctx->sm_count * cap_per_sm;
+#ifdef OGJK_EXPERIMENTAL
+  if constexpr (G == 2) {
+    if (ctx->regroup[0] > 0) {  // in-CTA regrouping after regroup[0] and regroup[1] iterations (regroup_kernel.cuh)
+      blocks = (a.npairs * G + kRegroupThreads - 1) / kRegroupThreads;
+      cap = (long long)ctx->sm_count * 8;
+      gjk_regroup_kernel<T, G><<<(unsigned)(blocks < cap ? blocks : cap), kRegroupThreads, 0, st>>>(a, list, b, e, head,
+                                                                                                   ctx->regroup[0], ctx->regroup[1]);
+      return;
+    }
+  }
+#endif
   gjk_group_kernel<T, G><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a, list, b, e, head);
 }
 
@@ -1952,6 +1965,17 @@ int ogjk_ctx_set_table_lanes(ogjk_ctx* c, int lanes) {
   if (!c || (lanes != 0 && lanes != 1 && lanes != 2 && lanes != 3 && lanes != 8 && lanes != 16 && lanes != 32))
     return fail(OGJK_ERR_ARG, "table lanes must be 0 (default), 1, 2, 3, 8, 16 or 32%s");
   c->table_lanes = lanes;
+  return OGJK_OK;
+}
+
+int ogjk_ctx_set_regroup(ogjk_ctx* c, int iters1, int iters2) {
+  if (!c || iters1 < 0 || iters2 < 0 || (iters1 > 0 && iters2 > 0 && iters2 <= iters1) || iters1 > kMaxIter || iters2 > kMaxIter)
+    return fail(OGJK_ERR_ARG, "regroup points must be 0 (off) or 1 <= iters1 < iters2 <= 25%s");
+#ifndef OGJK_EXPERIMENTAL
+  if (iters1 > 0) return fail(OGJK_ERR_ARG, "in-CTA regrouping lives in libopengjk_b200_exp.so (measured slower, see DESIGN.md)%s");
+#endif
+  c->regroup[0] = iters1;
+  c->regroup[1] = iters1 > 0 ? (iters2 > 0 ? iters2 : kMaxIter + 1) : 0;
   return OGJK_OK;
 }
 

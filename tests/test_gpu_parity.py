@@ -311,6 +311,31 @@ def test_multi_pass_scheduling_is_invisible(eng_exp, prec, dt):
         eng.set_passes(1)
 
 
+@pytest.mark.parametrize("prec,dt", PRECS)
+def test_in_cta_regrouping_is_invisible(eng, eng_exp, prec, dt):
+    """Pairs packed into other lanes of their CTA between iterations (regroup_kernel.cuh) give the plain
+    group kernel's bytes for every choice of regroup points, including batches that do not fill a CTA.
+    Experimental build only (measured slower on B200); the product library rejects the knob."""
+    o = Oracle(prec)
+    from tests.test_oracle import _cap_workload
+    ws = [W.mixed_hulls(30000, seed=81, dtype=dt), W.mixed_hulls(77, seed=82, dtype=dt), W.tiny_bodies(60, 83, 1.0, dt),
+          _cap_workload(dt, 300, 84)]
+    refs = [o.batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1) for w in ws]
+    try:
+        eng_exp.set_classes([(2048, 2)])  # every pair through the 2-lane class
+        for r1, r2 in ((4, 6), (3, 5), (1, 2), (4, 0), (24, 25), (2, 20)):
+            eng_exp.set_regroup(r1, r2)
+            for w, (dref, sref) in zip(ws, refs):
+                d, s = _gpu(eng_exp, w)
+                _assert_same(f"{w.name}/regroup{r1}:{r2}", d, s, dref, sref, prec)
+    finally:
+        eng_exp.set_regroup(0)
+        eng_exp.set_classes(DEFAULT_CLASSES)
+    with pytest.raises(Exception):
+        eng.set_regroup(4, 6)
+    eng.set_regroup(0)
+
+
 def test_chunked_path_falls_back_on_scattered_layouts(eng):
     """Pools whose polytopes are NOT stored in pair order: the chunked pipeline's device-side layout
     check must send the batch to the one-shot path -- both when whole chunks overlap (caught on the

@@ -45,13 +45,15 @@ def main():
     base = None
     rows = []
     for ent in args.libs.split(","):
-        lib, _, lanes = ent.partition(":")
+        lib, lanes, *rg = ent.split(":") if ":" in ent else (ent, "")  # lib[:table_lanes[:regroup1[:regroup2]]]
         path = _lib.LIB_PATH if lib == "default" else os.path.join(ROOT, "opengjk_b200", lib)
         eng = api.Engine(0, lib_path=path)
         if args.classes:
             eng.set_classes([tuple(int(x) for x in c.split(":")) for c in args.classes.split(",")])
         if lanes:
             eng.set_table_lanes(int(lanes))
+        if rg:
+            eng.set_regroup(int(rg[0]), int(rg[1]) if len(rg) > 1 else 0)
         if args.accel_min >= 0:
             eng.set_accel_min(args.accel_min)
         store = eng.store_create(d_coords, d_off, d_cnt, stream)
