@@ -75,9 +75,17 @@ STRONG = {"boxes100m_f32"}  # ONE batch of the stated size split over the ranks 
 # What limits each kernel, with the figures of the committed ncu capture (profiles/): the
 # HBM fraction is always reported, but only the large-hull kernels are HBM-shaped.
 NCU_NOTES = {
-    "hulls64_f64": {"limiter": "issue slots / FP64 pipe / warp divergence (not HBM-bound)",
-                    "lanes_active": 13.3, "issue_active_pct": 40.7, "pipe_pct": {"fp64": 30.3},
-                    "source": "profiles/r1k_hulls64_f64_ncu_summary.txt"},
+    "hulls64_f64": {"limiter": "scan load latency (long_scoreboard 5.0 cycles per issue) at 16 warps per SM / FP64 pipe / "
+                               "warp divergence: 63 % of a warp's lane-iterations are live, 0.65 of those lanes converge "
+                               "(not HBM-bound)",
+                    "lanes_active": 13.3, "issue_active_pct": 40.6, "pipe_pct": {"fp64": 30.2, "alu": 19.9},
+                    "source": "profiles/r2_hulls64_f64_ncu_summary.txt"},
+    "hulls1k_f32": {"limiter": "instruction issue (3.5 k warp instructions per pair, 61 % issue-active at 32 warps per SM), then "
+                               "the dependent cluster-record fetches (long_scoreboard); DRAM traffic is below the algorithmic bytes",
+                    "lanes_active": 27.5, "issue_active_pct": 60.7, "source": "profiles/r2_hulls1k_f32_ncu_summary.txt"},
+    "hulls1k10k_full_f32": {"limiter": "instruction issue (64 % issue-active at 28 warps per SM); tile and cluster pruning read "
+                                       "a sixth of the algorithmic bytes, hence a roofline fraction above 1",
+                            "issue_active_pct": 63.8, "source": "profiles/r2_hulls1k10k_full_f32_ncu_summary.txt"},
     "boxes100m_f32": {"limiter": "issue slots / warp divergence (not HBM-bound)", "lanes_active": 11.3,
                       "issue_active_pct": 68.0, "pipe_pct": {"alu": 53.0, "fma": 34.0},
                       "source": "profiles/r1d_boxes_f32_ncu_summary.txt"},
