@@ -85,8 +85,17 @@ template <typename T> struct WarpBody {
 // Both support calls of one GJK iteration (openGJK.c:992-993): body 1 along -v,
 // body 2 along +v.  (A fused single-stream scan of both bodies was measured and was
 // slower than two 2-chunk-per-trip scans: less ILP per trip.)
+#ifndef OGJK_SCAN_PREFETCH
+#define OGJK_SCAN_PREFETCH 0  // 1: every block line of both bodies is requested into L1 before the scans (group bodies)
+#endif
+template <typename Body> OGJK_DI auto prefetch_block(const Body& b, int) -> decltype(b.prefetch(), void()) { b.prefetch(); }
+template <typename Body> OGJK_DI void prefetch_block(const Body&, long) {}
 template <typename T, typename Body>
 OGJK_DI void support_both(const Body& b1, const Body& b2, const V3<T>& v, V3<T>& sa, int& ia, V3<T>& sb, int& ib) {
+#if OGJK_SCAN_PREFETCH
+  prefetch_block(b1, 0);
+  prefetch_block(b2, 0);
+#endif
   b1.support(-v.x, -v.y, -v.z, sa, ia);
   b2.support(v.x, v.y, v.z, sb, ib);
 }
@@ -337,6 +346,13 @@ OGJK_DI float group_fmax(unsigned gm, float x) {
 template <typename T, int G> struct GroupBody {
   const T* blk; int n; int np; int g; unsigned mask;
   OGJK_DI V3<T> vertex(int i) const { return V3<T>{blk[i], blk[np + i], blk[2 * np + i]}; }
+  // All 128-byte lines of the block [x | y | z] at once, lane g taking lines g, g+G, ...: the scan below
+  // otherwise meets them one trip after the other, each a full L2 / DRAM round trip.
+  OGJK_DI void prefetch() const {
+    constexpr int kLine = 128 / (int)sizeof(T);
+    const int last = 3 * np - 1;  // blocks are 16-byte, not line aligned: the last line is named by its last element
+    for (int e = g * kLine; e < last + kLine; e += G * kLine) asm volatile("prefetch.global.L1 [%0];" ::"l"(blk + (e < last ? e : last)));
+  }
   OGJK_DI void support(T dx, T dy, T dz, V3<T>& cur, int& cur_i) const {
     const int better = scan(dx, dy, dz, dot3(cur.x, cur.y, cur.z, dx, dy, dz));
     if (better != 0x7fffffff) { cur = vertex(better); cur_i = better; }
