@@ -29,6 +29,7 @@
 #ifdef OGJK_EXPERIMENTAL
 #include "gjk_experimental.cuh"
 #include "regroup_kernel.cuh"
+#include "tma_kernel.cuh"
 #endif
 #include "epa_kernels.cuh"
 #include "broadphase.cuh"
@@ -548,6 +549,24 @@ int launch_staged(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const u
   return OGJK_OK;
 }
 
+// Bulk-copy (TMA) staged flavour, double buffered per warp (tma_kernel.cuh).  The buffer size is a tuning
+// hook ($OGJK_TMA_SLOT bytes per buffer, default 14336: 4 warps x 2 buffers = 112 KB per CTA, 2 CTAs per SM).
+template <typename T, int G>
+int launch_tma(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const unsigned* b, const unsigned* e,
+               unsigned long long* head, cudaStream_t st) {
+  const char* env = getenv("OGJK_TMA_SLOT");
+  int slot = env ? atoi(env) : 14336;
+  slot = (slot < 1024 ? 1024 : slot > 26624 ? 26624 : slot) & ~127;
+  const size_t smem = (size_t)kTmaWarps * 2 * slot;
+  CU(cudaFuncSetAttribute(gjk_tma_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk_tma_kernel<T, G>, 32 * kTmaWarps, smem) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  long long blocks = (a.npairs * G + 32 * kTmaWarps - 1) / (32 * kTmaWarps), cap = (long long)ctx->sm_count * per_sm;
+  gjk_tma_kernel<T, G><<<(unsigned)(blocks < cap ? blocks : cap), 32 * kTmaWarps, smem, st>>>(a, list, b, e, head, slot);
+  return OGJK_OK;
+}
+
 // CTA-per-pair flavour: dynamic shared memory = the class's largest pair.
 template <typename T, int WARPS>
 int launch_cta(ogjk_ctx* ctx, const StoreArgs<T>& a, const int* list, const unsigned* b, const unsigned* e,
@@ -716,6 +735,9 @@ int run_store_batch(ogjk_ctx* ctx, const StoreArgs<T>& a, cudaStream_t st) {
       case 208: launch_persist<T, 8>(ctx, a, sorted, b, e, head, st); break;
       case 216: launch_persist<T, 16>(ctx, a, sorted, b, e, head, st); break;
       case 232: launch_persist<T, 32>(ctx, a, sorted, b, e, head, st); break;
+      case 602: rc = launch_tma<T, 2>(ctx, a, sorted, b, e, head, st); break;
+      case 604: rc = launch_tma<T, 4>(ctx, a, sorted, b, e, head, st); break;
+      case 608: rc = launch_tma<T, 8>(ctx, a, sorted, b, e, head, st); break;
       case 101: rc = launch_staged<T, 1>(ctx, a, sorted, b, e, head, hi, st); break;
       case 102: rc = launch_staged<T, 2>(ctx, a, sorted, b, e, head, hi, st); break;
       case 104: rc = launch_staged<T, 4>(ctx, a, sorted, b, e, head, hi, st); break;
@@ -1744,7 +1766,8 @@ int ogjk_ctx_set_classes(ogjk_ctx* c, int n, const int* hi_keys, const int* lane
   for (int i = 0; i < n; ++i) {
     const int l = lanes[i];
     // plain G or 0; 100 + G: shared-memory staged; 200 + G: persistent lanes (200 = register-resident);
-    // 300 + G: scan-assist (G = 2, 4, 8, 16); 500 + W: CTA-per-pair with W = 2, 4, 8, 16 warps
+    // 300 + G: scan-assist (G = 2, 4, 8, 16); 500 + W: CTA-per-pair with W = 2, 4, 8, 16 warps;
+    // 600 + G: bulk-copy (TMA) staging, double buffered per warp (G = 2, 4, 8)
     const int fam = l / 100, gl = l % 100;
     const bool pow2 = gl == 1 || gl == 2 || gl == 4 || gl == 8 || gl == 16 || gl == 32;
     bool ok = false;
@@ -1753,8 +1776,9 @@ int ogjk_ctx_set_classes(ogjk_ctx* c, int n, const int* hi_keys, const int* lane
     else if (fam == 1) ok = pow2;
     else if (fam == 2) ok = gl == 0 || pow2;
     else if (fam == 3 || fam == 5) ok = gl == 2 || gl == 4 || gl == 8 || gl == 16;
+    else if (fam == 6) ok = gl == 2 || gl == 4 || gl == 8;
 #else
-    else if (l >= 0 && (fam == 1 || fam == 2 || fam == 3 || fam == 5))
+    else if (l >= 0 && (fam == 1 || fam == 2 || fam == 3 || fam == 5 || fam == 6))
       return fail(OGJK_ERR_ARG, "experimental kernel flavour: only libopengjk_b200_exp.so (-DOGJK_EXPERIMENTAL) carries it%s");
 #endif
     if (l < 0 || !ok) return fail(OGJK_ERR_ARG, "unknown kernel flavour in class table%s");

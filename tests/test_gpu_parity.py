@@ -336,6 +336,32 @@ def test_in_cta_regrouping_is_invisible(eng, eng_exp, prec, dt):
     eng.set_regroup(0)
 
 
+@pytest.mark.parametrize("prec,dt", PRECS)
+def test_bulk_copy_staging_is_invisible(eng_exp, prec, dt):
+    """The TMA-staged flavour (tma_kernel.cuh: cp.async.bulk + mbarrier, double buffered per warp) gives the
+    plain group kernel's bytes -- for buffers that hold whole batches, buffers that hold only some of a
+    batch's pairs (the rest is read from global memory) and batches with a ragged tail."""
+    o = Oracle(prec)
+    ws = [W.mixed_hulls(30000, seed=91, dtype=dt), W.mixed_hulls(77, seed=92, dtype=dt), W.tiny_bodies(60, 93, 1.0, dt),
+          W.random_hulls(3000, 40, 300, 94, 3.0, dt)]
+    refs = [o.batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1) for w in ws]
+    saved = os.environ.get("OGJK_TMA_SLOT")
+    try:
+        for slot in ("14336", "2048", "26624"):
+            os.environ["OGJK_TMA_SLOT"] = slot
+            for lanes in (602, 604, 608):
+                eng_exp.set_classes([(2048, lanes)])
+                for w, (dref, sref) in zip(ws, refs):
+                    d, s = _gpu(eng_exp, w)
+                    _assert_same(f"{w.name}/tma{lanes}/slot{slot}", d, s, dref, sref, prec)
+    finally:
+        if saved is None:
+            os.environ.pop("OGJK_TMA_SLOT", None)
+        else:
+            os.environ["OGJK_TMA_SLOT"] = saved
+        eng_exp.set_classes(DEFAULT_CLASSES)
+
+
 def test_chunked_path_falls_back_on_scattered_layouts(eng):
     """Pools whose polytopes are NOT stored in pair order: the chunked pipeline's device-side layout
     check must send the batch to the one-shot path -- both when whole chunks overlap (caught on the
