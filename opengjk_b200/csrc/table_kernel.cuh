@@ -404,7 +404,7 @@ gjk_table3_kernel(const __grid_constant__ StoreArgs<T> a, const int* __restrict_
 #define OGJK_LB_TABLEB_F32 8
 #endif
 #ifndef OGJK_LB_TABLEB_F64
-#define OGJK_LB_TABLEB_F64 3
+#define OGJK_LB_TABLEB_F64 4
 #endif
 #ifndef OGJK_TB_K
 #define OGJK_TB_K 2  // clusters per body per trip of the scan (the warp-per-pair kernel takes 3 with its 128 registers)
