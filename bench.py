@@ -87,10 +87,12 @@ NCU_NOTES = {
                                        "a sixth of the algorithmic bytes, hence a roofline fraction above 1",
                             "issue_active_pct": 63.8, "source": "profiles/r2_hulls1k10k_full_f32_ncu_summary.txt"},
     "boxes100m_f32": {"limiter": "issue slots / warp divergence (not HBM-bound)", "lanes_active": 11.3,
-                      "issue_active_pct": 68.0, "pipe_pct": {"alu": 53.0, "fma": 34.0},
-                      "source": "profiles/r1d_boxes_f32_ncu_summary.txt"},
-    "epa10m_f32": {"limiter": "issue slots / shared-memory latency (not HBM-bound)", "lanes_active": 20.5,
-                   "issue_active_pct": 69.0, "source": "profiles/r1d_epa_f32_ncu_summary.txt"},
+                      "issue_active_pct": 68.1, "pipe_pct": {"alu": 52.5, "fma": 33.7},
+                      "source": "profiles/r2_boxes_f32_ncu_summary.txt (same kernel, 8 M-pair batch)"},
+    "epa10m_f32": {"limiter": "instruction issue (84 % issue-active; LSU pipe 51 %: the polytope lives in shared memory); "
+                              "mean 16.5 expansions per pair (not HBM-bound)", "lanes_active": 21.0,
+                   "issue_active_pct": 84.2, "pipe_pct": {"alu": 57.1, "fma": 24.4, "lsu": 51.2},
+                   "source": "profiles/r2_epa_f32_ncu_summary.txt (same kernel, 1 M-pair batch)"},
 }
 
 
