@@ -338,6 +338,18 @@ OGJK_API int64_t ogjk_multi_launch_count(const ogjk_multi* m);
 OGJK_API void ogjk_multi_shard_bounds(int64_t npairs, int ndev, int i, int64_t* lo, int64_t* hi);
 OGJK_API void ogjk_multi_store_destroy(ogjk_multi_store* store);
 OGJK_API int64_t ogjk_multi_store_bytes(const ogjk_multi_store* store);
+/* The reference's own call shape over every device of the multi context (replaces
+ * compute_minimum_distance / compute_gjk_epa, gpu/include/openGJK_GPU.h:153-159, :198-206): arrays of
+ * gkPolytope structs that point at host vertex arrays; device i computes pairs [lo, hi) of
+ * ogjk_multi_shard_bounds and writes that range of the caller's arrays. */
+OGJK_API int ogjk_multi_compute_minimum_distance_f32(ogjk_multi* m, int n, const ogjk_polytope_f32* bd1,
+        const ogjk_polytope_f32* bd2, ogjk_simplex_f32* simplices, float* distances);
+OGJK_API int ogjk_multi_compute_minimum_distance_f64(ogjk_multi* m, int n, const ogjk_polytope_f64* bd1,
+        const ogjk_polytope_f64* bd2, ogjk_simplex_f64* simplices, double* distances);
+OGJK_API int ogjk_multi_compute_gjk_epa_f32(ogjk_multi* m, int n, const ogjk_polytope_f32* bd1, const ogjk_polytope_f32* bd2,
+        ogjk_simplex_f32* simplices, float* distances, float* witness1, float* witness2);
+OGJK_API int ogjk_multi_compute_gjk_epa_f64(ogjk_multi* m, int n, const ogjk_polytope_f64* bd1, const ogjk_polytope_f64* bd2,
+        ogjk_simplex_f64* simplices, double* distances, double* witness1, double* witness2);
 OGJK_API int ogjk_multi_gjk_host_f32(ogjk_multi* m, int64_t npairs, const float* coords1, const int64_t* off1, const
         int* cnt1, int64_t npoly1, int64_t nverts1, const int* idx1, const float* coords2, const int64_t* off2, const
         int* cnt2, int64_t npoly2, int64_t nverts2, const int* idx2, ogjk_simplex_f32* simplices, float* distances);

@@ -49,6 +49,10 @@ EXPORTS = [
     "ogjk_single_rows_f32", "ogjk_single_rows_f64",
     # several GPUs behind one call (csrc/multi.cuh)
     "ogjk_multi_allgather_f32",
+    "ogjk_multi_compute_gjk_epa_f32",
+    "ogjk_multi_compute_gjk_epa_f64",
+    "ogjk_multi_compute_minimum_distance_f32",
+    "ogjk_multi_compute_minimum_distance_f64",
     "ogjk_multi_allgather_f64",
     "ogjk_multi_create",
     "ogjk_multi_ctx",
@@ -158,6 +162,8 @@ def lib(path=None):
                                                              vp, vp]
         getattr(L, f"ogjk_multi_gjk_epa_host_{sfx}").argtypes = [vp, i64, vp, vp, vp, i64, i64, vp, vp, vp, vp, i64, i64,
                                                                  vp, vp, vp, vp, vp, vp]
+        getattr(L, f"ogjk_multi_compute_minimum_distance_{sfx}").argtypes = [vp, i32, vp, vp, vp, vp]
+        getattr(L, f"ogjk_multi_compute_gjk_epa_{sfx}").argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
         getattr(L, f"ogjk_multi_store_create_{sfx}").argtypes = [vp, i64, i64, vp, vp, vp, i32, C.POINTER(vp)]
         getattr(L, f"ogjk_multi_store_gjk_{sfx}").argtypes = [vp, vp, vp, vp, vp, i64, vp, vp]
         getattr(L, f"ogjk_multi_store_gjk_epa_{sfx}").argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]

@@ -314,6 +314,24 @@ class MultiEngine:
     def bounds(self, npairs, i):
         return shard_bounds(npairs, self.ndev, i)
 
+    def compute_minimum_distance_structs(self, bodies1, bodies2, dtype=np.float32, epa=False):
+        """The reference's call shape (arrays of gkPolytope pointing at host vertex arrays) over every device:
+        ogjk_multi_compute_minimum_distance_* / ogjk_multi_compute_gjk_epa_*."""
+        prec, sdt = _PREC[np.dtype(dtype)]
+        a1, _k1 = _struct_array(bodies1, dtype)
+        a2, _k2 = _struct_array(bodies2, dtype)
+        n = len(bodies1)
+        simp = np.zeros(n, dtype=sdt)
+        dist = np.zeros(n, dtype=dtype)
+        if not epa:
+            fn = getattr(self._L, f"ogjk_multi_compute_minimum_distance_{prec}")
+            self._ck(fn(self._h, n, C.cast(a1, C.c_void_p), C.cast(a2, C.c_void_p), _p(simp), _p(dist)))
+            return dist, simp
+        w1, w2 = np.zeros((n, 3), dtype=dtype), np.zeros((n, 3), dtype=dtype)
+        fn = getattr(self._L, f"ogjk_multi_compute_gjk_epa_{prec}")
+        self._ck(fn(self._h, n, C.cast(a1, C.c_void_p), C.cast(a2, C.c_void_p), _p(simp), _p(dist), _p(w1), _p(w2)))
+        return {"distances": dist, "simplices": simp, "witness1": w1, "witness2": w2}
+
     def gjk_host(self, coords, off, cnt, pa, pb, want_simplices=True, out=None):
         """Indexed form over one shared host pool (replicated on every device)."""
         coords = np.ascontiguousarray(coords)

@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -50,6 +51,36 @@ static ogjk_ctx* ctx() {
   return g_ctx;
 }
 
+// $OPENGJK_B200_DEVICES = "all" or a comma list of device ordinals: the two whole-batch entry points
+// (compute_minimum_distance, compute_gjk_epa) spread every call over those GPUs (ogjk_multi_*: contiguous
+// pair slice per device, results written straight into the caller's arrays).  Unset: the current device.
+static ogjk_multi* g_multi = nullptr;
+static std::once_flag g_multi_once;
+static ogjk_multi* multi() {
+  std::call_once(g_multi_once, [] {
+    const char* env = getenv("OPENGJK_B200_DEVICES");
+    if (!env || !*env) return;
+    std::vector<int> devs;
+    if (strcmp(env, "all") != 0)
+      for (const char* p = env; *p;) {
+        char* end = nullptr;
+        const long d = strtol(p, &end, 10);
+        if (end == p) break;
+        devs.push_back((int)d);
+        p = *end == ',' ? end + 1 : end;
+      }
+    if (strcmp(env, "all") != 0 && devs.empty()) {
+      fprintf(stderr, "openGJK_GPU (opengjk_b200): OPENGJK_B200_DEVICES=%s is neither \"all\" nor a list of ordinals; using one device\n", env);
+      return;
+    }
+    if (ogjk_multi_create(devs.empty() ? nullptr : devs.data(), (int)devs.size(), &g_multi) != OGJK_OK) {
+      g_multi = nullptr;
+      fprintf(stderr, "openGJK_GPU (opengjk_b200): OPENGJK_B200_DEVICES=%s: %s; using one device\n", env, ogjk_last_error());
+    }
+  });
+  return g_multi;
+}
+
 // The reference API returns void: a failure is reported on stderr (as the reference prints its
 // CUDA errors) and the outputs are filled with NaN so that it cannot pass for a result.
 static void report(int rc, const char* what, int n, gkFloat* distances) {
@@ -68,6 +99,10 @@ EXPORT void compute_minimum_distance(const int n, const gkPolytope* bd1, const g
                                      gkFloat* distances) {
   if (n <= 0) return;
   std::lock_guard<std::mutex> lk(g_lock);
+  if (ogjk_multi* m = multi()) {
+    report(F(ogjk_multi_compute_minimum_distance)(m, n, bd1, bd2, simplices, distances), "compute_minimum_distance", n, distances);
+    return;
+  }
   ogjk_ctx* c = ctx();
   report(c ? F(ogjk_compute_minimum_distance)(c, n, bd1, bd2, simplices, distances) : OGJK_ERR_CUDA,
          "compute_minimum_distance", n, distances);
@@ -86,6 +121,10 @@ EXPORT void compute_gjk_epa(const int n, const gkPolytope* bd1, const gkPolytope
                             gkFloat* distances, gkFloat* witness1, gkFloat* witness2) {
   if (n <= 0) return;
   std::lock_guard<std::mutex> lk(g_lock);
+  if (ogjk_multi* m = multi()) {
+    report(F(ogjk_multi_compute_gjk_epa)(m, n, bd1, bd2, simplices, distances, witness1, witness2), "compute_gjk_epa", n, distances);
+    return;
+  }
   ogjk_ctx* c = ctx();
   report(c ? F(ogjk_compute_gjk_epa)(c, n, bd1, bd2, simplices, distances, witness1, witness2) : OGJK_ERR_CUDA,
          "compute_gjk_epa", n, distances);

@@ -433,6 +433,27 @@ int multi_allgather(ogjk_multi_* m) {
 
 }  // namespace
 
+// The reference's call shape (arrays of gkPolytope structs with host vertex arrays) over all devices: a
+// struct array is per pair, so device i simply gets [lo, hi) of every argument and gathers its own slice
+// with its context's host threads.
+template <typename T, typename P, typename S>
+int multi_structs(ogjk_multi_* m, int n, const P* bd1, const P* bd2, S* simplices, T* distances, T* w1, T* w2, T* normals,
+                  bool epa) {
+  if (!m) return fail(OGJK_ERR_ARG, "multi context is NULL%s");
+  if (n <= 0) return OGJK_OK;  // reference: silent return (gpu/opengjk_gpu.cu:2984)
+  if (!bd1 || !bd2 || !distances || (epa && (!simplices || !w1 || !w2))) return fail(OGJK_ERR_ARG, "NULL argument%s");
+  return multi_run(m, [&](int i) -> int {
+    int64_t lo, hi;
+    shard_bounds(n, m->ndev, i, &lo, &hi);
+    const int k = (int)(hi - lo);
+    if (k <= 0) return OGJK_OK;
+    S* so = simplices ? simplices + lo : nullptr;
+    if (!epa) return compute_min_dist<T, P, S>(m->w[i]->ctx, k, bd1 + lo, bd2 + lo, so, distances + lo);
+    return compute_epa_structs<T, P, S>(m->w[i]->ctx, k, bd1 + lo, bd2 + lo, so, distances + lo, w1 + 3 * lo, w2 + 3 * lo,
+                                        normals ? normals + 3 * lo : nullptr, true);
+  });
+}
+
 extern "C" {
 
 void ogjk_multi_shard_bounds(int64_t npairs, int ndev, int i, int64_t* lo, int64_t* hi) {
@@ -519,6 +540,17 @@ int64_t ogjk_multi_launch_count(const ogjk_multi* m) {
     if (!witness1 || !witness2) return fail(OGJK_ERR_ARG, "EPA needs witness output arrays%s");                          \
     return multi_host<T, S>(m, npairs, coords1, off1, cnt1, npoly1, nverts1, idx1, coords2, off2, cnt2, npoly2, nverts2,   \
                             idx2, simplices, distances, witness1, witness2, normals, true);                               \
+  }                                                                                                                      \
+  int ogjk_multi_compute_minimum_distance_##SFX(ogjk_multi* m, int n, const ogjk_polytope_##SFX* bd1,                     \
+                                                const ogjk_polytope_##SFX* bd2, S* simplices, T* distances) {            \
+    return multi_structs<T, ogjk_polytope_##SFX, S>(m, n, bd1, bd2, simplices, distances, nullptr, nullptr, nullptr,      \
+                                                    false);                                                              \
+  }                                                                                                                      \
+  int ogjk_multi_compute_gjk_epa_##SFX(ogjk_multi* m, int n, const ogjk_polytope_##SFX* bd1,                              \
+                                       const ogjk_polytope_##SFX* bd2, S* simplices, T* distances, T* witness1,          \
+                                       T* witness2) {                                                                    \
+    return multi_structs<T, ogjk_polytope_##SFX, S>(m, n, bd1, bd2, simplices, distances, witness1, witness2, nullptr,    \
+                                                    true);                                                               \
   }                                                                                                                      \
   int ogjk_multi_store_create_##SFX(ogjk_multi* m, int64_t npoly, int64_t nverts, const T* coords, const int64_t* off,     \
                                     const int* cnt, int via_nccl, ogjk_multi_store** out) {                               \

@@ -142,3 +142,46 @@ print("CONCURRENT_OK")
 ''' % (ROOT, LIBS["f32"])
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert "CONCURRENT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+def test_devices_environment_switch_spreads_the_drop_in_call():
+    """OPENGJK_B200_DEVICES=all: the flavour library's compute_minimum_distance / compute_gjk_epa run on every
+    GPU of the box (ogjk_multi_*) and still return the oracle's bytes; a bad value falls back to one device."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, os, sys
+import numpy as np
+sys.path.insert(0, %r)
+from opengjk_b200 import workloads as W
+from oracle.pyoracle import Oracle, polytope_dtype, simplex_dtype
+lib = C.CDLL(%r)
+prec, dt = "f32", np.float32
+p = lambda a: a.ctypes.data_as(C.c_void_p)
+def body(w, which):
+    arr = np.zeros(which.shape[0], dtype=polytope_dtype(prec))
+    arr["numpoints"] = w.cnt[which]
+    arr["coord"] = w.coords.ctypes.data + w.off[which].astype(np.uint64) * np.uint64(3 * w.coords.itemsize)
+    return arr
+w = W.mixed_hulls(30001, seed=301, dtype=dt)
+dref, sref = Oracle(prec).batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1)
+b1, b2 = body(w, w.pa), body(w, w.pb)
+simp = np.zeros(w.npairs, dtype=simplex_dtype(prec)); dist = np.zeros(w.npairs, dtype=dt)
+lib.compute_minimum_distance(C.c_int(w.npairs), p(b1), p(b2), p(simp), p(dist))
+assert dist.tobytes() == dref.tobytes()
+assert np.ascontiguousarray(simp["vrtx_idx"]).tobytes() == np.ascontiguousarray(sref["vrtx_idx"]).tobytes()
+we = W.random_hulls(4001, 8, 64, 302, 1.0, dt, 0.5)
+eref = Oracle(prec).gjk_epa_batch(we.coords, we.off, we.cnt, we.pa, we.pb, nthreads=os.cpu_count() or 1)
+b1, b2 = body(we, we.pa), body(we, we.pb)
+simp = np.zeros(we.npairs, dtype=simplex_dtype(prec)); dist = np.zeros(we.npairs, dtype=dt)
+w1 = np.zeros((we.npairs, 3), dtype=dt); w2 = np.zeros((we.npairs, 3), dtype=dt)
+lib.compute_gjk_epa(C.c_int(we.npairs), p(b1), p(b2), p(simp), p(dist), p(w1), p(w2))
+assert dist.tobytes() == eref["distances"].tobytes()
+assert w1.tobytes() == np.ascontiguousarray(eref["witness1"]).tobytes()
+print("DEVICES_OK")
+''' % (ROOT, LIBS["f32"])
+    for value in ("all", "0", "not-a-device-list"):
+        env = dict(os.environ, OPENGJK_B200_DEVICES=value)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+        assert "DEVICES_OK" in r.stdout, value + ": " + r.stdout[-2000:] + r.stderr[-3000:]

@@ -128,6 +128,31 @@ def test_multi_epa_and_replicated_stores(prec, dt):
             m.close()
 
 
+@pytest.mark.parametrize("prec,dt", PRECS)
+def test_multi_struct_array_entries(prec, dt):
+    """The reference's call shape (arrays of gkPolytope pointing at host vertex arrays) over several devices:
+    ogjk_multi_compute_minimum_distance_* / ogjk_multi_compute_gjk_epa_* equal the oracle byte for byte,
+    with a batch large enough for the pipelined gather and one smaller than the device count."""
+    o = Oracle(prec)
+    w = W.mixed_hulls(40003, seed=97, dtype=dt)
+    dref, sref = o.batch(w.coords, w.off, w.cnt, w.pa, w.pb, nthreads=os.cpu_count() or 1)
+    we = W.random_hulls(5001, 8, 64, 98, 1.0, dt, 0.5)
+    eref = o.gjk_epa_batch(we.coords, we.off, we.cnt, we.pa, we.pb, nthreads=os.cpu_count() or 1)
+    bodies = lambda w, which: [w.coords[w.off[h]:w.off[h] + w.cnt[h]] for h in which]
+    for devs in _devsets():
+        m = api.MultiEngine(devs)
+        try:
+            d, s = m.compute_minimum_distance_structs(bodies(w, w.pa), bodies(w, w.pb), dt)
+            _same(f"structs{devs}", d, s, dref, sref)
+            d, s = m.compute_minimum_distance_structs(bodies(w, w.pa[:1]), bodies(w, w.pb[:1]), dt)
+            _same(f"structs-one{devs}", d, s, dref[:1], sref[:1])
+            got = m.compute_minimum_distance_structs(bodies(we, we.pa), bodies(we, we.pb), dt, epa=True)
+            for k in ("distances", "witness1", "witness2"):
+                assert np.ascontiguousarray(got[k]).tobytes() == np.ascontiguousarray(eref[k]).tobytes(), (devs, k)
+        finally:
+            m.close()
+
+
 def test_resident_results_and_device_side_gather():
     """Results left on the devices: each device's slice equals the oracle's; after the NCCL
     gather every device holds the whole batch (skips the gather with a single GPU)."""
