@@ -232,6 +232,7 @@ struct ogjk_ctx_ {
   DevBuf d_coords1, d_coords2, d_off1, d_off2, d_cnt1, d_cnt2, d_idx1, d_idx2, d_simp, d_dist;
   PinBuf h_stage;
   HostPool* pool = nullptr;  // host threads for the struct-array gathers (lazy)
+  int host_threads = 0;      // size of that pool; 0 = one per hardware thread (at most 32); a multi context shares them out
 };
 
 namespace {
@@ -1225,7 +1226,7 @@ int gjk_host(ogjk_ctx* ctx, int64_t npairs, const T* coords1, const int64_t* off
 
 HostPool* host_pool(ogjk_ctx* ctx) {
   if (!ctx->pool) {
-    unsigned nt = std::thread::hardware_concurrency();
+    unsigned nt = ctx->host_threads > 0 ? (unsigned)ctx->host_threads : std::thread::hardware_concurrency();
     nt = nt > 32 ? 32 : (nt < 2 ? 2 : nt);
     ctx->pool = new (std::nothrow) HostPool((int)nt);
   }

@@ -511,6 +511,9 @@ int ogjk_multi_create(const int* devices, int ndev, ogjk_multi** out) {
     w->device = dev;
     const int rc = ogjk_ctx_create(dev, &w->ctx);
     if (rc) { ogjk_multi_destroy(m); return rc; }
+    // the devices' gather / copy threads run at the same time: share the host's hardware threads out
+    const unsigned hc = std::thread::hardware_concurrency();
+    w->ctx->host_threads = (int)((hc ? hc : 16u) / (unsigned)ndev < 4u ? 4u : (hc ? hc : 16u) / (unsigned)ndev);
     w->th = std::thread(multi_worker_main, w);
   }
   *out = m;
