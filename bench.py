@@ -292,12 +292,36 @@ def cpu_baseline(w, prec, budget_s=10.0, epa=False, sample_note=None):
         else:
             run1 = lambda: o.batch(w1.coords, w1.off, w1.cnt, w1.pa, w1.pb, nthreads=1)
         v_one, reps1, dt1 = _timed_passes(run1, w1.npairs, max(1.0, budget_s / 4))
-    return {"value": v_all, "unit": "pairs/s", "cores": cores, "kind": kind,
+    ref_cuda = reference_cuda_baseline(ws, epa)
+    return {"value": v_all, "unit": "pairs/s", "cores": cores, "kind": kind, "reference_cuda_kernels": ref_cuda,
             "sample": f"{note} x {reps} passes ({dt:.1f} s), OpenMP split over pairs"
                       + (" (GJK + EPA restatement: the reference has no CPU EPA)" if epa else ""),
             "single_thread": {"value": v_one, "unit": "pairs/s", "cores": 1,
                               "sample": f"{w1.npairs} pairs (every 8th of the sample) x {reps1} passes ({dt1:.1f} s)"},
             "simd_baseline": "unavailable (Google Highway is not present offline; simd/CMakeLists.txt:58-75 fetches it)"}
+
+
+def reference_cuda_baseline(ws, epa):
+    """The reference's own CUDA kernels (gpu/opengjk_gpu.cu built unmodified into oracle/_ref), kernel-only through its
+    mid-level API, on this GPU and on a bounded sample of the same pairs: its allocate_and_copy_device_arrays copies
+    every pair's two bodies separately, so the sample is cut to <= 256 MB of vertices.  Runs in a child process."""
+    import subprocess
+    import tempfile
+    per_pair = float(ws.cnt[ws.pa].astype(np.int64).sum() + ws.cnt[ws.pb].astype(np.int64).sum()) / ws.npairs * 3 * ws.coords.itemsize
+    m = int(max(1000, min(ws.npairs, 256e6 / max(per_pair, 1.0))))
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            f = os.path.join(td, "sample.npz")
+            np.savez(f, coords=ws.coords, off=ws.off, cnt=ws.cnt, pa=ws.pa[:m], pb=ws.pb[:m])
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_gpu_baseline.py"), "--npz", f] + (["epa"] if epa else []),
+                               capture_output=True, text=True, timeout=300)
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:  # a crash of the reference library is a property of the reference, not of this run
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:120]}"}
+    if "ms" not in out:
+        return out
+    return {"value": out["pairs"] / out["ms"] * 1e3, "unit": "pairs/s", "sample": f"the first {out['pairs']} pairs of the CPU sample",
+            "kind": "reference CUDA kernels, unmodified, kernel-only (device arrays built once), same GPU"}
 
 
 def config_of(name, n_total, world):

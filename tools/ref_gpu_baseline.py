@@ -8,10 +8,28 @@ import os
 import sys
 
 import numpy as np
-import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+if len(sys.argv) >= 3 and sys.argv[1] == "--npz":
+    # bench.py's baseline leg: time ONLY the reference's kernels on the arrays of an .npz file, in this process
+    # (a fault inside the reference library must not take the bench down).  argv: --npz file [epa]
+    from oracle.pyoracle import ReferenceGPU
+    z = np.load(sys.argv[2])
+    epa = len(sys.argv) > 3 and sys.argv[3] == "epa"
+    prec = "f64" if z["coords"].dtype == np.float64 else "f32"
+    if not ReferenceGPU.available(prec):
+        print(json.dumps({"unavailable": "oracle/_ref reference CUDA library not shipped"}))
+        sys.exit(0)
+    fd = os.dup(1)
+    os.dup2(2, 1)  # the reference prints diagnostics on stdout
+    t = ReferenceGPU(prec).time_kernels(z["coords"], z["off"], z["cnt"], z["pa"], z["pb"], reps=3, epa=epa)
+    os.dup2(fd, 1)
+    print(json.dumps({"ms": t["gjk_epa_ms"] if epa else t["gjk_ms"], "pairs": int(z["pa"].shape[0])}), flush=True)
+    sys.exit(0)
+
+import torch
+
 from opengjk_b200 import api, workloads as W  # noqa: E402
 from oracle.pyoracle import ReferenceGPU  # noqa: E402
 
