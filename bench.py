@@ -75,10 +75,10 @@ STRONG = {"boxes100m_f32"}  # ONE batch of the stated size split over the ranks 
 # What limits each kernel, with the figures of the committed ncu capture (profiles/): the
 # HBM fraction is always reported, but only the large-hull kernels are HBM-shaped.
 NCU_NOTES = {
-    "hulls64_f64": {"limiter": "scan load latency (long_scoreboard 5.0 cycles per issue) at 16 warps per SM / FP64 pipe / "
+    "hulls64_f64": {"limiter": "scan load latency (long_scoreboard 4.7 cycles per issue) at 16 warps per SM / FP64 pipe / "
                                "warp divergence: 63 % of a warp's lane-iterations are live, 0.65 of those lanes converge "
                                "(not HBM-bound)",
-                    "lanes_active": 13.3, "issue_active_pct": 40.6, "pipe_pct": {"fp64": 30.2, "alu": 19.9},
+                    "lanes_active": 13.1, "issue_active_pct": 42.8, "pipe_pct": {"fp64": 31.6, "alu": 23.3},
                     "source": "profiles/r2_hulls64_f64_ncu_summary.txt"},
     "hulls1k_f32": {"limiter": "instruction issue (3.5 k warp instructions per pair, 61 % issue-active at 32 warps per SM), then "
                                "the dependent cluster-record fetches (long_scoreboard); DRAM traffic is below the algorithmic bytes",

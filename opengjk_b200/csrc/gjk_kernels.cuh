@@ -343,7 +343,20 @@ OGJK_DI float group_fmax(unsigned gm, float x) {
 // the group reduces with a (value, lowest index) butterfly.  Every lane of the
 // group ends with the same support point, so the rest of the GJK iteration runs
 // convergently inside the group and nothing has to be broadcast.
-template <typename T, int G> struct GroupBody {
+// WIDE (fp64 blocks in GLOBAL memory only): the scan reads 32-byte chunks (4 vertices) with 256-bit loads
+// (ld.global.v4.f64 -> LDG.E.256 on sm_100a) instead of pairs of 16-byte chunks -- half the load instructions
+// and half the L1TEX requests for the same bytes; with 16 pairs per warp every request touches 16 lines, and
+// the L1TEX tag stage was 56 % busy on config 2.  Store blocks are 32-byte aligned in fp64 (np is a multiple of
+// 4 doubles).  Which lane sees which vertex changes, the result does not (see scan()).
+#ifndef OGJK_WIDE_F64
+#define OGJK_WIDE_F64 1
+#endif
+OGJK_DI void load_wide(const double* p, double (&v)[4]) {
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+OGJK_DI void load_wide(const float*, float (&)[4]) {}  // never called (WIDE is fp64 only)
+
+template <typename T, int G, bool WIDE = false> struct GroupBody {
   const T* blk; int n; int np; int g; unsigned mask;
   OGJK_DI V3<T> vertex(int i) const { return V3<T>{blk[i], blk[np + i], blk[2 * np + i]}; }
   // All 128-byte lines of the block [x | y | z] at once, lane g taking lines g, g+G, ...: the scan below
@@ -370,6 +383,22 @@ template <typename T, int G> struct GroupBody {
     // Two chunks per trip.  The common case -- nothing in the chunk pair beats the
     // running best -- costs one max-tree and one compare; the exact "strictly
     // greater, ascending index" update runs only when the max says it must.
+    if constexpr (WIDE && sizeof(T) == 8) {
+      // one 32-byte chunk (4 consecutive vertices) per trip and lane; np is a multiple of 4: no remainder
+      for (int w = g; 4 * w < np; w += G) {
+        T X[4], Y[4], Z[4], sc[4];
+        load_wide(xp + 4 * w, X); load_wide(yp + 4 * w, Y); load_wide(zp + 4 * w, Z);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) sc[t] = dot3(X[t], Y[t], Z[t], dx, dy, dz);
+        const T m = fmax(fmax(sc[0], sc[1]), fmax(sc[2], sc[3]));
+        if (m > best) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (sc[t] > best) { best = sc[t]; better = 4 * w + t; }
+        }
+      }
+      return group_argmax(mask, best, better);
+    }
     int c = g;
     for (; c + G < nchunks; c += 2 * G) {
       Chunk<T> X0, Y0, Z0, X1, Y1, Z1;
@@ -700,8 +729,9 @@ gjk_group_kernel(StoreArgs<T> a, const int* __restrict__ list, const unsigned* _
       const long long h1 = a.idx1 ? (long long)a.idx1[p] : p;
       const long long h2 = a.idx2 ? (long long)a.idx2[p] : p;
       const int n1 = a.s1.cnt[h1], n2 = a.s2.cnt[h2];
-      GroupBody<T, G> b1{a.s1.data + a.s1.boff[h1], n1, pad4(n1), g, mask};
-      GroupBody<T, G> b2{a.s2.data + a.s2.boff[h2], n2, pad4(n2), g, mask};
+      constexpr bool kWide = OGJK_WIDE_F64 && sizeof(T) == 8;
+      GroupBody<T, G, kWide> b1{a.s1.data + a.s1.boff[h1], n1, pad4(n1), g, mask};
+      GroupBody<T, G, kWide> b2{a.s2.data + a.s2.boff[h2], n2, pad4(n2), g, mask};
       Splx<T> s;
       V3<T> w1, w2;
       const T d = gjk_query<T>(b1, b2, s, w1, w2);
